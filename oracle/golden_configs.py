@@ -1,0 +1,34 @@
+"""TEST INFRASTRUCTURE ONLY.  The parity configurations shared by make_golden.py and tests/.
+
+Each entry fully determines weights (seed + flavour), inputs (seed) and the pruning schedule,
+so that a golden file generated from the real reference in the build container can be
+re-derived input-for-input on the GPU box.
+"""
+
+GOLDEN_CONFIGS = {
+    # BASELINE.json configs[0]: AST ViT-B/16, SPC-2 shape 128x128 (64 patches), keep 0.7 @ blocks 3/6/9, B=8
+    "ast_spc2_b8_kr07": dict(variant="ast", T=128, B=8, num_classes=35, drop_loc=(3, 6, 9),
+                             base_keep_rate=0.7, keep_rate_list=None, flavour="refinit", wseed=0, xseed=1234),
+    "ast_spc2_b8_kr07_pert": dict(variant="ast", T=128, B=8, num_classes=35, drop_loc=(3, 6, 9),
+                                  base_keep_rate=0.7, keep_rate_list=None, flavour="perturbed", wseed=1, xseed=99),
+    # BASELINE.json configs[1] shape (AudioMAE 1024x128, 512 patches, keep 0.7), small batch for the CPU
+    "audiomae_1024_b2_kr07": dict(variant="audiomae", T=1024, B=2, num_classes=527, drop_loc=(3, 6, 9),
+                                  base_keep_rate=0.7, keep_rate_list=None, flavour="refinit", wseed=0, xseed=1234),
+    "audiomae_1024_b2_kr07_pert": dict(variant="audiomae", T=1024, B=2, num_classes=527, drop_loc=(3, 6, 9),
+                                       base_keep_rate=0.7, keep_rate_list=None, flavour="perturbed", wseed=2,
+                                       xseed=7),
+    # BASELINE.json configs[2]: AST 1024x128 keep-rate sweep end points
+    "ast_1024_b2_kr05": dict(variant="ast", T=1024, B=2, num_classes=527, drop_loc=(3, 6, 9),
+                             base_keep_rate=0.5, keep_rate_list=None, flavour="refinit", wseed=0, xseed=1234),
+    "ast_1024_b2_kr09_pert": dict(variant="ast", T=1024, B=2, num_classes=527, drop_loc=(3, 6, 9),
+                                  base_keep_rate=0.9, keep_rate_list=None, flavour="perturbed", wseed=3, xseed=5),
+    # explicit keep_rate_list overriding the block defaults (engine_finetune.py:96-104 call form),
+    # ragged schedule incl. pruning in the first and last block, short clip
+    "audiomae_256_b3_list": dict(variant="audiomae", T=256, B=3, num_classes=50, drop_loc=(3, 6, 9),
+                                 base_keep_rate=0.7,
+                                 keep_rate_list=(0.9, 1.0, 0.61, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0, 1.0, 1.0, 0.8),
+                                 flavour="perturbed", wseed=4, xseed=11),
+    # unpruned (keep 1.0 everywhere): the unpruned baseline arm of configs[2]/[4]
+    "ast_spc2_b4_unpruned": dict(variant="ast", T=128, B=4, num_classes=35, drop_loc=(),
+                                 base_keep_rate=1.0, keep_rate_list=None, flavour="perturbed", wseed=5, xseed=3),
+}

@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY.  Generate tests/golden/*.pt from the REAL reference.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden
+
+For every entry of ``golden_configs.GOLDEN_CONFIGS`` it loads the deterministic state-dict
+into the unmodified reference model (oracle/ref_loader.py), runs the reference forward in
+extract mode (fp32, eval, no_grad) and stores
+
+    ref      logits + 'block-i.attn_score' (12 blocks) + 'block-i.topk_idx' from the reference
+    ref_plain  logits from the non-extract call ``model(x)``
+    f64      the same quantities from the oracle restatement in float64 (tie ranking / "exact")
+    meta     the config, torch version and the sha256 digest of the state-dict and the input
+
+The reference has no tests or golden vectors of its own, so these files
+are the parity pin.
+"""
+import hashlib
+import os
+import sys
+
+import torch
+
+from . import ref_loader, weights, vit_oracle as vo
+from .golden_configs import GOLDEN_CONFIGS
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def make_inputs(cfg):
+    if cfg["variant"] == "audiomae":
+        sd = weights.make_audiomae_state_dict(cfg["num_classes"], cfg["T"], cfg["wseed"], cfg["flavour"])
+    else:
+        sd = weights.make_ast_state_dict(cfg["num_classes"], cfg["T"], cfg["wseed"], cfg["flavour"])
+    x = weights.make_spectrogram(cfg["variant"], cfg["B"], cfg["T"], cfg["xseed"])
+    return sd, x
+
+
+def build_reference(cfg):
+    if cfg["variant"] == "audiomae":
+        return ref_loader.build_audiomae(cfg["num_classes"], cfg["T"], cfg["drop_loc"], cfg["base_keep_rate"])
+    return ref_loader.build_ast(cfg["num_classes"], cfg["T"], cfg["drop_loc"], cfg["base_keep_rate"])
+
+
+def main(names=None):
+    assert ref_loader.reference_available(), "run in the build container (needs /root/reference)"
+    os.makedirs(OUT_DIR, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for name, cfg in GOLDEN_CONFIGS.items():
+        if names and name not in names:
+            continue
+        sd, x = make_inputs(cfg)
+        model = build_reference(cfg)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+        krl = cfg["keep_rate_list"]
+        with torch.no_grad():
+            logits, feats = model(x, keep_rate_list=krl, flag_extract_features=True)
+            logits_plain = model(x, keep_rate_list=krl)
+            o_logits, o_feats = vo.forward(cfg["variant"], sd, x, krl, cfg["drop_loc"], cfg["base_keep_rate"],
+                                           flag_extract_features=True)
+            d_logits, d_feats = vo.forward(cfg["variant"], sd, x, krl, cfg["drop_loc"], cfg["base_keep_rate"],
+                                           flag_extract_features=True, dtype=torch.float64)
+        feats = {k: v for k, v in feats.items() if k != "mel"}
+        # the restatement must be bit-identical to the reference before anything is written
+        assert torch.equal(logits, o_logits) and torch.equal(logits, logits_plain), name
+        assert sorted(feats) == sorted(o_feats), name
+        for k in feats:
+            assert torch.equal(feats[k], o_feats[k]), (name, k)
+        blob = {
+            "meta": dict(cfg, name=name, torch=torch.__version__,
+                         sd_digest=weights.state_dict_digest(sd),
+                         x_digest=hashlib.sha256(x.numpy().tobytes()).hexdigest()),
+            "ref": {"logits": logits, **feats},
+            "ref_plain": {"logits": logits_plain},
+            "f64": {"logits": d_logits, **d_feats},
+        }
+        path = os.path.join(OUT_DIR, name + ".pt")
+        torch.save(blob, path)
+        print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), logits {tuple(logits.shape)}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
