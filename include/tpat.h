@@ -1,0 +1,201 @@
+/*
+ * tpat.h -- C-ABI of libtpat.so: the B200 (sm_100a) kernels behind the token-pruned ViT-B/16
+ * forward of andylee-24/token-pruning-audio-transformer.
+ *
+ * The reference has no native layer and no FFI (it is 100 % PyTorch); its "plugin
+ * interface" for this path is the Python model API (audiomae/models_vit.py:502-527,
+ * ast/src/models/ast_models.py:424-508).  The Python mirror of that API lives in
+ * token-pruning-audio-transformer_b200/tpat/ and reaches the GPU only through the entry points
+ * below.  Each entry point cites the reference code whose ATen/cuBLAS/cuDNN call sequence it
+ * replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; tpat_last_error() then holds a
+ *     thread-local message.  Nothing throws or aborts across the boundary.
+ *   - all pointers are DEVICE pointers unless named host_*; the library never allocates or frees
+ *     memory the caller sees.  `stream` is a cudaStream_t (torch.cuda.current_stream().cuda_stream).
+ *   - tokens are rows of a dense row-major [B * N, D] matrix; all clips of a batch share N.
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU the compute calls fail.
+ */
+#ifndef TPAT_H
+#define TPAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPAT_VERSION 1
+#define TPAT_MAX_DEPTH 32
+
+typedef void* tpat_stream_t; /* cudaStream_t */
+
+/* element types */
+enum { TPAT_F32 = 0, TPAT_BF16 = 1 };
+/* GEMM epilogues */
+enum {
+  TPAT_EPI_BIAS = 0,          /* C = A W^T + b                               */
+  TPAT_EPI_BIAS_GELU = 1,     /* C = gelu_erf(A W^T + b)                     */
+  TPAT_EPI_BIAS_RESIDUAL = 2, /* C = R + A W^T + b   (C may alias R)         */
+  TPAT_EPI_BIAS_POS = 3       /* patch-embed: C[b, extra+p] = A W^T + b + pos[extra+p] */
+};
+/* GEMM / attention implementation */
+enum {
+  TPAT_IMPL_SIMT = 0, /* fp32-FMA CUDA-core kernels: the fp32 parity ("fp32-scoring") mode     */
+  TPAT_IMPL_TC = 1    /* tcgen05 / TMEM / TMA kernels, bf16 operands, fp32 accumulate          */
+};
+/* importance-score flavour */
+enum {
+  TPAT_SCORE_NONE = 0,
+  TPAT_SCORE_CLS_ROW = 1, /* AST:      mean_h P[h, 0, j],      j >= extra  (ast_models.py:124) */
+  TPAT_SCORE_COLMEAN = 2  /* AudioMAE: mean_{h, i>=extra} P[h, i, j], j >= extra (models_vit.py:113) */
+};
+/* spectrogram -> token order */
+enum {
+  TPAT_TOKENS_TIME_MAJOR = 0, /* AudioMAE: token = t_blk * (F/16) + f_blk, kernel index [t_off][f_off] */
+  TPAT_TOKENS_FREQ_MAJOR = 1  /* AST:      token = f_blk * (T/16) + t_blk, kernel index [f_off][t_off] */
+};
+/* model family for tpat_forward */
+enum { TPAT_VARIANT_AUDIOMAE = 0, TPAT_VARIANT_AST = 1 };
+
+int tpat_version(void);
+const char* tpat_last_error(void);
+/* 1 when the current device is compute capability 10.x, 0 otherwise (no error is set) */
+int tpat_device_ok(void);
+
+/*
+ * Patch extraction (im2col of the 16x16 / stride-16 conv) + extra-token rows.
+ * Replaces: PatchEmbed.forward's unfold (models_vit.py:241-247, ast_models.py:36-42) and the
+ * cls / dist row assembly (models_vit.py:359-362, ast_models.py:463-466).
+ *   spec      [B, T, F] fp32 row-major (AudioMAE [B,1,T,F] and AST [B,T,F] share this layout)
+ *   patches   [B * P, 256] (out_dtype), P = (T/16)*(F/16), row order / column order per `order`
+ *   tokens    [B, extra + P, D] fp32: rows 0..extra-1 of every clip are written with
+ *             extra_tok[e] + pos[e]  (extra_tok = cls (and dist), [extra, D] fp32; pos [extra+P, D])
+ */
+int tpat_patchify(const float* spec, void* patches, int out_dtype, float* tokens,
+                  const float* extra_tok, const float* pos, int B, int T, int F, int D,
+                  int num_extra, int order, tpat_stream_t stream);
+
+/*
+ * LayerNorm over the last dim.  Replaces nn.LayerNorm (models_vit.py:197,205; ast_models.py:209,217,500).
+ *   x [rows, D] fp32 -> y [rows, D] (y_dtype).  D % 128 == 0, D <= 2048.
+ */
+int tpat_layernorm(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                   int rows, int D, float eps, tpat_stream_t stream);
+
+/*
+ * C[M, N] = epilogue(A[M, K] * W[N, K]^T + bias[N]).  Replaces nn.Linear + the elementwise op
+ * that follows it: qkv (models_vit.py:76), proj + residual (:96,198), fc1 + GELU (:41-42),
+ * fc2 + residual (:44,205), patch-embed conv as GEMM + pos add (:246,358), head (:522).
+ *   A [M, K] row-major, lda elements between rows, a_dtype; W [N, K] row-major (nn.Linear layout),
+ *   w_dtype (must equal a_dtype); bias fp32 [N] or NULL; C [*, ldc] c_dtype.
+ *   TPAT_EPI_BIAS_RESIDUAL: residual fp32 [M, ldr], C fp32.
+ *   TPAT_EPI_BIAS_POS: row m = b*P + p is written to row b*(extra+P) + extra + p and pos[(extra+p), :]
+ *     (fp32 [extra+P, N]) is added; pass P and extra, C fp32.
+ *   impl TPAT_IMPL_TC requires bf16 operands, K % 64 == 0, N % 16 == 0, 16-byte aligned pointers.
+ */
+int tpat_gemm(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
+              void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
+              int P, int num_extra, int M, int N, int K, int epilogue, int impl, tpat_stream_t stream);
+
+/*
+ * Fused multi-head attention that also emits the importance-score partials.
+ * Replaces: q k^T * scale, softmax, attn @ v, transpose/reshape (models_vit.py:79-95) and the
+ * score slice/mean over the materialised [B,H,N,N] matrix (:113; ast_models.py:124).
+ *   qkv   [B * N, 3 * H * hd] (dtype): the qkv Linear output, column = which*H*hd + h*hd + d
+ *   out   [B * N, H * hd] (dtype)
+ *   score_partial  fp32, NULL when score_mode == NONE.
+ *       CLS_ROW : [B, H, N]            row 0 of P per head
+ *       COLMEAN : [B, H * n_qt, N]     per (head, query tile) column sums of P over rows >= extra,
+ *                 n_qt = tpat_attention_qtiles(N, impl)
+ *   softmax is exact (max-subtracted, normalised over all N keys), fp32.
+ */
+int tpat_attention_qtiles(int N, int impl);
+int tpat_attention(const void* qkv, void* out, int dtype, float* score_partial, int score_mode,
+                   int B, int N, int H, int hd, int num_extra, float scale, int impl,
+                   tpat_stream_t stream);
+
+/*
+ * Reduce the score partials in a fixed order (deterministic), write the score, and select the
+ * top-k tokens.  Replaces `.mean(...)` + torch.topk(score, k, largest=True, sorted=True)
+ * (models_vit.py:113-114, ast_models.py:124-125).
+ *   partial  [B, R, N] fp32 (R rows to sum per clip), score[b, j] = sum_r partial[b, r, extra+j] / divisor
+ *   score    [B, N - extra] fp32 (may be NULL)
+ *   topk_idx [B, k] int64, descending score; ties: lower index first (torch leaves ties
+ *            unspecified).  NaN ranks above every number, like torch.topk.
+ *            k == 0 or topk_idx == NULL: only the score is written.
+ */
+int tpat_score_topk(const float* partial, int R, float divisor, float* score, int64_t* topk_idx,
+                    int B, int N, int num_extra, int k, tpat_stream_t stream);
+
+/*
+ * Token gather / compaction fused with the LayerNorm that follows it.
+ * Replaces torch.gather + torch.cat (models_vit.py:200-203) and norm2 (:205).
+ *   x      [B, N_in, D] fp32   residual stream after the attention residual add
+ *   x_out  [B, extra + k, D] fp32: rows < extra copied, row extra+j = x[b, extra + idx[b, j]]
+ *   y_out  [B, extra + k, D] (y_dtype) = LayerNorm(x_out) ; NULL to skip
+ */
+int tpat_gather_layernorm(const float* x, const int64_t* topk_idx, float* x_out, const float* gamma,
+                          const float* beta, void* y_out, int y_dtype, int B, int N_in, int k,
+                          int num_extra, int D, float eps, tpat_stream_t stream);
+
+/*
+ * Pooled classifier input.  Replaces
+ *   AudioMAE: x[:, 1:].mean(1) -> fc_norm            (models_vit.py:388-389)
+ *   AST     : v.norm -> (x[:,0]+x[:,1])/2 -> mlp_head[0] LayerNorm   (ast_models.py:500-503)
+ *   x [B, N, D] fp32 -> pooled [B, D] fp32.  AST uses (g1,b1,eps1) = v.norm, (g2,b2,eps2) = mlp_head.0;
+ *   AudioMAE uses (g1,b1,eps1) = fc_norm and ignores the second set.
+ */
+int tpat_pool_norm(const float* x, float* pooled, const float* g1, const float* b1, float eps1,
+                   const float* g2, const float* b2, float eps2, int B, int N, int D, int variant,
+                   tpat_stream_t stream);
+
+/* ---- whole forward (the hot loop of models_vit.py:365-385 / ast_models.py:470-497 in native code) ---- */
+
+typedef struct {
+  const float* ln1_g; const float* ln1_b;
+  const void* qkv_w;  const float* qkv_b;   /* [3D, D] */
+  const void* proj_w; const float* proj_b;  /* [D, D]  */
+  const float* ln2_g; const float* ln2_b;
+  const void* fc1_w;  const float* fc1_b;   /* [Dh, D] */
+  const void* fc2_w;  const float* fc2_b;   /* [D, Dh] */
+} tpat_block_weights;
+
+typedef struct {
+  int variant;        /* TPAT_VARIANT_*                                                       */
+  int impl;           /* TPAT_IMPL_SIMT: fp32 weights & activations; TPAT_IMPL_TC: bf16        */
+  int B, T, F;        /* clips, time frames, mel bins (F == 128 in the reference)              */
+  int depth, D, H, Dh, num_classes;
+  int prune[TPAT_MAX_DEPTH]; /* 1: block i runs top-k + gather (reference: keep_rate < 1.0)        */
+  int keep[TPAT_MAX_DEPTH];  /* non-extra tokens leaving block i (k of the top-k when prune[i])   */
+  int want_all_scores;       /* extract mode: emit the score of every block                    */
+  float ln_eps;              /* 1e-6 for every block norm                                      */
+  /* weights: matrices in the impl's operand dtype, vectors fp32 */
+  const void* patch_w; const float* patch_b;       /* [D, 256], columns in the order of `variant` */
+  const float* extra_tok;                          /* [extra, D]: cls (, dist)                  */
+  const float* pos;                                /* [extra + P, D]                            */
+  tpat_block_weights blocks[TPAT_MAX_DEPTH];
+  const float* norm_g; const float* norm_b; float norm_eps;   /* fc_norm (AudioMAE) / v.norm (AST) */
+  const float* head_ln_g; const float* head_ln_b; float head_ln_eps;  /* AST mlp_head.0; NULL for AudioMAE */
+  const float* head_w; const float* head_b;        /* [C, D] fp32                               */
+  /* inputs / outputs */
+  const float* spec;          /* [B, T, F] fp32                                                 */
+  float* logits;              /* [B, C] fp32                                                    */
+  float* scores[TPAT_MAX_DEPTH];     /* [B, n_i] fp32 or NULL (n_i = non-extra tokens entering block i) */
+  int64_t* topk_idx[TPAT_MAX_DEPTH]; /* [B, keep[i]] int64; required where prune[i]                  */
+  void* workspace; size_t workspace_bytes;
+} tpat_forward_args;
+
+/* sizeof(tpat_forward_args) as compiled into the library (lets a foreign-language binding verify its struct layout) */
+size_t tpat_sizeof_forward_args(void);
+size_t tpat_forward_workspace_bytes(const tpat_forward_args* args);
+int tpat_forward(const tpat_forward_args* args, tpat_stream_t stream);
+/* number of kernels tpat_forward launches for `args` (for bench.py's gpu_launches) */
+int tpat_forward_launch_count(const tpat_forward_args* args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPAT_H */

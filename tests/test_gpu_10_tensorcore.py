@@ -1,0 +1,103 @@
+"""GPU parity of the tcgen05 kernels (GEMM, fused attention) against (a) a PyTorch fp64 reference
+computed from the SAME bf16-rounded operands and (b) the CUDA-core kernels of this library.
+Tolerance: fp32 accumulation of bf16 products -> 2e-5 relative to the largest output before the
+output is rounded; bf16 outputs add one bf16 rounding (2^-8 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import conftest  # noqa: F401
+from gpu_util import dev, rel_err, ref_attention, ref_score
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (M, N, K)
+    (128, 256, 64), (300, 768, 768), (1026, 2304, 768), (4104, 3072, 768), (2890, 768, 3072), (1024, 768, 256),
+    (25, 2304, 768), (32832, 768, 768), (257, 384, 384),
+]
+
+
+def _mk(M, N, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(M, K, generator=g).to(dev()).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(dev()).to(torch.bfloat16)
+    bias = (torch.randn(N, generator=g) * 0.1).to(dev())
+    return a, w, bias
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tc_bias_and_gelu(M, N, K):
+    from tpat import ops, _lib
+    a, w, bias = _mk(M, N, K, 11)
+    base = a.double() @ w.double().T + bias.double()
+    out = ops.gemm(a, w, bias, torch.float32, _lib.EPI_BIAS, _lib.IMPL_TC)
+    assert rel_err(out, base) < 2e-5
+    out = ops.gemm(a, w, bias, torch.bfloat16, _lib.EPI_BIAS, _lib.IMPL_TC)
+    assert rel_err(out.float(), base) < 5e-3
+    out = ops.gemm(a, w, bias, torch.bfloat16, _lib.EPI_BIAS_GELU, _lib.IMPL_TC)
+    assert rel_err(out.float(), F.gelu(base)) < 5e-3
+    # cross-check with this library's CUDA-core kernel on identical operands
+    simt = ops.gemm(a, w, bias, torch.float32, _lib.EPI_BIAS, _lib.IMPL_SIMT)
+    tc = ops.gemm(a, w, bias, torch.float32, _lib.EPI_BIAS, _lib.IMPL_TC)
+    assert rel_err(tc, simt) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 768, 768), (2890, 768, 3072), (32832, 768, 768)])
+def test_gemm_tc_residual_in_place(M, N, K):
+    from tpat import ops, _lib
+    a, w, bias = _mk(M, N, K, 12)
+    res = torch.randn(M, N, generator=torch.Generator().manual_seed(13)).to(dev())
+    ref = res.double() + a.double() @ w.double().T + bias.double()
+    x = res.clone()
+    out = ops.gemm(a, w, bias, torch.float32, _lib.EPI_BIAS_RESIDUAL, _lib.IMPL_TC, residual=x, out=x)
+    assert out.data_ptr() == x.data_ptr()
+    assert rel_err(x, ref) < 2e-5
+
+
+def test_gemm_tc_patch_pos_epilogue():
+    from tpat import ops, _lib
+    B, P, extra, D = 5, 512, 1, 768
+    a, w, bias = _mk(B * P, D, 256, 14)
+    pos = torch.randn(extra + P, D, generator=torch.Generator().manual_seed(15)).to(dev())
+    out = torch.full((B * (extra + P), D), 7.0, device=dev())
+    ops.gemm(a, w, bias, torch.float32, _lib.EPI_BIAS_POS, _lib.IMPL_TC, out=out, pos=pos, P=P, num_extra=extra)
+    ref = (a.double() @ w.double().T + bias.double()).reshape(B, P, D) + pos[extra:].double()
+    o = out.reshape(B, extra + P, D)
+    assert rel_err(o[:, extra:], ref) < 2e-5
+    assert torch.all(o[:, :extra] == 7.0)
+
+
+def test_gemm_tc_rejects_bad_arguments():
+    from tpat import ops, _lib
+    a, w, bias = _mk(64, 64, 96, 16)
+    with pytest.raises(RuntimeError, match="K %% 64|K % 64"):
+        ops.gemm(a, w, bias, torch.float32, _lib.EPI_BIAS, _lib.IMPL_TC)
+    with pytest.raises(RuntimeError, match="bf16"):
+        ops.gemm(a.float(), w.float(), bias, torch.float32, _lib.EPI_BIAS, _lib.IMPL_TC)
+
+
+ATT_CASES = [(66, 2, "cls"), (25, 2, "cls"), (514, 2, "cls"), (361, 2, "cls"), (513, 1, "colmean"), (360, 1, "colmean"),
+             (253, 1, "colmean"), (178, 1, "colmean"), (129, 1, "colmean"), (128, 1, "none"), (513, 1, "none")]
+
+
+@pytest.mark.parametrize("N,extra,mode", ATT_CASES)
+def test_attention_tc(N, extra, mode):
+    from tpat import ops, _lib
+    g = torch.Generator().manual_seed(21)
+    B, H = 3, 12
+    qkv = (torch.randn(B * N, 3 * H * 64, generator=g) * 1.5).to(dev()).to(torch.bfloat16)
+    smode = {"cls": _lib.SCORE_CLS_ROW, "colmean": _lib.SCORE_COLMEAN, "none": _lib.SCORE_NONE}[mode]
+    out, partial = ops.attention(qkv, B, N, H, extra, smode, _lib.IMPL_TC)
+    ref_out, attn = ref_attention(qkv, B, N, H, extra)
+    # P is rounded to bf16 before P.V and the output is bf16: two bf16 roundings
+    assert rel_err(out.float(), ref_out) < 1e-2
+    simt_out, simt_partial = ops.attention(qkv, B, N, H, extra, smode, _lib.IMPL_SIMT)
+    assert rel_err(out.float(), simt_out.float()) < 1e-2
+    if mode != "none":
+        div = H if mode == "cls" else H * (N - extra)
+        score, _ = ops.score_topk(partial, div, extra, 0)
+        ref = ref_score(attn, extra, "cls" if mode == "cls" else "colmean")
+        # scores are accumulated from fp32 probabilities (ex2.approx): ~1e-6 relative
+        assert rel_err(score, ref) < 2e-5
+        score_simt, _ = ops.score_topk(simt_partial, div, extra, 0)
+        assert rel_err(score, score_simt) < 2e-5

@@ -1,0 +1,170 @@
+"""GPU parity of the whole forward through the reference-facing model API against the golden
+vectors produced by the REAL reference (tests/golden, oracle/make_golden.py) and the oracle.
+
+fp32 mode  (CUDA-core kernels):  kept top-k SETS identical per clip and block, in mel-patch
+           coordinates, except where the reference's own score gap at the cut is below 1e-9
+           (fp32 summation order); logits within 1e-5 of max|logit| (north_star fp32 tolerance:
+           2e-5 used).
+bf16 mode  (tcgen05 kernels): SURVEY.md F14/H1 measured that with random-init weights the
+           reference's OWN bf16 run reaches only 0.97-0.99 kept-set overlap and 3.8e-2 logit error
+           against its fp64 run, so the north-star 99.9 % / 1e-2 cannot be met by any bf16
+           implementation on these inputs; the thresholds asserted here are the emulated
+           "bf16 operands, fp32 accumulate" floor measured on the reference (>= 0.985 overlap,
+           <= 3e-2 of max|logit|) and the measured values are printed for DESIGN.md.
+"""
+import pytest
+import torch
+import torch.nn as nn
+
+import conftest  # noqa: F401
+from conftest import load_golden, make_case
+from gpu_util import dev, rel_err, set_overlap
+from oracle import vit_oracle as vo
+from oracle.golden_configs import GOLDEN_CONFIGS
+
+pytestmark = pytest.mark.gpu
+
+
+def build_model(meta, sd, precision):
+    from tpat import models_vit, ASTModel
+    if meta["variant"] == "audiomae":
+        m = models_vit.vit_base_patch16(num_classes=meta["num_classes"], drop_path_rate=0.1, mean_pooling=True,
+                                        mask_2d=True, target_length=meta["T"], drop_loc=tuple(meta["drop_loc"]),
+                                        base_keep_rate=meta["base_keep_rate"], precision=precision)
+        m.patch_embed = models_vit.PatchEmbed((meta["T"], 128), 16, 1, 768)
+        m.pos_embed = nn.Parameter(torch.zeros(1, m.patch_embed.num_patches + 1, 768), requires_grad=False)
+        m.load_state_dict(sd, strict=True)
+    else:
+        m = ASTModel(label_dim=meta["num_classes"], input_tdim=meta["T"], imagenet_pretrain=False,
+                     audioset_pretrain=False, verbose=False, drop_loc=tuple(meta["drop_loc"]),
+                     base_keep_rate=meta["base_keep_rate"], precision=precision)
+        m.load_state_dict(sd, strict=False)
+    return m.to(dev()).eval()
+
+
+def prune_blocks(ref):
+    return sorted(int(k.split(".")[0].split("-")[1]) for k in ref if k.endswith("topk_idx"))
+
+
+def mel_idx(feats, blocks):
+    return vo.melspec_indices([feats[f"block-{i}.topk_idx"].cpu() for i in blocks])
+
+
+def check_fp32_sets(feats, ref, blocks):
+    """Set equality per clip/block in mel coordinates, modulo near-ties at the cut in the reference."""
+    if not blocks:
+        return
+    got, exp = mel_idx(feats, blocks), mel_idx(ref, blocks)
+    for bi, (g, e) in enumerate(zip(got, exp)):
+        blk = blocks[bi]
+        score = ref[f"block-{blk}.attn_score"]
+        k = e.shape[1]
+        for c in range(e.shape[0]):
+            sg, se = set(g[c].tolist()), set(e[c].tolist())
+            if sg == se:
+                continue
+            srt = torch.sort(score[c], descending=True).values
+            gap = (srt[k - 1] - srt[k]).item() if k < srt.numel() else float("inf")
+            assert gap < 1e-9 and len(sg ^ se) <= 2, f"block {blk} clip {c}: kept sets differ, cut gap {gap:.3e}"
+            return  # later blocks of this config are no longer comparable once a near-tie flipped
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CONFIGS))
+def test_forward_fp32_matches_reference_golden(name):
+    g = load_golden(name)
+    meta, ref = g["meta"], g["ref"]
+    sd, x = make_case(meta)
+    model = build_model(meta, sd, "fp32")
+    with torch.no_grad():
+        logits, feats = model(x.to(dev()), keep_rate_list=meta["keep_rate_list"], flag_extract_features=True)
+        logits_plain = model(x.to(dev()), keep_rate_list=meta["keep_rate_list"])
+    assert sorted(k for k in feats if k != "mel") == sorted(k for k in ref if k != "logits")
+    assert torch.equal(feats["mel"], x if meta["variant"] == "audiomae" else x.unsqueeze(1).transpose(2, 3))
+    blocks = prune_blocks(ref)
+    for i in blocks:
+        t = feats[f"block-{i}.topk_idx"]
+        assert t.dtype == torch.int64 and t.shape == ref[f"block-{i}.topk_idx"].shape and t.device.type == "cpu"
+    check_fp32_sets(feats, ref, blocks)
+    first = blocks[0] if blocks else 12
+    for i in range(12):   # scores of blocks up to and including the first pruning block see identical tokens
+        if i <= first:
+            assert rel_err(feats[f"block-{i}.attn_score"], ref[f"block-{i}.attn_score"]) < 2e-5, i
+    err = rel_err(logits.cpu(), ref["logits"])
+    print(f"[fp32] {name}: logits err {err:.2e}")
+    assert err < 2e-5
+    assert torch.equal(logits, logits_plain)            # extract mode changes outputs reported, not math
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CONFIGS))
+def test_forward_bf16_against_reference_golden(name):
+    g = load_golden(name)
+    meta, ref, f64 = g["meta"], g["ref"], g["f64"]
+    sd, x = make_case(meta)
+    model = build_model(meta, sd, "bf16")
+    with torch.no_grad():
+        logits, feats = model(x.to(dev()), keep_rate_list=meta["keep_rate_list"], flag_extract_features=True)
+    blocks = prune_blocks(ref)
+    overlaps = []
+    if blocks:
+        got, exp = mel_idx(feats, blocks), mel_idx(f64, blocks)
+        overlaps = [set_overlap(a, b) for a, b in zip(got, exp)]
+    err = rel_err(logits.cpu(), f64["logits"])
+    s0 = rel_err(feats["block-0.attn_score"], f64["block-0.attn_score"])
+    print(f"[bf16] {name}: kept-set overlap vs fp64 {['%.4f' % o for o in overlaps]}, logits err {err:.2e}, "
+          f"block-0 score err {s0:.2e}")
+    assert all(o >= 0.985 for o in overlaps)
+    assert err < 3e-2
+    assert s0 < 5e-3
+
+
+def test_forward_is_deterministic_and_batch_invariant():
+    """Full-size property (BASELINE configs[1] shape, B=64): the same clip gives bit-identical
+    logits and indices run to run and regardless of which batch it sits in (no atomics, fixed
+    reduction orders, per-clip top-k)."""
+    from oracle import weights
+    meta = dict(variant="audiomae", T=1024, num_classes=527, drop_loc=(3, 6, 9), base_keep_rate=0.7)
+    sd = weights.make_audiomae_state_dict(527, 1024, 0, "refinit")
+    x = weights.make_spectrogram("audiomae", 64, 1024, 1234).to(dev())
+    for precision in ("bf16", "fp32"):
+        model = build_model(meta, sd, precision)
+        with torch.no_grad():
+            a = model(x)
+            ia = [t.clone() for t in model.last_topk_idx if t is not None]
+            b = model(x)
+            ib = [t for t in model.last_topk_idx if t is not None]
+            c = model(x[8:16])
+            ic = [t for t in model.last_topk_idx if t is not None]
+        assert torch.equal(a, b) and all(torch.equal(p, q) for p, q in zip(ia, ib))
+        assert torch.equal(a[8:16], c) and all(torch.equal(p[8:16], q) for p, q in zip(ia, ic))
+        assert [t.shape[1] for t in ia] == [359, 252, 177]
+        assert torch.isfinite(a).all()
+        for t, n_in in zip(ia, (512, 359, 252)):   # indices are a duplicate-free subset of the incoming tokens
+            assert int(t.min()) >= 0 and int(t.max()) < n_in
+            assert all(len(set(r)) == len(r) for r in t[:4].tolist())
+
+
+def test_cuda_graph_path_matches_eager_launches():
+    g = load_golden("ast_spc2_b8_kr07")
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    model = build_model(meta, sd, "bf16")
+    with torch.no_grad():
+        eager = model(x.to(dev()))
+        idx_e = [t.clone() for t in model.last_topk_idx if t is not None]
+        model.use_cuda_graph = True
+        for _ in range(2):
+            graphed = model(x.to(dev()))
+        idx_g = [t for t in model.last_topk_idx if t is not None]
+    assert torch.equal(eager, graphed) and all(torch.equal(p, q) for p, q in zip(idx_e, idx_g))
+
+
+def test_weights_are_repacked_after_an_update():
+    g = load_golden("ast_spc2_b4_unpruned")
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    model = build_model(meta, sd, "bf16")
+    with torch.no_grad():
+        a = model(x.to(dev()))
+        model.mlp_head[1].bias.add_(1.0)               # in-place update bumps the parameter version
+        b = model(x.to(dev()))
+    assert torch.allclose(b, a + 1.0, atol=1e-5)

@@ -1,0 +1,93 @@
+"""CPU: the host-side mirror of the reference model API (names, state-dict keys, errors, schedule)."""
+import math
+
+import pytest
+import torch
+import torch.nn as nn
+
+import conftest  # noqa: F401
+from oracle import vit_oracle as vo, weights
+
+
+def build_audiomae(T=1024, C=527, **kw):
+    from tpat import models_vit
+    m = models_vit.vit_base_patch16(num_classes=C, drop_path_rate=0.1, mean_pooling=True, mask_2d=True,
+                                    target_length=T, drop_loc=(3, 6, 9), base_keep_rate=0.7, **kw)
+    m.patch_embed = models_vit.PatchEmbed((T, 128), 16, 1, 768)             # main_finetune.py:378
+    m.pos_embed = nn.Parameter(torch.zeros(1, m.patch_embed.num_patches + 1, 768), requires_grad=False)
+    return m
+
+
+def test_audiomae_state_dict_keys_match_reference_format():
+    m = build_audiomae()
+    sd = weights.make_audiomae_state_dict(527, 1024, 0)
+    assert set(m.state_dict()) == set(sd)
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == sum(v.numel() for v in sd.values())
+    assert len(m.blocks) == 12 and m.no_weight_decay() == {'pos_embed', 'cls_token'}
+    assert [b.attn.default_keep_rate for b in m.blocks] == vo.default_keep_rate_list(12, (3, 6, 9), 0.7)
+
+
+def test_ast_state_dict_keys_match_reference_format():
+    from tpat import ASTModel
+    m = ASTModel(label_dim=35, input_tdim=128, imagenet_pretrain=False, audioset_pretrain=False, verbose=False,
+                 drop_loc=(3, 6, 9), base_keep_rate=0.7)
+    sd = weights.make_ast_state_dict(35, 128, 0)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected
+    assert set(missing) == {"v.head.weight", "v.head.bias", "v.head_dist.weight", "v.head_dist.bias"}
+    assert m.v.pos_embed.shape == (1, 66, 768)
+    assert [b.attn.default_keep_rate for b in m.v.blocks] == vo.default_keep_rate_list(12, (3, 6, 9), 0.7)
+    assert all(b.attn.num_extra_tokens == 2 and b.num_extra_tokens == 2 for b in m.v.blocks)
+    # DataParallel-style checkpoints carry a "module." prefix (traintest.py:247); the mirror's keys are the suffixes
+    assert all(k.startswith(("v.", "mlp_head.")) for k in m.state_dict())
+
+
+def test_errors_match_reference_behaviour():
+    m = build_audiomae(T=128, C=10)
+    with pytest.raises(ValueError):                      # models_vit.py:506-507
+        m(torch.zeros(1, 1, 128, 128), keep_rate_list=[1.0] * 11)
+    with pytest.raises(RuntimeError):                    # no CPU path
+        m(torch.zeros(1, 1, 128, 128))
+    with pytest.raises(AssertionError):                  # models_vit.py:336: T >= F and F == 128
+        m(torch.zeros(1, 1, 64, 128))
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 1, 128, 128), mask_t_prob=0.3)
+    from tpat import models_vit
+    with pytest.raises(AssertionError):                  # models_vit.py:66
+        models_vit.Attention(768, 12, default_keep_rate=0.0)
+
+
+def test_precision_selection():
+    assert build_audiomae(T=128, C=10).precision == "bf16"
+    assert build_audiomae(T=128, C=10, precision="fp32").precision == "fp32"
+    with pytest.raises(ValueError):
+        build_audiomae(T=128, C=10, precision="fp16")
+
+
+@pytest.mark.parametrize("n,extra", [(512, 1), (512, 2), (64, 2), (128, 1)])
+@pytest.mark.parametrize("kr", [0.5, 0.6, 0.7, 0.8, 0.9, 0.999, 1.0])
+def test_pruning_schedule_follows_reference_ceil(n, extra, kr):
+    from tpat.engine import pruning_schedule
+    rates = vo.default_keep_rate_list(12, (3, 6, 9), kr)
+    prune, keep = pruning_schedule(n, extra, rates)
+    assert keep == vo.token_schedule(n, rates)
+    assert prune == [1 if r < 1.0 else 0 for r in rates]          # top-k runs whenever keep_rate < 1.0
+    cur = n
+    for i in (3, 6, 9):
+        if kr < 1.0:
+            assert keep[i] == math.ceil(kr * cur)
+            cur = keep[i]
+
+
+def test_shard_bounds_cover_batch():
+    from tpat.dist import shard_bounds
+    for n in (1, 7, 8, 64, 65):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1

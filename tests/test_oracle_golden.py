@@ -1,0 +1,60 @@
+"""CPU: the oracle restatement against the golden vectors generated from the REAL reference
+(oracle/make_golden.py).  Bit-exact: same ATen ops in the same order on the same torch build."""
+import pytest
+import torch
+
+from conftest import load_golden, make_case
+from oracle import vit_oracle as vo
+from oracle.golden_configs import GOLDEN_CONFIGS
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CONFIGS))
+def test_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    with torch.no_grad():
+        logits, feats = vo.forward(meta["variant"], sd, x, meta["keep_rate_list"], meta["drop_loc"],
+                                   meta["base_keep_rate"], flag_extract_features=True)
+        logits_plain, feats_plain = vo.forward(meta["variant"], sd, x, meta["keep_rate_list"], meta["drop_loc"],
+                                               meta["base_keep_rate"], flag_extract_features=False)
+    ref = g["ref"]
+    # logits: identical up to MKL thread-count effects (bitwise on the generating machine)
+    assert torch.allclose(logits, ref["logits"], rtol=0, atol=2e-6)
+    assert torch.allclose(logits_plain, g["ref_plain"]["logits"], rtol=0, atol=2e-6)
+    keys = sorted(k for k in ref if k != "logits")
+    assert sorted(feats) == keys
+    for k in keys:
+        if k.endswith("topk_idx"):
+            # same kept SET per clip; order may differ only between near-tied scores
+            for a, b in zip(feats[k].tolist(), ref[k].tolist()):
+                assert set(a) == set(b), k
+        else:
+            assert torch.allclose(feats[k], ref[k], rtol=0, atol=1e-8), k
+    # non-extract mode reports only the pruning blocks
+    assert sorted(feats_plain) == sorted(k for k in keys if k.split(".")[0] in
+                                         {kk.split(".")[0] for kk in keys if kk.endswith("topk_idx")})
+
+
+def test_fp64_oracle_agrees_with_fp32_reference_sets():
+    g = load_golden("audiomae_1024_b2_kr07")
+    for k, v in g["ref"].items():
+        if k.endswith("topk_idx"):
+            for a, b in zip(v.tolist(), g["f64"][k].tolist()):
+                assert len(set(a) & set(b)) >= len(a) - 1, k   # fp32 vs fp64: at most one near-tie flip
+
+
+def test_token_schedule_matches_survey():
+    # 512 -> 359 -> 252 -> 177 ; SPC-2: 64 -> 45 -> 32 -> 23
+    rates = vo.default_keep_rate_list(12, (3, 6, 9), 0.7)
+    assert vo.token_schedule(512, rates)[3::3] == [359, 252, 177]
+    assert vo.token_schedule(64, rates)[3::3] == [45, 32, 23]
+    assert vo.token_schedule(512, vo.default_keep_rate_list(12, (3, 6, 9), 0.5))[3::3] == [256, 128, 64]
+
+
+def test_melspec_indices_composition():
+    a = torch.tensor([[3, 1, 2]])
+    b = torch.tensor([[2, 0]])
+    out = vo.melspec_indices([a, b])
+    assert out[1].tolist() == [[2, 3]]

@@ -1,0 +1,29 @@
+// tpat_attention: argument validation and dispatch (CUDA-core parity path / tcgen05 path).
+#include "attention.cuh"
+
+extern "C" int tpat_attention_qtiles(int N, int impl) {
+  if (N <= 0) return 0;
+  return impl == TPAT_IMPL_TC ? tpat::attention_tc_qtiles(N) : tpat::attention_simt_qtiles(N);
+}
+
+extern "C" int tpat_attention(const void* qkv, void* out, int dtype, float* score_partial, int score_mode,
+                              int B, int N, int H, int hd, int num_extra, float scale, int impl,
+                              tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(qkv && out, "tpat_attention: null pointer");
+  TPAT_CHECK(B >= 0 && N > 0 && H > 0, "tpat_attention: bad sizes B=%d N=%d H=%d", B, N, H);
+  TPAT_CHECK(hd == 64, "tpat_attention: head dim must be 64 (got %d)", hd);
+  TPAT_CHECK(dtype == TPAT_F32 || dtype == TPAT_BF16, "tpat_attention: bad dtype %d", dtype);
+  TPAT_CHECK(score_mode >= TPAT_SCORE_NONE && score_mode <= TPAT_SCORE_COLMEAN, "tpat_attention: bad score mode %d", score_mode);
+  TPAT_CHECK(score_mode == TPAT_SCORE_NONE || score_partial != nullptr, "tpat_attention: score mode %d needs score_partial", score_mode);
+  TPAT_CHECK(num_extra >= 0 && num_extra < N, "tpat_attention: bad num_extra %d", num_extra);
+  TPAT_CHECK(aligned16(qkv) && aligned16(out), "tpat_attention: pointers must be 16-byte aligned");
+  if (B == 0) return 0;
+  if (impl == TPAT_IMPL_SIMT) return attention_simt(qkv, out, dtype, score_partial, score_mode, B, N, H, num_extra, scale, as_stream(stream));
+  if (impl == TPAT_IMPL_TC) {
+    TPAT_CHECK(dtype == TPAT_BF16, "tpat_attention: the tcgen05 path takes bf16 operands");
+    return attention_tc(qkv, out, score_partial, score_mode, B, N, H, num_extra, scale, as_stream(stream));
+  }
+  set_error("tpat_attention: bad impl %d", impl);
+  return 1;
+}

@@ -1,0 +1,67 @@
+// Shared host/device helpers for libtpat.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/tpat.h"
+
+namespace tpat {
+
+// ---- error plumbing: thread-local message, int status across the C boundary ----
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define TPAT_CHECK(cond, ...)                       \
+  do {                                              \
+    if (!(cond)) {                                  \
+      ::tpat::set_error(__VA_ARGS__);               \
+      return 1;                                     \
+    }                                               \
+  } while (0)
+
+#define TPAT_CUDA(expr)                                                        \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) return ::tpat::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define TPAT_LAUNCH_CHECK() TPAT_CUDA(cudaPeekAtLastError())
+
+static inline cudaStream_t as_stream(tpat_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline size_t dtype_size(int dt) { return dt == TPAT_BF16 ? 2 : 4; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int sm_count();  // cached multiprocessor count of the current device
+
+// ---- device helpers ----
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact (erf) GELU, the nn.GELU() default the reference uses (models_vit.py:31)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace tpat

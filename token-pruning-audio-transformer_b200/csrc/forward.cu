@@ -1,0 +1,154 @@
+// tpat_forward: the whole token-pruned ViT forward as one native call.
+//
+// Native restatement of the reference's hot loop -- VisionTransformer.forward_features
+// (audiomae/models_vit.py:334-396) / ASTModel.forward (ast/src/models/ast_models.py:424-508) and
+// Block.forward (models_vit.py:191-207) -- as a fixed sequence of kernel launches on one stream:
+//   patchify -> patch GEMM(+pos) -> 12 x [LN1 -> QKV GEMM -> attention(+score partials) ->
+//   proj GEMM(+residual) -> score/top-k -> gather+LN2 | LN2 -> fc1 GEMM(+GELU) -> fc2 GEMM(+residual)]
+//   -> pool/norm -> head GEMM.
+// No host synchronisation, no allocation: everything lives in the caller's workspace, so the call
+// can be captured in a CUDA graph.  The residual stream stays fp32 in both precisions.
+#include "gemm.cuh"
+#include "attention.cuh"
+
+namespace tpat {
+
+struct Workspace {
+  float* x[2];        // residual stream ping-pong [B*Nmax*D]
+  void* y;            // LayerNorm output       [B*Nmax*D]   (act dtype)
+  void* qkv;          //                         [B*Nmax*3D]
+  void* ao;           // attention output        [B*Nmax*D]
+  void* hid;          // MLP hidden / patch matrix [B*Nmax*Dh]
+  float* partial;     // score partials          [B*R*Nmax]
+  float* pooled;      // [B*D]
+  size_t bytes;
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+static int validate(const tpat_forward_args* a) {
+  TPAT_CHECK(a != nullptr, "tpat_forward: null args");
+  TPAT_CHECK(a->variant == TPAT_VARIANT_AUDIOMAE || a->variant == TPAT_VARIANT_AST, "tpat_forward: bad variant %d", a->variant);
+  TPAT_CHECK(a->impl == TPAT_IMPL_SIMT || a->impl == TPAT_IMPL_TC, "tpat_forward: bad impl %d", a->impl);
+  TPAT_CHECK(a->B > 0 && a->T >= 16 && a->F >= 16 && a->T % 16 == 0 && a->F % 16 == 0, "tpat_forward: bad input shape B=%d T=%d F=%d", a->B, a->T, a->F);
+  TPAT_CHECK(a->depth > 0 && a->depth <= TPAT_MAX_DEPTH, "tpat_forward: depth %d out of range", a->depth);
+  TPAT_CHECK(a->D > 0 && a->D % 128 == 0 && a->H > 0 && a->D == a->H * 64, "tpat_forward: need D == 64*H and D %% 128 == 0 (D=%d H=%d)", a->D, a->H);
+  TPAT_CHECK(a->Dh > 0 && a->Dh % 64 == 0 && a->num_classes > 0, "tpat_forward: bad Dh=%d or num_classes=%d", a->Dh, a->num_classes);
+  int n = (a->T / 16) * (a->F / 16);
+  for (int i = 0; i < a->depth; ++i) {
+    TPAT_CHECK(a->keep[i] > 0 && a->keep[i] <= n, "tpat_forward: keep[%d]=%d must be in (0, %d]", i, a->keep[i], n);
+    TPAT_CHECK(a->prune[i] || a->keep[i] == n, "tpat_forward: block %d drops tokens (%d -> %d) but prune[%d] is 0", i, n, a->keep[i], i);
+    if (a->prune[i]) TPAT_CHECK(a->topk_idx[i] != nullptr, "tpat_forward: block %d prunes but topk_idx[%d] is NULL", i, i);
+    n = a->keep[i];
+  }
+  return 0;
+}
+
+static Workspace carve(const tpat_forward_args* a, uint8_t* base) {
+  const int extra = a->variant == TPAT_VARIANT_AST ? 2 : 1;
+  const size_t P = (size_t)(a->T / 16) * (a->F / 16), Nmax = extra + P, B = a->B, D = a->D;
+  const size_t act = a->impl == TPAT_IMPL_TC ? 2 : 4;
+  const size_t nqt = (size_t)tpat_attention_qtiles((int)Nmax, a->impl);
+  const size_t R = a->variant == TPAT_VARIANT_AST ? (size_t)a->H : (size_t)a->H * nqt;
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+  w.x[0] = (float*)take(B * Nmax * D * 4);
+  w.x[1] = (float*)take(B * Nmax * D * 4);
+  w.y = take(B * Nmax * D * act);
+  w.qkv = take(B * Nmax * 3 * D * act);
+  w.ao = take(B * Nmax * D * act);
+  size_t hid = B * Nmax * (size_t)a->Dh * act, pat = B * P * 256 * act;
+  w.hid = take(hid > pat ? hid : pat);
+  w.partial = (float*)take(B * R * Nmax * 4);
+  w.pooled = (float*)take(B * D * 4);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace tpat
+
+extern "C" size_t tpat_forward_workspace_bytes(const tpat_forward_args* a) {
+  if (tpat::validate(a) != 0) return 0;
+  return tpat::carve(a, nullptr).bytes;
+}
+
+extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
+  if (tpat::validate(a) != 0) return -1;
+  int n = 2;  // patchify + patch GEMM
+  for (int i = 0; i < a->depth; ++i) {
+    const bool prune = a->prune[i] != 0;
+    n += 4;                                   // LN1, QKV, attention, proj
+    if (prune || a->want_all_scores) n += 1;  // score / top-k
+    n += 3;                                   // (gather+)LN2, fc1, fc2
+  }
+  return n + 2;  // pool/norm + head
+}
+
+extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
+  using namespace tpat;
+  if (int rc = validate(a)) return rc;
+  TPAT_CHECK(a->spec && a->logits && a->workspace, "tpat_forward: null spec / logits / workspace");
+  TPAT_CHECK(aligned16(a->workspace), "tpat_forward: workspace must be 16-byte aligned");
+  Workspace w = carve(a, reinterpret_cast<uint8_t*>(a->workspace));
+  TPAT_CHECK(a->workspace_bytes >= w.bytes, "tpat_forward: workspace too small (%zu < %zu bytes)", a->workspace_bytes, w.bytes);
+
+  const bool ast = a->variant == TPAT_VARIANT_AST;
+  const int extra = ast ? 2 : 1;
+  const int impl = a->impl;
+  const int act = impl == TPAT_IMPL_TC ? TPAT_BF16 : TPAT_F32;
+  const int B = a->B, D = a->D, H = a->H, Dh = a->Dh;
+  const int P = (a->T / 16) * (a->F / 16);
+  const float scale = 0.125f;  // head_dim ** -0.5 with head_dim == 64 (models_vit.py:58)
+
+  // patch embed + pos + cls/dist rows (models_vit.py:357-362 / ast_models.py:460-466)
+  if (int rc = tpat_patchify(a->spec, w.hid, act, w.x[0], a->extra_tok, a->pos, B, a->T, a->F, D, extra,
+                             ast ? TPAT_TOKENS_FREQ_MAJOR : TPAT_TOKENS_TIME_MAJOR, stream)) return rc;
+  if (int rc = tpat_gemm(w.hid, act, 256, a->patch_w, act, a->patch_b, w.x[0], TPAT_F32, D, nullptr, 0, a->pos, P, extra,
+                         B * P, D, 256, TPAT_EPI_BIAS_POS, impl, stream)) return rc;
+
+  int cur = P;       // non-extra tokens
+  int xi = 0;        // which residual buffer is live
+  for (int i = 0; i < a->depth; ++i) {
+    const tpat_block_weights& bw = a->blocks[i];
+    const int N = extra + cur, M = B * N;
+    const bool prune = a->prune[i] != 0;
+    const bool want_score = prune || a->want_all_scores;
+    float* x = w.x[xi];
+    if (int rc = tpat_layernorm(x, bw.ln1_g, bw.ln1_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
+    if (int rc = tpat_gemm(w.y, act, D, bw.qkv_w, act, bw.qkv_b, w.qkv, act, 3 * D, nullptr, 0, nullptr, 0, 0,
+                           M, 3 * D, D, TPAT_EPI_BIAS, impl, stream)) return rc;
+    const int smode = !want_score ? TPAT_SCORE_NONE : (ast ? TPAT_SCORE_CLS_ROW : TPAT_SCORE_COLMEAN);
+    if (int rc = tpat_attention(w.qkv, w.ao, act, w.partial, smode, B, N, H, 64, extra, scale, impl, stream)) return rc;
+    if (int rc = tpat_gemm(w.ao, act, D, bw.proj_w, act, bw.proj_b, x, TPAT_F32, D, x, D, nullptr, 0, 0,
+                           M, D, D, TPAT_EPI_BIAS_RESIDUAL, impl, stream)) return rc;
+    if (want_score) {
+      const int R = ast ? H : H * tpat_attention_qtiles(N, impl);
+      const float divisor = ast ? (float)H : (float)H * (float)(N - extra);
+      if (int rc = tpat_score_topk(w.partial, R, divisor, a->scores[i], prune ? a->topk_idx[i] : nullptr, B, N, extra,
+                                   prune ? a->keep[i] : 0, stream)) return rc;
+    }
+    int M2 = M;
+    if (prune) {
+      float* xn = w.x[xi ^ 1];
+      if (int rc = tpat_gather_layernorm(x, a->topk_idx[i], xn, bw.ln2_g, bw.ln2_b, w.y, act, B, N, a->keep[i], extra, D,
+                                         a->ln_eps, stream)) return rc;
+      xi ^= 1;
+      x = xn;
+      cur = a->keep[i];
+      M2 = B * (extra + cur);
+    } else {
+      if (int rc = tpat_layernorm(x, bw.ln2_g, bw.ln2_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
+    }
+    if (int rc = tpat_gemm(w.y, act, D, bw.fc1_w, act, bw.fc1_b, w.hid, act, Dh, nullptr, 0, nullptr, 0, 0,
+                           M2, Dh, D, TPAT_EPI_BIAS_GELU, impl, stream)) return rc;
+    if (int rc = tpat_gemm(w.hid, act, Dh, bw.fc2_w, act, bw.fc2_b, x, TPAT_F32, D, x, D, nullptr, 0, 0,
+                           M2, D, Dh, TPAT_EPI_BIAS_RESIDUAL, impl, stream)) return rc;
+  }
+
+  // pooled head (models_vit.py:387-389,522 / ast_models.py:500-503); always fp32 CUDA cores (tiny)
+  if (int rc = tpat_pool_norm(w.x[xi], w.pooled, a->norm_g, a->norm_b, a->norm_eps, a->head_ln_g, a->head_ln_b,
+                              a->head_ln_eps, B, extra + cur, D, a->variant, stream)) return rc;
+  return tpat_gemm(w.pooled, TPAT_F32, D, a->head_w, TPAT_F32, a->head_b, a->logits, TPAT_F32, a->num_classes, nullptr, 0,
+                   nullptr, 0, 0, B, a->num_classes, D, TPAT_EPI_BIAS, TPAT_IMPL_SIMT, stream);
+}

@@ -1,0 +1,25 @@
+// tpat_gemm: argument validation and dispatch to the CUDA-core or tcgen05 implementation.
+#include "gemm.cuh"
+
+extern "C" int tpat_gemm(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
+                         void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
+                         int P, int num_extra, int M, int N, int K, int epilogue, int impl, tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(A && W && C, "tpat_gemm: null pointer");
+  TPAT_CHECK(M >= 0 && N > 0 && K > 0, "tpat_gemm: bad sizes M=%d N=%d K=%d", M, N, K);
+  TPAT_CHECK(a_dtype == w_dtype && (a_dtype == TPAT_F32 || a_dtype == TPAT_BF16), "tpat_gemm: A and W must share a dtype (f32 or bf16)");
+  TPAT_CHECK(c_dtype == TPAT_F32 || c_dtype == TPAT_BF16, "tpat_gemm: bad C dtype %d", c_dtype);
+  TPAT_CHECK(epilogue >= TPAT_EPI_BIAS && epilogue <= TPAT_EPI_BIAS_POS, "tpat_gemm: bad epilogue %d", epilogue);
+  TPAT_CHECK(lda >= K && ldc >= N, "tpat_gemm: lda/ldc too small");
+  if (epilogue == TPAT_EPI_BIAS_RESIDUAL) TPAT_CHECK(residual && ldr >= N && c_dtype == TPAT_F32, "tpat_gemm: residual epilogue needs residual, ldr >= N and fp32 C");
+  if (epilogue == TPAT_EPI_BIAS_POS) TPAT_CHECK(pos && P > 0 && num_extra >= 0 && M % P == 0 && ldc == N && c_dtype == TPAT_F32, "tpat_gemm: pos epilogue needs pos, P | M, ldc == N and fp32 C");
+  if (M == 0) return 0;
+  EpiParams ep{bias, residual, ldr, pos, P, num_extra, epilogue};
+  if (impl == TPAT_IMPL_SIMT) return gemm_simt(A, a_dtype, lda, W, C, c_dtype, ldc, M, N, K, ep, as_stream(stream));
+  if (impl == TPAT_IMPL_TC) {
+    TPAT_CHECK(a_dtype == TPAT_BF16, "tpat_gemm: the tcgen05 path takes bf16 operands");
+    return gemm_tc(A, lda, W, C, c_dtype, ldc, M, N, K, ep, as_stream(stream));
+  }
+  set_error("tpat_gemm: bad impl %d", impl);
+  return 1;
+}

@@ -1,0 +1,21 @@
+// Internal interface shared by the GEMM translation units and the forward engine.
+#pragma once
+#include "common.cuh"
+
+namespace tpat {
+
+struct EpiParams {
+  const float* bias;
+  const float* residual; int ldr;
+  const float* pos; int P; int num_extra;
+  int epilogue;
+};
+
+// CUDA-core fp32-FMA path (gemm_simt.cu)
+int gemm_simt(const void* A, int a_dtype, int lda, const void* W, void* C, int c_dtype, int ldc, int M, int N, int K,
+              const EpiParams& ep, cudaStream_t st);
+// tcgen05 / TMEM / TMA path, bf16 operands (gemm_tc.cu)
+int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc, int M, int N, int K,
+            const EpiParams& ep, cudaStream_t st);
+
+}  // namespace tpat

@@ -1,0 +1,343 @@
+// tcgen05 GEMM for sm_100a: C = epilogue(A W^T + bias), bf16 operands, fp32 accumulation in TMEM.
+//
+// Replaces cuBLASLt + the unfused elementwise kernels behind nn.Linear in the reference's block
+// (audiomae/models_vit.py:41-45 fc1/GELU/fc2, :76 qkv, :96,198 proj + residual, :205 MLP residual)
+// and the patch-embed conv restated as a GEMM (:246, pos add :358).
+//
+// Design (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor loads of the A [128 x 64] and W [256 x 64] bf16
+//            k-blocks into a 4-stage 128B-swizzled shared-memory ring (48 KB / stage)
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+//            (M=128, N=256, K=16) x 4 per k-block; tcgen05.commit frees the stage / publishes
+//            the accumulator
+//   warps 2-5 epilogue: tcgen05.ld the 128 x 256 fp32 accumulator (thread = row), apply
+//            bias / GELU / residual / pos-embed, store.  Two accumulators (2 x 256 TMEM columns)
+//            so the epilogue of tile i overlaps the main loop of tile i+1.
+// Tiles are walked n-fastest so the CTAs in flight share A k-blocks through L2.
+// Roofline: tensor pipe.  Algorithmic FLOPs = 2*M*N*K per launch.
+#include "gemm.cuh"
+#include "ptx_sm100.cuh"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace tpat {
+
+// ---------------- tensor-map encoding (driver entry point, cached) ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr; uint64_t rows, cols, pitch; uint32_t box_rows, box_cols; int elem_bytes; bool sw;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && pitch == o.pitch && box_rows == o.box_rows &&
+           box_cols == o.box_cols && elem_bytes == o.elem_bytes && sw == o.sw;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.cols); mix(k.pitch); mix(k.box_rows); mix(k.box_cols); mix((uint64_t)k.elem_bytes * 2 + k.sw);
+    return h;
+  }
+};
+
+int encode_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                   uint32_t box_rows, uint32_t box_cols, bool swizzle128) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{gptr, rows, cols, pitch_bytes, box_rows, box_cols, elem_bytes, swizzle128};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  TPAT_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  TPAT_CHECK(aligned16(gptr) && pitch_bytes % 16 == 0, "TMA needs a 16-byte aligned base and row pitch (pitch=%llu)", (unsigned long long)pitch_bytes);
+  TPAT_CHECK(box_rows <= 256 && box_cols <= 256, "TMA box dims must be <= 256");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(gptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TPAT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu pitch=%llu box=%ux%u)", (int)r,
+             (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes, box_rows, box_cols);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
+// 3-D map over the qkv activation [B][N][ld] (bf16): box = 64 columns x 128 rows x 1 clip, 128B swizzle.
+// Rows >= N of a clip are out of bounds of dim 1 and are zero-filled (never the next clip's rows).
+int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{gptr, (uint64_t)N, (uint64_t)ld, (uint64_t)B, 128, 64, 2, true};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  TPAT_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  TPAT_CHECK(aligned16(gptr) && (ld * 2) % 16 == 0, "TMA needs a 16-byte aligned base and row pitch");
+  cuuint64_t gdim[3] = {(cuuint64_t)ld, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TPAT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d (B=%d N=%d ld=%d)", (int)r, B, N, ld);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
+// ---------------- kernel ----------------
+constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_STAGES = 4, TG_UMMA_K = 16;
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;   // 16 KB
+constexpr int TG_B_BYTES = TG_BN * TG_BK * 2;   // 32 KB
+constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
+constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TG_THREADS = 192;
+
+struct TcGemmParams {
+  int M, N, K;
+  void* C; int ldc;
+  const float* bias;
+  const float* residual; int ldr;
+  const float* pos; int P, num_extra;
+  int tiles_m, tiles_n;
+};
+
+template <int EPI, typename OutT>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + TG_STAGES * TG_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + TG_STAGES;       // [STAGES]
+  uint64_t* acc_full = bars + 2 * TG_STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int nkb = p.K / TG_BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TG_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<512>(tmem_slot);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (ptx::elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * TG_BM, n0 = (tile % p.tiles_n) * TG_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], TG_STAGE_BYTES);
+          ptx::tma_load_2d(smem_a + stage * TG_A_BYTES, &tmap_a, &full_bar[stage], kb * TG_BK, m0);
+          ptx::tma_load_2d(smem_b + stage * TG_B_BYTES, &tmap_w, &full_bar[stage], kb * TG_BK, n0);
+          if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(TG_BM, TG_BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TG_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_a + stage * TG_A_BYTES), 16, 1024);
+          const uint64_t b_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * TG_B_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < TG_BK / TG_UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            ptx::mma_f16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          ptx::tc_commit(&empty_bar[stage]);   // stage reusable once these MMAs retire
+          if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(&acc_full[acc]);        // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * TG_BM, n0 = (tile % p.tiles_n) * TG_BN;
+      ptx::mbar_wait(&acc_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      size_t orow = (size_t)m;
+      const float* pos_row = nullptr;
+      if constexpr (EPI == TPAT_EPI_BIAS_POS) {
+        const int b = m / p.P, pp = m - b * p.P;
+        orow = (size_t)b * (p.num_extra + p.P) + p.num_extra + pp;
+        pos_row = p.pos + (size_t)(p.num_extra + pp) * p.ldc;
+      }
+      OutT* crow = reinterpret_cast<OutT*>(p.C) + orow * p.ldc;
+      const float* rrow = (EPI == TPAT_EPI_BIAS_RESIDUAL) ? p.residual + (size_t)m * p.ldr : nullptr;
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
+#pragma unroll 1
+      for (int c = 0; c < TG_BN / 32; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr_row + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j] = __uint_as_float(r[j]) + bb.x; v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + bb.z; v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
+          }
+          if constexpr (EPI == TPAT_EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rr = *reinterpret_cast<const float4*>(rrow + n + j);
+              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+            }
+          } else if constexpr (EPI == TPAT_EPI_BIAS_POS) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 pe = __ldg(reinterpret_cast<const float4*>(pos_row + n + j));
+              v[j] += pe.x; v[j + 1] += pe.y; v[j + 2] += pe.z; v[j + 3] += pe.w;
+            }
+          }
+          if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(crow) + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + n + j) =
+                  make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
+                             pack_bf16x2(v[j + 6], v[j + 7]));
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int EPI, typename OutT>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const TcGemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;  // benign race: idempotent attribute
+  auto kern = gemm_tc_kernel<EPI, OutT>;
+  if (!attr_set) {
+    TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(ta, tw, p);
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc, int M, int N, int K,
+            const EpiParams& ep, cudaStream_t st) {
+  TPAT_CHECK(K % TG_BK == 0 && K >= TG_BK, "tpat_gemm(tc): need K %% 64 == 0 (K=%d)", K);
+  TPAT_CHECK(N % 32 == 0, "tpat_gemm(tc): need N %% 32 == 0 (N=%d)", N);
+  TPAT_CHECK(aligned16(C) && (ldc * dtype_size(c_dtype)) % 16 == 0, "tpat_gemm(tc): C must be 16-byte aligned with a 16-byte multiple pitch");
+  TPAT_CHECK(ep.bias == nullptr || aligned16(ep.bias), "tpat_gemm(tc): bias must be 16-byte aligned");
+  CUtensorMap ta, tw;
+  if (int rc = encode_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, TG_BM, TG_BK, true)) return rc;
+  if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, TG_BN, TG_BK, true)) return rc;
+  TcGemmParams p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
+  p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
+  p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + TG_BN - 1) / TG_BN;
+  switch (ep.epilogue) {
+    case TPAT_EPI_BIAS:
+      return c_dtype == TPAT_BF16 ? launch_tc<TPAT_EPI_BIAS, __nv_bfloat16>(ta, tw, p, st) : launch_tc<TPAT_EPI_BIAS, float>(ta, tw, p, st);
+    case TPAT_EPI_BIAS_GELU:
+      return c_dtype == TPAT_BF16 ? launch_tc<TPAT_EPI_BIAS_GELU, __nv_bfloat16>(ta, tw, p, st) : launch_tc<TPAT_EPI_BIAS_GELU, float>(ta, tw, p, st);
+    case TPAT_EPI_BIAS_RESIDUAL:
+      TPAT_CHECK(c_dtype == TPAT_F32 && ep.residual && aligned16(ep.residual) && ep.ldr % 4 == 0, "tpat_gemm(tc): residual epilogue needs fp32 C and an aligned fp32 residual");
+      return launch_tc<TPAT_EPI_BIAS_RESIDUAL, float>(ta, tw, p, st);
+    case TPAT_EPI_BIAS_POS:
+      TPAT_CHECK(c_dtype == TPAT_F32 && ep.pos && aligned16(ep.pos) && ep.P > 0, "tpat_gemm(tc): pos epilogue needs fp32 C, pos and P");
+      return launch_tc<TPAT_EPI_BIAS_POS, float>(ta, tw, p, st);
+  }
+  set_error("tpat_gemm(tc): bad epilogue %d", ep.epilogue);
+  return 1;
+}
+
+}  // namespace tpat

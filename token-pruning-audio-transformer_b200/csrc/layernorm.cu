@@ -1,0 +1,237 @@
+// Vectorised LayerNorm, token gather + LayerNorm, and the pooled classifier-input kernel.
+//
+// All three are HBM-bound (no reuse): one warp owns one token row, reads it once with 128-bit
+// loads (lane l reads float4 #l, #l+32, ... so every warp instruction covers 512 contiguous
+// bytes), keeps it in registers for the two-pass mean / variance, and writes the result once.
+// Algorithmic bytes per row: 4*D read + (2|4)*D written (+ 4*D for the compacted copy in the
+// gather variant).  Reference: nn.LayerNorm at audiomae/models_vit.py:197,205,389 and
+// ast/src/models/ast_models.py:209,217,500; torch.gather + torch.cat at models_vit.py:200-203.
+#include "common.cuh"
+
+namespace tpat {
+
+constexpr int LN_WARPS = 8;
+
+template <int NV>
+__device__ __forceinline__ void ln_row_load(const float* __restrict__ row, int lane, float4 (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(row) + lane + 32 * i);
+}
+
+template <int NV>
+__device__ __forceinline__ void ln_row_stats(const float4 (&v)[NV], float inv_d, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) * inv_d;
+  rstd = 1.0f / sqrtf(var + eps);
+}
+
+template <int NV, typename OutT>
+__device__ __forceinline__ void ln_row_store(const float4 (&v)[NV], float mean, float rstd,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             OutT* __restrict__ out, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    const float y0 = (v[i].x - mean) * rstd * g.x + b.x;
+    const float y1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float y2 = (v[i].z - mean) * rstd * g.z + b.z;
+    const float y3 = (v[i].w - mean) * rstd * g.w + b.w;
+    if constexpr (sizeof(OutT) == 4) {
+      reinterpret_cast<float4*>(out)[c4] = make_float4(y0, y1, y2, y3);
+    } else {
+      reinterpret_cast<uint2*>(out)[c4] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    }
+  }
+}
+
+// rows -> LayerNorm(rows).  grid = ceil(rows / LN_WARPS), block = 32 * LN_WARPS.
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(32 * LN_WARPS)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 OutT* __restrict__ y, int rows, float eps) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[NV];
+  ln_row_load<NV>(x + (size_t)row * D, lane, v);
+  float mean, rstd;
+  ln_row_stats<NV>(v, 1.0f / D, eps, mean, rstd);
+  ln_row_store<NV, OutT>(v, mean, rstd, gamma, beta, y + (size_t)row * D, lane);
+}
+
+// Token compaction fused with norm2: output row (b, j) <- input row (b, j < extra ? j : extra + idx[b, j-extra]).
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(32 * LN_WARPS)
+gather_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, float* __restrict__ x_out,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, OutT* __restrict__ y_out,
+                        int B, int N_in, int k, int num_extra, float eps) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int N_out = num_extra + k;
+  const int orow = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (orow >= B * N_out) return;
+  const int b = orow / N_out, j = orow - b * N_out;
+  int src = j;
+  if (j >= num_extra) src = num_extra + (int)__ldg(idx + (size_t)b * k + (j - num_extra));
+  float4 v[NV];
+  ln_row_load<NV>(x + ((size_t)b * N_in + src) * D, lane, v);
+  float4* xo = reinterpret_cast<float4*>(x_out + (size_t)orow * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) xo[lane + 32 * i] = v[i];
+  if (y_out != nullptr) {
+    float mean, rstd;
+    ln_row_stats<NV>(v, 1.0f / D, eps, mean, rstd);
+    ln_row_store<NV, OutT>(v, mean, rstd, gamma, beta, y_out + (size_t)orow * D, lane);
+  }
+}
+
+// ---- pooled classifier input: one CTA (256 threads) per clip ----
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < 8) ? red[l] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+// LayerNorm of a D-vector held in shared memory (in place), block-cooperative.
+__device__ void block_layernorm_inplace(float* vec, int D, const float* __restrict__ g, const float* __restrict__ b,
+                                        float eps, float* red) {
+  float s = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) s += vec[c];
+  const float mean = block_sum_256(s, red) / D;
+  float q = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) { const float d = vec[c] - mean; q += d * d; }
+  const float var = block_sum_256(q, red) / D;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) vec[c] = (vec[c] - mean) * rstd * g[c] + b[c];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+pool_norm_kernel(const float* __restrict__ x, float* __restrict__ pooled, const float* __restrict__ g1,
+                 const float* __restrict__ b1, float eps1, const float* __restrict__ g2,
+                 const float* __restrict__ b2, float eps2, int N, int D, int variant) {
+  extern __shared__ float sm[];  // [2*D + 8]
+  float* v0 = sm;
+  float* v1 = sm + D;
+  float* red = sm + 2 * D;
+  const float* xb = x + (size_t)blockIdx.x * N * D;
+  if (variant == TPAT_VARIANT_AUDIOMAE) {
+    // x[:, 1:, :].mean(dim=1) -> fc_norm   (models_vit.py:388-389)
+    const float inv = 1.0f / (float)(N - 1);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float s = 0.f;
+      for (int t = 1; t < N; ++t) s += __ldg(xb + (size_t)t * D + c);
+      v0[c] = s * inv;
+    }
+    __syncthreads();
+    block_layernorm_inplace(v0, D, g1, b1, eps1, red);
+  } else {
+    // v.norm on rows 0 (cls) and 1 (dist) -- LayerNorm is per row, the other rows are never
+    // read by the head -- average, then mlp_head[0] LayerNorm   (ast_models.py:500-503)
+    for (int c = threadIdx.x; c < D; c += blockDim.x) { v0[c] = xb[c]; v1[c] = xb[D + c]; }
+    __syncthreads();
+    block_layernorm_inplace(v0, D, g1, b1, eps1, red);
+    block_layernorm_inplace(v1, D, g1, b1, eps1, red);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) v0[c] = (v0[c] + v1[c]) / 2.0f;
+    __syncthreads();
+    block_layernorm_inplace(v0, D, g2, b2, eps2, red);
+  }
+  for (int c = threadIdx.x; c < D; c += blockDim.x) pooled[(size_t)blockIdx.x * D + c] = v0[c];
+}
+
+template <typename OutT>
+static int launch_layernorm(const float* x, const float* g, const float* b, OutT* y, int rows, int D, float eps,
+                            cudaStream_t st) {
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+#define TPAT_LN_CASE(nv) \
+  case nv: layernorm_kernel<nv, OutT><<<grid, 32 * LN_WARPS, 0, st>>>(x, g, b, y, rows, eps); break;
+  switch (D / 128) {
+    TPAT_LN_CASE(1) TPAT_LN_CASE(2) TPAT_LN_CASE(3) TPAT_LN_CASE(4) TPAT_LN_CASE(5) TPAT_LN_CASE(6)
+    TPAT_LN_CASE(8) TPAT_LN_CASE(10) TPAT_LN_CASE(12) TPAT_LN_CASE(16)
+    default: set_error("tpat_layernorm: unsupported D=%d", D); return 1;
+  }
+#undef TPAT_LN_CASE
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename OutT>
+static int launch_gather_ln(const float* x, const int64_t* idx, float* xo, const float* g, const float* b, OutT* yo,
+                            int B, int N_in, int k, int extra, int D, float eps, cudaStream_t st) {
+  const int rows = B * (extra + k);
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+#define TPAT_GLN_CASE(nv) \
+  case nv: gather_layernorm_kernel<nv, OutT><<<grid, 32 * LN_WARPS, 0, st>>>(x, idx, xo, g, b, yo, B, N_in, k, extra, eps); break;
+  switch (D / 128) {
+    TPAT_GLN_CASE(1) TPAT_GLN_CASE(2) TPAT_GLN_CASE(3) TPAT_GLN_CASE(4) TPAT_GLN_CASE(5) TPAT_GLN_CASE(6)
+    TPAT_GLN_CASE(8) TPAT_GLN_CASE(10) TPAT_GLN_CASE(12) TPAT_GLN_CASE(16)
+    default: set_error("tpat_gather_layernorm: unsupported D=%d", D); return 1;
+  }
+#undef TPAT_GLN_CASE
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tpat
+
+extern "C" int tpat_layernorm(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                              int rows, int D, float eps, tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(x && gamma && beta && y, "tpat_layernorm: null pointer");
+  TPAT_CHECK(rows >= 0 && D > 0 && D % 128 == 0 && D <= 2048, "tpat_layernorm: need D %% 128 == 0, D <= 2048 (D=%d)", D);
+  TPAT_CHECK(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "tpat_layernorm: pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  if (y_dtype == TPAT_F32) return launch_layernorm<float>(x, gamma, beta, (float*)y, rows, D, eps, as_stream(stream));
+  if (y_dtype == TPAT_BF16) return launch_layernorm<__nv_bfloat16>(x, gamma, beta, (__nv_bfloat16*)y, rows, D, eps, as_stream(stream));
+  set_error("tpat_layernorm: bad dtype %d", y_dtype);
+  return 1;
+}
+
+extern "C" int tpat_gather_layernorm(const float* x, const int64_t* topk_idx, float* x_out, const float* gamma,
+                                     const float* beta, void* y_out, int y_dtype, int B, int N_in, int k,
+                                     int num_extra, int D, float eps, tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(x && topk_idx && x_out, "tpat_gather_layernorm: null pointer");
+  TPAT_CHECK(y_out == nullptr || (gamma && beta), "tpat_gather_layernorm: y_out needs gamma and beta");
+  TPAT_CHECK(B >= 0 && k > 0 && num_extra >= 0 && num_extra + k <= N_in, "tpat_gather_layernorm: bad sizes N_in=%d k=%d extra=%d", N_in, k, num_extra);
+  TPAT_CHECK(D > 0 && D % 128 == 0 && D <= 2048, "tpat_gather_layernorm: unsupported D=%d", D);
+  TPAT_CHECK(x != x_out, "tpat_gather_layernorm: in-place compaction is not supported");
+  TPAT_CHECK(aligned16(x) && aligned16(x_out) && (y_out == nullptr || aligned16(y_out)), "tpat_gather_layernorm: pointers must be 16-byte aligned");
+  if (B == 0) return 0;
+  if (y_dtype == TPAT_F32) return launch_gather_ln<float>(x, topk_idx, x_out, gamma, beta, (float*)y_out, B, N_in, k, num_extra, D, eps, as_stream(stream));
+  if (y_dtype == TPAT_BF16) return launch_gather_ln<__nv_bfloat16>(x, topk_idx, x_out, gamma, beta, (__nv_bfloat16*)y_out, B, N_in, k, num_extra, D, eps, as_stream(stream));
+  set_error("tpat_gather_layernorm: bad dtype %d", y_dtype);
+  return 1;
+}
+
+extern "C" int tpat_pool_norm(const float* x, float* pooled, const float* g1, const float* b1, float eps1,
+                              const float* g2, const float* b2, float eps2, int B, int N, int D, int variant,
+                              tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(x && pooled && g1 && b1, "tpat_pool_norm: null pointer");
+  TPAT_CHECK(variant == TPAT_VARIANT_AUDIOMAE || variant == TPAT_VARIANT_AST, "tpat_pool_norm: bad variant %d", variant);
+  TPAT_CHECK(variant == TPAT_VARIANT_AUDIOMAE || (g2 && b2), "tpat_pool_norm: AST needs the mlp_head LayerNorm parameters");
+  TPAT_CHECK(B >= 0 && N >= 2 && D > 0 && D <= 4096, "tpat_pool_norm: bad sizes N=%d D=%d", N, D);
+  if (B == 0) return 0;
+  const size_t smem = (size_t)(2 * D + 8) * sizeof(float);
+  pool_norm_kernel<<<B, 256, smem, as_stream(stream)>>>(x, pooled, g1, b1, eps1, g2, b2, eps2, N, D, variant);
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,75 @@
+// Patch extraction for the 16x16 / stride-16 patch-embed conv + the cls/dist rows.
+//
+// Replaces the unfold half of PatchEmbed.forward (reference audiomae/models_vit.py:241-247,
+// ast/src/models/ast_models.py:36-42) and the extra-token assembly (models_vit.py:359-362,
+// ast_models.py:463-466).  HBM-bound: reads the fp32 spectrogram once (coalesced 512 B rows),
+// transposes 16 x F tiles through shared memory and writes the [B*P, 256] patch matrix with
+// fully coalesced 1 KB / 512 B rows.  Algorithmic bytes per clip (T=1024, F=128):
+// 512 KB read + 256 KB (bf16) or 512 KB (fp32) written.
+#include "common.cuh"
+
+namespace tpat {
+
+// One CTA per (clip, 16-frame time block).  smem tile [16][F + 1] fp32.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ spec, OutT* __restrict__ patches, float* __restrict__ tokens,
+                const float* __restrict__ extra_tok, const float* __restrict__ pos,
+                int T, int F, int D, int num_extra, int order) {
+  extern __shared__ float tile[];  // [16][F+1]
+  const int tb = blockIdx.x, b = blockIdx.y;
+  const int TB = T / 16, FB = F / 16, P = TB * FB;
+  const int ld = F + 1;
+  const float* src = spec + ((size_t)b * T + (size_t)tb * 16) * F;
+  // coalesced load: 16 rows x F floats, float4 per thread
+  const int nvec = 16 * F / 4;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const int r = (v * 4) / F, c = (v * 4) % F;
+    const float4 val = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * F + c));
+    float* d = tile + r * ld + c;
+    d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
+  }
+  __syncthreads();
+  // FB patches x 256 columns; consecutive threads -> consecutive columns (coalesced stores)
+  for (int o = threadIdx.x; o < FB * 256; o += blockDim.x) {
+    const int fb = o >> 8, col = o & 255;
+    int to, fo;
+    size_t row;
+    if (order == TPAT_TOKENS_TIME_MAJOR) {  // AudioMAE: conv over [T, F], kernel [t_off][f_off]
+      to = col >> 4; fo = col & 15;
+      row = (size_t)b * P + (size_t)tb * FB + fb;
+    } else {                                // AST: conv over [F, T], kernel [f_off][t_off]
+      fo = col >> 4; to = col & 15;
+      row = (size_t)b * P + (size_t)fb * TB + tb;
+    }
+    patches[row * 256 + col] = from_f32<OutT>(tile[to * ld + fb * 16 + fo]);
+  }
+  // extra-token rows of this clip: cls (+dist) + pos
+  if (tb == 0 && tokens != nullptr) {
+    float* dst = tokens + (size_t)b * (num_extra + P) * D;
+    for (int i = threadIdx.x; i < num_extra * D; i += blockDim.x) dst[i] = extra_tok[i] + pos[i];
+  }
+}
+
+}  // namespace tpat
+
+extern "C" int tpat_patchify(const float* spec, void* patches, int out_dtype, float* tokens,
+                             const float* extra_tok, const float* pos, int B, int T, int F, int D,
+                             int num_extra, int order, tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(spec && patches, "tpat_patchify: null pointer");
+  TPAT_CHECK(B > 0 && T > 0 && F > 0 && T % 16 == 0 && F % 16 == 0 && F <= 512,
+             "tpat_patchify: need T %% 16 == 0, F %% 16 == 0, F <= 512 (got B=%d T=%d F=%d)", B, T, F);
+  TPAT_CHECK(order == TPAT_TOKENS_TIME_MAJOR || order == TPAT_TOKENS_FREQ_MAJOR, "tpat_patchify: bad order %d", order);
+  TPAT_CHECK(out_dtype == TPAT_F32 || out_dtype == TPAT_BF16, "tpat_patchify: bad dtype %d", out_dtype);
+  TPAT_CHECK(tokens == nullptr || (extra_tok && pos && num_extra >= 0), "tpat_patchify: tokens needs extra_tok and pos");
+  TPAT_CHECK(aligned16(spec), "tpat_patchify: spec must be 16-byte aligned");
+  dim3 grid(T / 16, B);
+  const size_t smem = (size_t)16 * (F + 1) * sizeof(float);
+  if (out_dtype == TPAT_F32)
+    patchify_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(spec, (float*)patches, tokens, extra_tok, pos, T, F, D, num_extra, order);
+  else
+    patchify_kernel<__nv_bfloat16><<<grid, 256, smem, as_stream(stream)>>>(spec, (__nv_bfloat16*)patches, tokens, extra_tok, pos, T, F, D, num_extra, order);
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,101 @@
+"""ctypes binding of libtpat.so (the C-ABI declared in include/tpat.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing and cannot be built the
+import fails, and every compute call raises ``RuntimeError(tpat_last_error())`` on a non-zero
+status.
+"""
+import ctypes
+import os
+import sys
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libtpat.so")
+
+TPAT_MAX_DEPTH = 32
+F32, BF16 = 0, 1
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_POS = 0, 1, 2, 3
+IMPL_SIMT, IMPL_TC = 0, 1
+SCORE_NONE, SCORE_CLS_ROW, SCORE_COLMEAN = 0, 1, 2
+TOKENS_TIME_MAJOR, TOKENS_FREQ_MAJOR = 0, 1
+VARIANT_AUDIOMAE, VARIANT_AST = 0, 1
+
+
+class BlockWeights(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class ForwardArgs(Structure):
+    _fields_ = [
+        ("variant", c_int), ("impl", c_int), ("B", c_int), ("T", c_int), ("F", c_int),
+        ("depth", c_int), ("D", c_int), ("H", c_int), ("Dh", c_int), ("num_classes", c_int),
+        ("prune", c_int * TPAT_MAX_DEPTH), ("keep", c_int * TPAT_MAX_DEPTH),
+        ("want_all_scores", c_int), ("ln_eps", c_float),
+        ("patch_w", c_void_p), ("patch_b", c_void_p), ("extra_tok", c_void_p), ("pos", c_void_p),
+        ("blocks", BlockWeights * TPAT_MAX_DEPTH),
+        ("norm_g", c_void_p), ("norm_b", c_void_p), ("norm_eps", c_float),
+        ("head_ln_g", c_void_p), ("head_ln_b", c_void_p), ("head_ln_eps", c_float),
+        ("head_w", c_void_p), ("head_b", c_void_p),
+        ("spec", c_void_p), ("logits", c_void_p),
+        ("scores", c_void_p * TPAT_MAX_DEPTH), ("topk_idx", c_void_p * TPAT_MAX_DEPTH),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
+# every symbol include/tpat.h declares: (restype, argtypes)
+SIGNATURES = {
+    "tpat_version": (c_int, []),
+    "tpat_last_error": (c_char_p, []),
+    "tpat_device_ok": (c_int, []),
+    "tpat_patchify": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_void_p]),
+    "tpat_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "tpat_gemm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                          c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_attention_qtiles": (c_int, [c_int, c_int]),
+    "tpat_attention": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                               c_int, c_void_p]),
+    "tpat_score_topk": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_gather_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                      c_int, c_int, c_int, c_float, c_void_p]),
+    "tpat_pool_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int,
+                               c_int, c_int, c_int, c_void_p]),
+    "tpat_sizeof_forward_args": (c_size_t, []),
+    "tpat_forward_workspace_bytes": (c_size_t, [POINTER(ForwardArgs)]),
+    "tpat_forward": (c_int, [POINTER(ForwardArgs), c_void_p]),
+    "tpat_forward_launch_count": (c_int, [POINTER(ForwardArgs)]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        sys.path.insert(0, _PKG_ROOT)
+        try:
+            import build as _build  # token-pruning-audio-transformer_b200/build.py
+            _build.build(verbose=False)
+        finally:
+            sys.path.pop(0)
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing and could not be built; there is no fallback path")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = the .so does not export what tpat.h declares
+        fn.restype = res
+        fn.argtypes = args
+    if lib.tpat_sizeof_forward_args() != ctypes.sizeof(ForwardArgs):
+        raise ImportError("ForwardArgs layout does not match the tpat_forward_args compiled into libtpat.so")
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    msg = lib.tpat_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        raise RuntimeError(f"libtpat {what} failed (status {status}): {last_error()}")

@@ -1,0 +1,210 @@
+"""Drop-in mirror of the reference's AST pruning model API (ast/src/models/ast_models.py).
+
+Same constructor signature, attribute names (``.v.blocks[i].attn.default_keep_rate`` ...) and
+state-dict keys (``v.cls_token, v.dist_token, v.pos_embed, v.patch_embed.proj.*, v.blocks.*,
+v.norm.*, v.head*, v.head_dist*, mlp_head.0.*, mlp_head.1.*``) as the reference; the forward is
+one ``tpat_forward`` call into libtpat.so (AST flavour: two extra tokens, frequency-major token
+order, CLS-row importance score -- SURVEY.md F2/F11/F12/F13).
+
+    model = ASTModel(label_dim=527, input_tdim=1024, imagenet_pretrain=False, audioset_pretrain=False,
+                     drop_loc=(3, 6, 9), base_keep_rate=0.7)
+    logits = model(x)                                     # x [B, T, 128] on a B200
+    logits, feats = model(x, flag_extract_features=True)
+
+Stated differences: the reference needs ``timm==0.4.5`` for the DeiT skeleton and, with
+``imagenet_pretrain=True``, a network download of DeiT weights; neither exists here, so the
+skeleton is built locally and ``imagenet_pretrain=True`` raises -- load a checkpoint with
+``load_state_dict`` instead.  ``@autocast`` (ast_models.py:424) is replaced by the explicit
+``precision`` attribute ("bf16" tensor-core kernels / "fp32" parity kernels).  Inference only in
+this round; custom_rank / drop_token_blk_idx raise NotImplementedError.
+"""
+import os
+from functools import partial
+from typing import Optional, Union
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .engine import ForwardEngine, resolve_precision
+from .models_vit import Block, PatchEmbed, block_tensors, resolve_keep_rates, trunc_normal_
+
+
+class _DeiTDistilledSkeleton(nn.Module):
+    """The attribute / parameter layout timm 0.4.5 gives ``vit_deit_base_distilled_patch16_384``
+    (only what ASTModel touches: ast_models.py:273-330,395-409)."""
+
+    def __init__(self, embed_dim=768, depth=12, num_heads=12, drop_path_rate=0.0):
+        super().__init__()
+        self.patch_embed = PatchEmbed(img_size=384, patch_size=16, in_chans=3, embed_dim=embed_dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.dist_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.patch_embed.num_patches + 2, embed_dim))
+        self.pos_drop = nn.Dropout(p=0.0)
+        norm_layer = partial(nn.LayerNorm, eps=1e-6)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]
+        self.blocks = nn.ModuleList([
+            Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=4.0, qkv_bias=True, drop_path=dpr[i],
+                  norm_layer=norm_layer, block_id=i) for i in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.head = nn.Linear(embed_dim, 1000)        # unused by the AST forward; kept for checkpoint keys
+        self.head_dist = nn.Linear(embed_dim, 1000)   # unused by the AST forward; kept for checkpoint keys
+        trunc_normal_(self.cls_token, std=.02)
+        trunc_normal_(self.dist_token, std=.02)
+        trunc_normal_(self.pos_embed, std=.02)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+
+class ASTModel(nn.Module):
+    """The AST model with TopK token pruning (reference ast_models.py:239-508), computed by libtpat.so.
+
+    :param label_dim: number of classes (527 AudioSet, 50 ESC-50, 35 Speech Commands v2)
+    :param fstride, tstride: must be 16 (reference asserts the same, ast_models.py:258)
+    :param input_fdim, input_tdim: mel bins / time frames of the input spectrogram
+    :param drop_loc, base_keep_rate: pruning blocks (0-indexed) and their default keep rate
+    """
+
+    def __init__(self, label_dim=527, fstride=16, tstride=16, input_fdim=128, input_tdim=1024, imagenet_pretrain=True,
+                 audioset_pretrain=False, model_size='base384', verbose=True, depth=12,
+                 audioset_pretrained_model_path: str = None, drop_path_rate=0.0, drop_loc: tuple = None,
+                 base_keep_rate: tuple = None, precision: Optional[str] = None):
+        super().__init__()
+        assert fstride == 16 and tstride == 16, 'Currently only support fstride=16 and tstride=16.'
+        if verbose:
+            print('---------------AST Model Summary---------------')
+            print('ImageNet pretraining: {:s}, AudioSet pretraining: {:s}'.format(str(imagenet_pretrain), str(audioset_pretrain)))
+        if model_size != 'base384':
+            raise Exception('We only support base384.')
+        f_dim, t_dim = self.get_shape(fstride, tstride, input_fdim, input_tdim)
+        num_patches = f_dim * t_dim
+
+        if audioset_pretrain == False:
+            if imagenet_pretrain:
+                raise RuntimeError("imagenet_pretrain=True needs timm's DeiT download, which is unavailable offline; "
+                                   "build with imagenet_pretrain=False and load a checkpoint with load_state_dict")
+            self.v = _DeiTDistilledSkeleton(drop_path_rate=drop_path_rate)
+            self.original_num_patches = self.v.patch_embed.num_patches
+            self.oringal_hw = int(self.original_num_patches ** 0.5)
+            self.original_embedding_dim = self.v.pos_embed.shape[2]
+            self.mlp_head = nn.Sequential(nn.LayerNorm(self.original_embedding_dim),
+                                          nn.Linear(self.original_embedding_dim, label_dim))
+            self.v.patch_embed.num_patches = num_patches
+            if verbose:
+                print('frequncey stride={:d}, time stride={:d}'.format(fstride, tstride))
+                print('number of patches={:d}'.format(num_patches))
+            # 1-channel projection (ast_models.py:301-305) and a fresh learnable pos-embed (:326-330)
+            self.v.patch_embed.proj = torch.nn.Conv2d(1, self.original_embedding_dim, kernel_size=(16, 16),
+                                                      stride=(fstride, tstride))
+            self.v.pos_embed = nn.Parameter(torch.zeros(1, num_patches + 2, self.original_embedding_dim))
+            trunc_normal_(self.v.pos_embed, std=.02)
+        else:
+            if imagenet_pretrain == False:
+                raise ValueError('currently model pretrained on only audioset is not supported, please set '
+                                 'imagenet_pretrain = True to use audioset pretrained model.')
+            if audioset_pretrained_model_path is None or not os.path.exists(audioset_pretrained_model_path):
+                raise FileNotFoundError(f"audioset_pretrained_model_path={audioset_pretrained_model_path!r} not found")
+            sd = torch.load(audioset_pretrained_model_path, map_location='cpu')
+            sd = {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in sd.items()}  # DataParallel prefix
+            base = ASTModel(label_dim=527, fstride=16, tstride=16, input_fdim=128, input_tdim=1024,
+                            imagenet_pretrain=False, audioset_pretrain=False, model_size=model_size, verbose=False,
+                            drop_loc=drop_loc, base_keep_rate=base_keep_rate, precision=precision)
+            base.load_state_dict(sd, strict=True)
+            self.v = base.v
+            self.original_embedding_dim = self.v.pos_embed.shape[2]
+            self.mlp_head = nn.Sequential(nn.LayerNorm(self.original_embedding_dim),
+                                          nn.Linear(self.original_embedding_dim, label_dim))
+            self.v.patch_embed.num_patches = num_patches
+            if verbose:
+                print('frequncey stride={:d}, time stride={:d}'.format(fstride, tstride))
+                print('number of patches={:d}'.format(num_patches))
+            # crop the AudioSet (8 x 64) positional embedding in time (ast_models.py:369-388)
+            new_pos_embed = self.v.pos_embed[:, 2:, :].detach().reshape(1, 512, 768).transpose(1, 2).reshape(1, 768, 8, 64)
+            if t_dim < 64:
+                new_pos_embed = new_pos_embed[:, :, :, 32 - int(t_dim / 2): 32 - int(t_dim / 2) + t_dim]
+            elif t_dim > 64:
+                raise ValueError(f'{t_dim=} > 64')
+            assert f_dim == 8
+            new_pos_embed = new_pos_embed.reshape(1, 768, num_patches).transpose(1, 2)
+            self.v.pos_embed = nn.Parameter(torch.cat([self.v.pos_embed[:, :2, :].detach(), new_pos_embed], dim=1))
+
+        # TopK wiring (ast_models.py:391-412)
+        self.use_custom_rank = None
+        self.drop_token_blk_idx = None
+        self.retain_min = None
+        self.retain_max = None
+        assert depth == len(self.v.blocks), "the DeiT-base skeleton has 12 blocks"
+        self.depth = depth
+        self.num_extra_tokens = 2
+        self.num_heads = 12
+        keep_rate_list = [1.0] * depth
+        for drop_loc_idx in (drop_loc or ()):
+            keep_rate_list[drop_loc_idx] = base_keep_rate
+        for blk_id in range(depth):
+            self.v.blocks[blk_id].attn.num_extra_tokens = 2
+            self.v.blocks[blk_id].attn.block_id = blk_id
+            self.v.blocks[blk_id].attn.default_keep_rate = keep_rate_list[blk_id]
+            self.v.blocks[blk_id].block_id = blk_id
+            self.v.blocks[blk_id].num_extra_tokens = 2
+
+        self.label_dim = label_dim
+        self.precision = resolve_precision(precision)
+        self.use_cuda_graph = False
+        self._engine = ForwardEngine(_lib.VARIANT_AST, depth, 768, 12, 3072)
+        self.last_scores = None
+        self.last_topk_idx = None
+
+    def get_shape(self, fstride, tstride, input_fdim=128, input_tdim=1024):
+        """Output grid of the 16x16 conv (ast_models.py:416-422), computed arithmetically."""
+        f_dim = (input_fdim - 16) // fstride + 1
+        t_dim = (input_tdim - 16) // tstride + 1
+        return f_dim, t_dim
+
+    def _engine_tensors(self):
+        v = self.v
+        return {
+            "patch_w": v.patch_embed.proj.weight, "patch_b": v.patch_embed.proj.bias,
+            "extra_tok": torch.cat([v.cls_token.detach(), v.dist_token.detach()], dim=1),
+            "pos": v.pos_embed,
+            "blocks": [block_tensors(b) for b in v.blocks[:self.depth]],
+            "norm_g": v.norm.weight, "norm_b": v.norm.bias,
+            "head_ln_g": self.mlp_head[0].weight, "head_ln_b": self.mlp_head[0].bias,
+            "head_w": self.mlp_head[1].weight, "head_b": self.mlp_head[1].bias,
+        }
+
+    def _pack_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def forward(self, x, keep_rate_list: Union[list, tuple, type(None)] = None, flag_extract_features: bool = False):
+        """x [B, time_frame_num, frequency_bins], e.g. (12, 1024, 128) (ast_models.py:431)."""
+        if (keep_rate_list is not None) and (len(keep_rate_list) != len(self.v.blocks)):
+            raise ValueError(f"keep_rate should be a list/tuple of length {len(self.v.blocks)}, got {keep_rate_list}")
+        if self.use_custom_rank is not None or self.drop_token_blk_idx is not None:
+            raise NotImplementedError("custom_rank / drop_token_blk_idx ablation paths are not built yet (SURVEY a12)")
+        B, T, F = x.shape
+        n_patches = (T // 16) * (F // 16)
+        if self.v.pos_embed.shape[1] != n_patches + 2:
+            raise RuntimeError(f"pos_embed has {self.v.pos_embed.shape[1]} rows but the input has {n_patches} patches + 2")
+        rates = resolve_keep_rates(keep_rate_list, self.v.blocks)
+        self._engine.pack(self._engine_tensors, self._pack_key())
+        logits, scores, idxs = self._engine.run(x, rates, self.label_dim, want_all_scores=flag_extract_features,
+                                                precision=self.precision, use_graph=self.use_cuda_graph)
+        self.last_scores, self.last_topk_idx = scores, idxs
+        if flag_extract_features:
+            feature_dict = {'mel': x.unsqueeze(1).transpose(2, 3).cpu()}      # ast_models.py:434-439
+            for i in range(self.depth):
+                if scores[i] is not None:
+                    feature_dict[f'block-{i}.attn_score'] = scores[i].cpu()
+                if idxs[i] is not None:
+                    feature_dict[f'block-{i}.topk_idx'] = idxs[i].cpu()
+            return logits, feature_dict
+        return logits

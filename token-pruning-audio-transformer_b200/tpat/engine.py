@@ -1,0 +1,202 @@
+"""Host-side driver of ``tpat_forward``: weight packing, workspace, pruning schedule, CUDA graphs.
+
+The model classes (models_vit.VisionTransformer, ast_models.ASTModel) keep their parameters as
+ordinary ``nn.Parameter``s under the reference's state-dict names; this engine reads them,
+keeps bf16 copies of the matrices for the tensor-core path, fills the C ``tpat_forward_args``
+struct and makes ONE native call per forward.
+"""
+import ctypes
+import math
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ForwardArgs, check, lib
+
+PRECISIONS = ("bf16", "fp32")
+
+
+def resolve_precision(p: Optional[str]) -> str:
+    p = p or os.environ.get("TPAT_PRECISION", "bf16")
+    if p not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {p!r}")
+    return p
+
+
+def pruning_schedule(n_patches: int, num_extra: int, keep_rates: Sequence[float]) -> Tuple[List[int], List[int]]:
+    """(prune flags, non-extra tokens leaving each block), following the reference exactly:
+    ``num_left_tokens = math.ceil(keep_rate * (N - num_extra_tokens))`` in Python double arithmetic
+    and top-k only ``if keep_rate < 1.0`` (models_vit.py:104-110; ast_models.py:116-121)."""
+    prune, keep, cur = [], [], n_patches
+    for kr in keep_rates:
+        N = cur + num_extra
+        k = math.ceil(kr * (N - num_extra))
+        assert k > 0, "num_left_tokens should be at least 1"      # models_vit.py:106
+        if kr < 1.0:
+            prune.append(1)
+            cur = k
+        else:
+            prune.append(0)
+        keep.append(cur)
+    return prune, keep
+
+
+class ForwardEngine:
+    """One instance per model.  ``tensors`` maps a small fixed vocabulary of names to device tensors:
+    patch_w [D,1,16,16], patch_b, extra_tok [extra,D], pos [extra+P,D], blocks[i].{ln1_g,...},
+    norm_g/norm_b, head_ln_g/head_ln_b (AST), head_w, head_b."""
+
+    def __init__(self, variant: int, depth: int, D: int, H: int, Dh: int):
+        if depth > _lib.TPAT_MAX_DEPTH:
+            raise ValueError(f"depth {depth} exceeds TPAT_MAX_DEPTH={_lib.TPAT_MAX_DEPTH}")
+        self.variant, self.depth, self.D, self.H, self.Dh = variant, depth, D, H, Dh
+        self.num_extra = 2 if variant == _lib.VARIANT_AST else 1
+        self._pack_key = None
+        self._packed: Dict[str, object] = {}
+        self._bf16: Dict[int, torch.Tensor] = {}
+        self._workspace: Optional[torch.Tensor] = None
+        self._graphs: Dict[tuple, tuple] = {}
+        self.last_launch_count = 0
+
+    # ---- weights -------------------------------------------------------------------------
+    @staticmethod
+    def _f32(t: torch.Tensor) -> torch.Tensor:
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        return t
+
+    def pack(self, tensors_fn, key) -> None:
+        """(Re)build the device-side weight views when ``key`` (data pointers + versions) changed.
+        ``tensors_fn`` is only called on a miss."""
+        if key == self._pack_key:
+            return
+        tensors = tensors_fn()
+        f = self._f32
+        pk: Dict[str, object] = {}
+        pk["patch_w"] = f(tensors["patch_w"]).reshape(self.D, 256)
+        pk["patch_b"] = f(tensors["patch_b"])
+        pk["extra_tok"] = f(tensors["extra_tok"]).reshape(self.num_extra, self.D).contiguous()
+        pk["pos"] = f(tensors["pos"]).reshape(-1, self.D)
+        pk["blocks"] = [{k: f(v) for k, v in blk.items()} for blk in tensors["blocks"]]
+        for k in ("norm_g", "norm_b", "head_ln_g", "head_ln_b", "head_w", "head_b"):
+            pk[k] = f(tensors[k]) if tensors.get(k) is not None else None
+        self._packed = pk
+        self._bf16 = {}
+        self._graphs = {}
+        self._pack_key = key
+
+    def _mat(self, t: torch.Tensor, impl: int) -> torch.Tensor:
+        if impl == _lib.IMPL_SIMT:
+            return t
+        c = self._bf16.get(id(t))
+        if c is None:
+            c = t.to(torch.bfloat16).contiguous()
+            self._bf16[id(t)] = c
+        return c
+
+    # ---- one forward ---------------------------------------------------------------------
+    def _fill_args(self, spec, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, workspace):
+        pk = self._packed
+        a = ForwardArgs()
+        a.variant, a.impl = self.variant, impl
+        a.B, a.T, a.F = spec.shape
+        a.depth, a.D, a.H, a.Dh, a.num_classes = self.depth, self.D, self.H, self.Dh, num_classes
+        for i in range(self.depth):
+            a.prune[i], a.keep[i] = prune[i], keep[i]
+        a.want_all_scores = 1 if want_all_scores else 0
+        a.ln_eps = 1e-6
+        a.patch_w = self._mat(pk["patch_w"], impl).data_ptr()
+        a.patch_b = pk["patch_b"].data_ptr()
+        a.extra_tok = pk["extra_tok"].data_ptr()
+        a.pos = pk["pos"].data_ptr()
+        for i, blk in enumerate(pk["blocks"]):
+            bw = a.blocks[i]
+            for name in ("ln1_g", "ln1_b", "qkv_b", "proj_b", "ln2_g", "ln2_b", "fc1_b", "fc2_b"):
+                setattr(bw, name, blk[name].data_ptr())
+            for name in ("qkv_w", "proj_w", "fc1_w", "fc2_w"):
+                setattr(bw, name, self._mat(blk[name], impl).data_ptr())
+        a.norm_g, a.norm_b, a.norm_eps = pk["norm_g"].data_ptr(), pk["norm_b"].data_ptr(), 1e-6
+        if pk["head_ln_g"] is not None:
+            a.head_ln_g, a.head_ln_b, a.head_ln_eps = pk["head_ln_g"].data_ptr(), pk["head_ln_b"].data_ptr(), 1e-5
+        a.head_w, a.head_b = pk["head_w"].data_ptr(), pk["head_b"].data_ptr()
+        a.spec, a.logits = spec.data_ptr(), logits.data_ptr()
+        for i in range(self.depth):
+            a.scores[i] = scores[i].data_ptr() if scores[i] is not None else None
+            a.topk_idx[i] = idxs[i].data_ptr() if idxs[i] is not None else None
+        if workspace is not None:
+            a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+        return a
+
+    def _alloc_outputs(self, spec, prune, keep, want_all_scores, num_classes):
+        B, T, F = spec.shape
+        dev = spec.device
+        logits = torch.empty(B, num_classes, device=dev, dtype=torch.float32)
+        scores: List[Optional[torch.Tensor]] = [None] * self.depth
+        idxs: List[Optional[torch.Tensor]] = [None] * self.depth
+        cur = (T // 16) * (F // 16)
+        for i in range(self.depth):
+            if prune[i] or want_all_scores:
+                scores[i] = torch.empty(B, cur, device=dev, dtype=torch.float32)
+            if prune[i]:
+                idxs[i] = torch.empty(B, keep[i], device=dev, dtype=torch.int64)
+            cur = keep[i]
+        return logits, scores, idxs
+
+    def _ensure_workspace(self, args: ForwardArgs, device) -> torch.Tensor:
+        need = lib.tpat_forward_workspace_bytes(ctypes.byref(args))
+        if need == 0:
+            raise RuntimeError(f"libtpat tpat_forward_workspace_bytes failed: {_lib.last_error()}")
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != device:
+            self._workspace = torch.empty(need, device=device, dtype=torch.uint8)
+            self._graphs = {}
+        return self._workspace
+
+    def run(self, spec: torch.Tensor, keep_rates: Sequence[float], num_classes: int, want_all_scores: bool = False,
+            precision: str = "bf16", use_graph: bool = False):
+        """spec [B,T,F] fp32 CUDA.  Returns (logits [B,C], scores list, topk_idx list) -- device tensors."""
+        if not spec.is_cuda:
+            raise RuntimeError("tpat: input must be a CUDA tensor; there is no CPU path")
+        if not lib.tpat_device_ok():
+            raise RuntimeError("tpat: the current device is not compute capability 10.x (B200, sm_100a)")
+        if spec.dtype != torch.float32 or not spec.is_contiguous():
+            spec = spec.float().contiguous()
+        impl = _lib.IMPL_TC if precision == "bf16" else _lib.IMPL_SIMT
+        B, T, F = spec.shape
+        prune, keep = pruning_schedule((T // 16) * (F // 16), self.num_extra, keep_rates)
+        if use_graph:
+            return self._run_graph(spec, prune, keep, want_all_scores, impl, num_classes)
+        logits, scores, idxs = self._alloc_outputs(spec, prune, keep, want_all_scores, num_classes)
+        args = self._fill_args(spec, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, None)
+        ws = self._ensure_workspace(args, spec.device)
+        args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        self.last_launch_count = lib.tpat_forward_launch_count(ctypes.byref(args))
+        check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
+        return logits, scores, idxs
+
+    def _run_graph(self, spec, prune, keep, want_all_scores, impl, num_classes):
+        key = (tuple(spec.shape), tuple(prune), tuple(keep), bool(want_all_scores), impl, num_classes, spec.device.index)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = torch.empty_like(spec)
+            static_in.copy_(spec)
+            logits, scores, idxs = self._alloc_outputs(spec, prune, keep, want_all_scores, num_classes)
+            args = self._fill_args(static_in, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, None)
+            ws = self._ensure_workspace(args, spec.device)
+            args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+            self.last_launch_count = lib.tpat_forward_launch_count(ctypes.byref(args))
+            # warm-up outside capture (function attributes, tensor-map cache), then capture
+            check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
+            ent = (g, static_in, logits, scores, idxs, ws)
+            self._graphs[key] = ent
+        g, static_in, logits, scores, idxs, _ = ent
+        static_in.copy_(spec)
+        g.replay()
+        return (logits.clone(), [None if s is None else s.clone() for s in scores],
+                [None if t is None else t.clone() for t in idxs])

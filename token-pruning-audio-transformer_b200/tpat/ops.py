@@ -1,0 +1,127 @@
+"""Per-kernel Python wrappers over the C-ABI (torch tensors in, torch tensors out).
+
+torch is used for device memory and the current stream only; every computation happens in
+libtpat.so.  These wrappers exist so that each kernel can be parity-tested in isolation and so
+that a caller can assemble a forward by hand; the model classes use ``engine.ForwardEngine``
+(one native call per forward) instead.
+"""
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: libtpat has no CPU path")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def patchify(spec: torch.Tensor, out_dtype: torch.dtype, order: int, tokens: Optional[torch.Tensor] = None,
+             extra_tok: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """spec [B,T,F] fp32 -> patch matrix [B*P, 256]; optionally fills the extra rows of ``tokens``."""
+    _req(spec, torch.float32, "spec")
+    B, T, F = spec.shape
+    P = (T // 16) * (F // 16)
+    patches = torch.empty(B * P, 256, device=spec.device, dtype=out_dtype)
+    D = tokens.shape[-1] if tokens is not None else 0
+    extra = extra_tok.shape[0] if extra_tok is not None else 0
+    check(lib.tpat_patchify(spec.data_ptr(), patches.data_ptr(), _DT[out_dtype], _ptr(tokens), _ptr(extra_tok), _ptr(pos),
+                            B, T, F, D, extra, order, _stream()), "tpat_patchify")
+    return patches
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype) -> torch.Tensor:
+    _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    check(lib.tpat_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _DT[out_dtype], rows, D,
+                             float(eps), _stream()), "tpat_layernorm")
+    return y
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dtype: torch.dtype, epilogue: int = 0,
+         impl: int = _lib.IMPL_SIMT, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         pos: Optional[torch.Tensor] = None, P: int = 0, num_extra: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T + bias).  a [M,K], w [N,K] (nn.Linear layout)."""
+    _req(a, name="a"); _req(w, a.dtype, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        rows = M if epilogue != _lib.EPI_BIAS_POS else (M // P) * (P + num_extra)
+        out = torch.empty(rows, N, device=a.device, dtype=out_dtype)
+    _req(out, out_dtype, "out")
+    if residual is not None:
+        _req(residual, torch.float32, "residual")
+    check(lib.tpat_gemm(a.data_ptr(), _DT[a.dtype], K, w.data_ptr(), _DT[w.dtype], _ptr(bias), out.data_ptr(),
+                        _DT[out_dtype], N, _ptr(residual), N if residual is not None else 0, _ptr(pos), P, num_extra,
+                        M, N, K, epilogue, impl, _stream()), "tpat_gemm")
+    return out
+
+
+def attention_qtiles(N: int, impl: int) -> int:
+    return lib.tpat_attention_qtiles(N, impl)
+
+
+def attention(qkv: torch.Tensor, B: int, N: int, H: int, num_extra: int, score_mode: int, impl: int):
+    """qkv [B*N, 3*H*64] -> (out [B*N, H*64], score_partial or None)."""
+    _req(qkv, name="qkv")
+    out = torch.empty(B * N, H * 64, device=qkv.device, dtype=qkv.dtype)
+    partial = None
+    if score_mode == _lib.SCORE_CLS_ROW:
+        partial = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32)
+    elif score_mode == _lib.SCORE_COLMEAN:
+        partial = torch.empty(B, H * attention_qtiles(N, impl), N, device=qkv.device, dtype=torch.float32)
+    check(lib.tpat_attention(qkv.data_ptr(), out.data_ptr(), _DT[qkv.dtype], _ptr(partial), score_mode, B, N, H, 64,
+                             num_extra, 64 ** -0.5, impl, _stream()), "tpat_attention")
+    return out, partial
+
+
+def score_topk(partial: torch.Tensor, divisor: float, num_extra: int, k: int):
+    """partial [B,R,N] -> (score [B,N-extra] fp32, topk_idx [B,k] int64 or None)."""
+    _req(partial, torch.float32, "partial")
+    B, R, N = partial.shape
+    score = torch.empty(B, N - num_extra, device=partial.device, dtype=torch.float32)
+    idx = torch.empty(B, k, device=partial.device, dtype=torch.int64) if k > 0 else None
+    check(lib.tpat_score_topk(partial.data_ptr(), R, float(divisor), score.data_ptr(), _ptr(idx), B, N, num_extra, k,
+                              _stream()), "tpat_score_topk")
+    return score, idx
+
+
+def gather_layernorm(x: torch.Tensor, idx: torch.Tensor, num_extra: int, gamma: Optional[torch.Tensor],
+                     beta: Optional[torch.Tensor], eps: float, out_dtype: torch.dtype):
+    """x [B,N,D] fp32, idx [B,k] -> (x_out [B,extra+k,D] fp32, LayerNorm(x_out) or None)."""
+    _req(x, torch.float32, "x"); _req(idx, torch.int64, "idx")
+    B, N, D = x.shape
+    k = idx.shape[1]
+    xo = torch.empty(B, num_extra + k, D, device=x.device, dtype=torch.float32)
+    yo = torch.empty(B, num_extra + k, D, device=x.device, dtype=out_dtype) if gamma is not None else None
+    check(lib.tpat_gather_layernorm(x.data_ptr(), idx.data_ptr(), xo.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(yo),
+                                    _DT[out_dtype], B, N, k, num_extra, D, float(eps), _stream()), "tpat_gather_layernorm")
+    return xo, yo
+
+
+def pool_norm(x: torch.Tensor, variant: int, g1, b1, eps1: float, g2=None, b2=None, eps2: float = 0.0) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    B, N, D = x.shape
+    out = torch.empty(B, D, device=x.device, dtype=torch.float32)
+    check(lib.tpat_pool_norm(x.data_ptr(), out.data_ptr(), g1.data_ptr(), b1.data_ptr(), float(eps1), _ptr(g2), _ptr(b2),
+                             float(eps2), B, N, D, variant, _stream()), "tpat_pool_norm")
+    return out
