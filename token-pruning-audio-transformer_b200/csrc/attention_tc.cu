@@ -2,50 +2,53 @@
 //
 // Replaces q k^T * scale, softmax, attn @ v and the score slice/mean over the materialised
 // [B,H,N,N] matrix (reference audiomae/models_vit.py:79-95,113; ast/src/models/ast_models.py:92-109,124).
-// One CTA per (clip, head, 128-query tile); 192 threads:
-//   warp 0   TMA producer: Q tile once, then K / V 128-key tiles into a 4-slot 16 KB ring
-//            (3-D tensor map over qkv[B][N][3*H*64]: rows >= N are zero-filled, never the next clip)
-//   warp 1   MMA issuer (one elected thread): S = Q K^T (M=128,N=128,K=64) into one of two TMEM
-//            buffers; O += P V (M=128,N=64,K=128) with P from 128B-swizzled smem, V as MN-major B
-//   warps 2-5 softmax: thread = query row = TMEM lane.
+// One CTA per (clip, head, 128-query tile), two CTAs resident per SM (<= 113 KB smem, 256 TMEM
+// columns each) so one CTA's softmax hides the other's prologue / MMA round trips.  192 threads:
+//   warp 0   TMA producer: Q tile once, then K / V 64-key tiles into a 6-slot 8 KB ring
+//            (3-D tensor maps over qkv[B][N][3*H*64]: rows >= N are zero-filled, never the next clip)
+//   warp 1   MMA issuer (one elected thread): S = Q K^T (M=128,N=64,K=64) into one of two TMEM
+//            buffers; O += P V (M=128,N=64,K<=64) with P from 128B-swizzled smem, V as MN-major B
+//   warps 2-5 softmax: thread = query row = TMEM lane; 64 scores per thread per key block.
 // Exact softmax in two passes over the keys (the score needs the final row normaliser before
 // any column can be accumulated):
-//   pass 1  S -> running row max (and, when a score is requested, the running sum of exp)
-//   pass 2  S recomputed -> P = exp(s - max) [/ sum] in fp32 -> score partials (fp32, warp
-//           transpose-reduce, fixed order, no atomics) -> bf16 P -> O += P V
-// Without a score request pass 1 tracks the max only and O is divided by the row sum at the end,
-// so each element costs one exp.  The N x N matrix never leaves the SM.
+//   pass 1  S -> running row max (+ running sum of exp only in warps that must emit normalised P)
+//   pass 2  S recomputed -> P = 2^(s*c - m*c - log2 l) in fp32 (one FFMA + one MUFU.EX2 per element)
+//           -> score partials (fp32 warp transpose-reduce, fixed order, no atomics) -> bf16 P -> O += P V
+// Warps that do not emit scores track the max only in pass 1, use unnormalised P and divide O by
+// the row sum at the end.  The N x N matrix never leaves the SM; O leaves through one TMA store.
 #include "attention.cuh"
 #include "ptx_sm100.cuh"
 
 namespace tpat {
 
-int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld);
+int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld, int box_rows);
 
 constexpr int AT_BM = 128;          // queries per CTA
-constexpr int AT_BK = 128;          // keys per block
+constexpr int AT_BK = 64;           // keys per block
 constexpr int AT_HD = 64;
-constexpr int AT_SLOTS = 4;         // K/V ring slots
-constexpr int AT_TILE_BYTES = 128 * 64 * 2;    // 16 KB: Q, K, V tiles and each 64-key half of P
-constexpr int AT_P_BYTES = 2 * AT_TILE_BYTES;  // 32 KB
+constexpr int AT_SLOTS = 6;         // K/V ring slots
+constexpr int AT_Q_BYTES = AT_BM * AT_HD * 2;    // 16 KB (also one P buffer / the O staging tile)
+constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;   // 8 KB
+constexpr int AT_P_BYTES = AT_BM * AT_BK * 2;    // 16 KB
 constexpr int AT_THREADS = 192;
+constexpr int AT_TMEM_COLS = 256;   // S0 [0,64) S1 [64,128) O [128,192)
 
 struct AttnTcParams {
-  __nv_bfloat16* out;
   float* score_partial;
   int score_mode;
   int N, H, num_extra, n_qt, nb;
   float scale_log2;  // scale * log2(e)
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcParams p) {
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                    const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;                                   // 16 KB
-  uint8_t* kv_s = q_s + AT_TILE_BYTES;                   // AT_SLOTS x 16 KB
-  uint8_t* p_s = kv_s + AT_SLOTS * AT_TILE_BYTES;        // 2 x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * AT_P_BYTES);
+  uint8_t* p_s = q_s + AT_Q_BYTES;                       // 2 x 16 KB
+  uint8_t* kv_s = p_s + 2 * AT_P_BYTES;                  // AT_SLOTS x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_s + AT_SLOTS * AT_KV_BYTES);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* kv_full = bars + 1;            // [SLOTS]
   uint64_t* kv_empty = kv_full + AT_SLOTS; // [SLOTS]
@@ -55,15 +58,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
   uint64_t* p_empty = p_full + 2;          // [2]
   uint64_t* o_full = p_empty + 2;          // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* colsum_s = reinterpret_cast<float*>(bars + 32);  // [4][nb*128] when COLMEAN
+  float* colsum_s = reinterpret_cast<float*>(bars + 32);  // [4][nb*64] when COLMEAN
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * AT_BM;
   const int nb = p.nb;
-  const bool need_sum_pass1 = p.score_mode != TPAT_SCORE_NONE;
 
-  if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tmap_qkv);
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_q);
+    ptx::prefetch_tensormap(&tmap_kv);
+    ptx::prefetch_tensormap(&tmap_o);
+  }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < AT_SLOTS; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
@@ -75,27 +81,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc<512>(tmem_slot);
+    ptx::tmem_alloc<AT_TMEM_COLS>(tmem_slot);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_o = tmem_base + 2 * AT_BK;
 
   const int col_q = h * AT_HD, col_k = (p.H + h) * AT_HD, col_v = (2 * p.H + h) * AT_HD;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
-      ptx::tma_load_3d(q_s, &tmap_qkv, q_full, col_q, q0, b);
+      ptx::mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
+      ptx::tma_load_3d(q_s, &tmap_q, q_full, col_q, q0, b);
       int slot = 0; uint32_t phase = 0;
       auto load_tile = [&](int col, int key0) {
         ptx::mbar_wait(&kv_empty[slot], phase ^ 1);
-        ptx::mbar_arrive_expect_tx(&kv_full[slot], AT_TILE_BYTES);
-        ptx::tma_load_3d(kv_s + slot * AT_TILE_BYTES, &tmap_qkv, &kv_full[slot], col, key0, b);
+        ptx::mbar_arrive_expect_tx(&kv_full[slot], AT_KV_BYTES);
+        ptx::tma_load_3d(kv_s + slot * AT_KV_BYTES, &tmap_kv, &kv_full[slot], col, key0, b);
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
       };
       for (int j = 0; j < nb; ++j) load_tile(col_k, j * AT_BK);      // pass 1: K_0 .. K_{nb-1}
@@ -109,8 +115,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(128, 128, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(128, 64, 0, 1);   // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(128, AT_BK, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(128, AT_HD, 0, 1);  // P (K-major) x V (MN-major)
       int slot = 0; uint32_t phase = 0;
       int sidx = 0;  // running S-tile counter: buffer = sidx & 1, use count = sidx >> 1
       const uint64_t q_desc = ptx::smem_desc_sw128(ptx::smem_u32(q_s), 16, 1024);
@@ -119,10 +125,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
         ptx::mbar_wait(&kv_full[slot], phase);
         ptx::mbar_wait(&s_empty[sb], ((sidx >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint64_t k_desc = ptx::smem_desc_sw128(ptx::smem_u32(kv_s + slot * AT_TILE_BYTES), 16, 1024);
+        const uint64_t k_desc = ptx::smem_desc_sw128(ptx::smem_u32(kv_s + slot * AT_KV_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k)
-          ptx::mma_f16_ss((tmem_base + sb * 128), q_desc + (uint64_t)(2 * k), k_desc + (uint64_t)(2 * k), idesc_s, k != 0);
+          ptx::mma_f16_ss(tmem_base + sb * AT_BK, q_desc + (uint64_t)(2 * k), k_desc + (uint64_t)(2 * k), idesc_s, k != 0);
         ptx::tc_commit(&kv_empty[slot]);
         ptx::tc_commit(&s_full[sb]);
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
@@ -138,12 +144,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
         ptx::mbar_wait(&p_full[pb], (j >> 1) & 1);       // P_j written by the softmax warps
         ptx::tc_fence_after();
         const uint32_t p_addr = ptx::smem_u32(p_s + pb * AT_P_BYTES);
-        const uint32_t v_addr = ptx::smem_u32(kv_s + slot * AT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < AT_BK / 16; ++k) {
-          // A: 16 keys = 32 B inside the 64-key swizzle atom, second 64-key half 16 KB further
-          const uint64_t a_desc = ptx::smem_desc_sw128(p_addr + (k >> 2) * AT_TILE_BYTES + (k & 3) * 32, 16, 1024);
-          // B (MN-major): 16 keys = two 8-row groups of 1024 B
+        const uint32_t v_addr = ptx::smem_u32(kv_s + slot * AT_KV_BYTES);
+        const int valid = min(AT_BK, p.N - j * AT_BK);   // keys of this block that exist
+        const int ksteps = (valid + 15) >> 4;            // P is zero beyond `valid`, V rows beyond N are zero-filled
+        for (int k = 0; k < ksteps; ++k) {
+          // A: 16 keys = 32 B inside the 64-key swizzle atom;  B (MN-major): 16 keys = two 8-row groups of 1024 B
+          const uint64_t a_desc = ptx::smem_desc_sw128(p_addr + k * 32, 16, 1024);
           const uint64_t b_desc = ptx::smem_desc_sw128(v_addr + k * 2048, 16, 1024);
           ptx::mma_f16_ss(tmem_o, a_desc, b_desc, idesc_o, (j | k) != 0);
         }
@@ -160,149 +166,180 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcPa
     const int row = q0 + r_local;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float c = p.scale_log2;
+    // warps that must emit NORMALISED probabilities need the row sum before pass 2 (warp-uniform)
+    const bool norm_in_pass2 = (p.score_mode == TPAT_SCORE_COLMEAN) ||
+                               (p.score_mode == TPAT_SCORE_CLS_ROW && qt == 0 && quarter == 0);
     float m_run = -INFINITY, l_run = 0.f;
     int sidx = 0;
-    // ---- pass 1: row max (+ sum of exp when a score is requested) ----
+    // ---- pass 1: row max (+ sum of exp where needed) ----
     for (int j = 0; j < nb; ++j, ++sidx) {
       const int sb = sidx & 1;
       ptx::mbar_wait(&s_full[sb], (sidx >> 1) & 1);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < AT_BK / 32; ++ch) {
-        const int col0 = j * AT_BK + ch * 32;
-        if (col0 >= p.N) break;
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32((tmem_base + sb * 128) + lane_off + ch * 32, r);
-        ptx::tmem_ld_wait();
-        float mx = m_run;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (col0 + i < p.N) ? __uint_as_float(r[i]) : -INFINITY;
-          r[i] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
-        }
-        if (need_sum_pass1) {
-          float acc = 0.f;
-          const float mc = mx * c;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc += exp2f(fmaf(__uint_as_float(r[i]), c, -mc));
-          l_run = l_run * exp2f((m_run - mx) * c) + acc;
-        }
-        m_run = mx;
-      }
+      const int valid = p.N - j * AT_BK;                 // > 0
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK, r0);
+      if (valid > 32) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + 32, r1);
+      ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);
+      if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);     // values are in registers: release the buffer early
+      if (valid < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (i >= valid) r0[i] = 0xff800000u;   // -inf
+      } else if (valid > 32 && valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (32 + i >= valid) r1[i] = 0xff800000u;
+      }
+      float mx0 = m_run, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1])); }
+      if (valid > 32) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(r1[i])); mx1 = fmaxf(mx1, __uint_as_float(r1[i + 1])); }
+      }
+      const float mx = fmaxf(mx0, mx1);
+      if (norm_in_pass2) {
+        const float mc = mx * c;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          a0 += ptx::ex2_ftz(fmaf(__uint_as_float(r0[i]), c, -mc));
+          a1 += ptx::ex2_ftz(fmaf(__uint_as_float(r0[i + 1]), c, -mc));
+          a2 += ptx::ex2_ftz(fmaf(__uint_as_float(r0[i + 2]), c, -mc));
+          a3 += ptx::ex2_ftz(fmaf(__uint_as_float(r0[i + 3]), c, -mc));
+        }
+        if (valid > 32) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            a0 += ptx::ex2_ftz(fmaf(__uint_as_float(r1[i]), c, -mc));
+            a1 += ptx::ex2_ftz(fmaf(__uint_as_float(r1[i + 1]), c, -mc));
+            a2 += ptx::ex2_ftz(fmaf(__uint_as_float(r1[i + 2]), c, -mc));
+            a3 += ptx::ex2_ftz(fmaf(__uint_as_float(r1[i + 3]), c, -mc));
+          }
+        }
+        l_run = l_run * ptx::ex2_ftz((m_run - mx) * c) + ((a0 + a1) + (a2 + a3));
+      }
+      m_run = mx;
     }
-    const float mc = m_run * c;
-    const float inv_l = need_sum_pass1 ? 1.0f / l_run : 1.0f;
+    // exponent offset: p = 2^(s*c - off);  normalised warps fold log2(l) into the offset
+    const float off = norm_in_pass2 ? fmaf(m_run, c, __log2f(l_run)) : m_run * c;
     const float row_w = (row >= p.num_extra && row < p.N) ? 1.0f : 0.f;
     const bool cls_writer = (p.score_mode == TPAT_SCORE_CLS_ROW) && (row == 0);
     float* colsum_w = colsum_s + (size_t)quarter * nb * AT_BK;
-    float l2 = 0.f;
+    float l2a = 0.f, l2b = 0.f, l2c = 0.f, l2d = 0.f;
     // ---- pass 2: probabilities, score partials, P -> smem ----
     for (int j = 0; j < nb; ++j, ++sidx) {
       const int sb = sidx & 1, pb = j & 1;
       ptx::mbar_wait(&s_full[sb], (sidx >> 1) & 1);
-      ptx::mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      uint8_t* p_tile = p_s + pb * AT_P_BYTES;
-#pragma unroll 1
-      for (int ch = 0; ch < AT_BK / 32; ++ch) {
-        const int col0 = j * AT_BK + ch * 32;
-        uint32_t r[32];
+      const int valid = p.N - j * AT_BK;                 // > 0
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK, r0);
+      if (valid > 32) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + 32, r1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);
+      ptx::mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);  // PV(j-2) has consumed this P buffer
+      uint8_t* p_row = p_s + pb * AT_P_BYTES + r_local * 128;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t (&r)[32] = hf == 0 ? r0 : r1;
+        const int col0 = j * AT_BK + hf * 32;
+        const int vh = valid - hf * 32;                  // valid columns in this half (may be <= 0)
+        if (vh <= 0) {
+          if (hf * 32 < ((valid + 15) & ~15)) {          // still inside the MMA's K range: zero it
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(p_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
         float v[32];
-        if (col0 < p.N) {
-          ptx::tmem_ld_32x32b_x32((tmem_base + sb * 128) + lane_off + ch * 32, r);
-          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = exp2f(fmaf(__uint_as_float(r[i]), c, -mc)) * inv_l;
-            v[i] = (col0 + i < p.N) ? e : 0.f;
-          }
-        } else {
+        for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));
+        if (vh < 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          for (int i = 0; i < 32; ++i) if (i >= vh) v[i] = 0.f;
         }
-        if (!need_sum_pass1) {
+        if (!norm_in_pass2) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) l2 += v[i];
+          for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
         }
-        // bf16 P row segment -> 128B-swizzled K-major tile (64 keys per half)
-        {
-          uint8_t* half = p_tile + (ch >> 1) * AT_TILE_BYTES + r_local * 128;
+        // bf16 P row segment -> 128B-swizzled K-major tile
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk = ((ch & 1) * 4 + g) ^ (r_local & 7);
-            *reinterpret_cast<uint4*>(half + chunk * 16) =
-                make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                           pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
-          }
-        }
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(p_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) =
+              make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                         pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
         if (p.score_mode == TPAT_SCORE_COLMEAN) {
-          if (col0 < p.N) {
-            // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
+          // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= row_w;
+          for (int i = 0; i < 32; ++i) v[i] *= row_w;
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-              const bool upper = (lane & off) != 0;
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool upper = (lane & o) != 0;
 #pragma unroll
-              for (int i = 0; i < off; ++i) {
-                const float send = upper ? v[i] : v[i + off];
-                const float keep = upper ? v[i + off] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-              }
+            for (int i = 0; i < o; ++i) {
+              const float send = upper ? v[i] : v[i + o];
+              const float keep = upper ? v[i + o] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
-            colsum_w[col0 + lane] = v[0];
           }
+          colsum_w[col0 + lane] = v[0];
         } else if (cls_writer) {
           float* dst = p.score_partial + ((size_t)b * p.H + h) * p.N;
           for (int i = 0; i < 32; ++i)
             if (col0 + i < p.N) dst[col0 + i] = v[i];
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);
       ptx::fence_proxy_async_smem();   // make the generic-proxy P writes visible to the tensor core
       ptx::mbar_arrive(&p_full[pb]);
     }
-    // ---- epilogue: O (TMEM) -> bf16 -> global ----
-    ptx::mbar_wait(o_full, 0);
+    // ---- epilogue: O (TMEM) -> bf16 -> swizzled smem tile -> one TMA store ----
+    ptx::mbar_wait(o_full, 0);         // every PV MMA retired: the P buffers are free as well
     ptx::tc_fence_after();
-    const float o_scale = need_sum_pass1 ? 1.0f : 1.0f / l2;
-    __nv_bfloat16* dst = p.out + ((size_t)b * p.N + row) * (p.H * AT_HD) + h * AT_HD;
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + ch * 32, r);
+    const float o_scale = norm_in_pass2 ? 1.0f : 1.0f / ((l2a + l2b) + (l2c + l2d));
+    {
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld_32x32b_x32(tmem_o + lane_off, r0);
+      ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + 32, r1);
       ptx::tmem_ld_wait();
-      if (row < p.N) {
+      uint8_t* o_row = p_s + r_local * 128;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t (&r)[32] = hf == 0 ? r0 : r1;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<uint4*>(dst + ch * 32 + g * 8) =
+          *reinterpret_cast<uint4*>(o_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) =
               make_uint4(pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * o_scale, __uint_as_float(r[g * 8 + 1]) * o_scale),
                          pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * o_scale, __uint_as_float(r[g * 8 + 3]) * o_scale),
                          pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * o_scale, __uint_as_float(r[g * 8 + 5]) * o_scale),
                          pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * o_scale, __uint_as_float(r[g * 8 + 7]) * o_scale));
       }
     }
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    if (warp == 2 && lane == 0) {
+      ptx::tma_store_3d(&tmap_o, p_s, h * AT_HD, q0, b);   // rows >= N are clipped by the tensor map
+      ptx::tma_store_commit();
+    }
     if (p.score_mode == TPAT_SCORE_COLMEAN) {
       // sum the four warps' column sums in a fixed order and publish this tile's partial row
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
       float* dstp = p.score_partial + ((size_t)b * p.H * p.n_qt + (size_t)h * p.n_qt + qt) * p.N;
       const int ldc = nb * AT_BK;
       for (int jcol = threadIdx.x - 64; jcol < p.N; jcol += 128)
         dstp[jcol] = ((colsum_s[jcol] + colsum_s[ldc + jcol]) + colsum_s[2 * ldc + jcol]) + colsum_s[3 * ldc + jcol];
     }
+    if (warp == 2 && lane == 0) ptx::tma_store_wait_read<0>();   // smem must outlive the bulk store's reads
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<512>(tmem_base);
+    ptx::tmem_dealloc<AT_TMEM_COLS>(tmem_base);
   }
 }
 
@@ -311,10 +348,11 @@ int attention_tc_qtiles(int N) { return (N + AT_BM - 1) / AT_BM; }
 int attention_tc(const void* qkv, void* out, float* score_partial, int score_mode, int B, int N, int H,
                  int num_extra, float scale, cudaStream_t st) {
   TPAT_CHECK(N <= 4096, "tpat_attention(tc): N=%d too large (max 4096)", N);
-  CUtensorMap tm;
-  if (int rc = encode_tmap_3d_qkv(&tm, qkv, B, N, 3 * H * AT_HD)) return rc;
+  CUtensorMap tm_q, tm_kv, tm_o;
+  if (int rc = encode_tmap_3d_qkv(&tm_q, qkv, B, N, 3 * H * AT_HD, AT_BM)) return rc;
+  if (int rc = encode_tmap_3d_qkv(&tm_kv, qkv, B, N, 3 * H * AT_HD, AT_BK)) return rc;
+  if (int rc = encode_tmap_3d_qkv(&tm_o, out, B, N, H * AT_HD, AT_BM)) return rc;
   AttnTcParams p;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.score_partial = score_partial;
   p.score_mode = score_mode;
   p.N = N; p.H = H; p.num_extra = num_extra;
@@ -322,7 +360,7 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
   p.nb = (N + AT_BK - 1) / AT_BK;
   p.scale_log2 = scale * 1.4426950408889634f;
   const size_t colsum_bytes = score_mode == TPAT_SCORE_COLMEAN ? (size_t)4 * p.nb * AT_BK * sizeof(float) : 0;
-  const size_t smem = 1024 + AT_TILE_BYTES * (1 + AT_SLOTS) + 2 * AT_P_BYTES + 256 + colsum_bytes;
+  const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_SLOTS * AT_KV_BYTES + 256 + colsum_bytes;
   TPAT_CHECK(smem <= 227 * 1024, "tpat_attention(tc): N=%d needs %zu bytes of shared memory", N, smem);
   static bool attr_set = false;
   if (!attr_set) {
@@ -330,7 +368,7 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
     attr_set = true;
   }
   dim3 grid(p.n_qt, H, B);
-  attention_tc_kernel<<<grid, AT_THREADS, smem, st>>>(tm, p);
+  attention_tc_kernel<<<grid, AT_THREADS, smem, st>>>(tm_q, tm_kv, tm_o, p);
   TPAT_LAUNCH_CHECK();
   return 0;
 }

@@ -91,12 +91,12 @@ int encode_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t 
   return 0;
 }
 
-// 3-D map over the qkv activation [B][N][ld] (bf16): box = 64 columns x 128 rows x 1 clip, 128B swizzle.
+// 3-D map over a token-major activation [B][N][ld] (bf16): box = 64 columns x box_rows rows x 1 clip, 128B swizzle.
 // Rows >= N of a clip are out of bounds of dim 1 and are zero-filled (never the next clip's rows).
-int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld) {
+int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld, int box_rows) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{gptr, (uint64_t)N, (uint64_t)ld, (uint64_t)B, 128, 64, 2, true};
+  TmapKey key{gptr, (uint64_t)N, (uint64_t)ld, (uint64_t)B, (uint32_t)box_rows, 64, 2, true};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -107,7 +107,7 @@ int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld)
   TPAT_CHECK(aligned16(gptr) && (ld * 2) % 16 == 0, "TMA needs a 16-byte aligned base and row pitch");
   cuuint64_t gdim[3] = {(cuuint64_t)ld, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)N * ld * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -126,8 +126,10 @@ constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_STAGES = 4, TG_UMMA_K = 1
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;   // 16 KB
 constexpr int TG_B_BYTES = TG_BN * TG_BK * 2;   // 32 KB
 constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
-constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TG_THREADS = 192;
+constexpr int TG_EPI_WARPS = 8;
+constexpr int TG_STAGING_BYTES = TG_EPI_WARPS * 4096;   // one 32-row x 128 B transpose buffer per epilogue warp
+constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + TG_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TG_THREADS = 64 + 32 * TG_EPI_WARPS;      // TMA warp + MMA warp + 8 epilogue warps
 
 struct TcGemmParams {
   int M, N, K;
@@ -138,6 +140,22 @@ struct TcGemmParams {
   int tiles_m, tiles_n;
 };
 
+// erf-form GELU for the bf16 tensor-core path: Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7)
+// with MUFU rcp / ex2 -- ~16 instructions instead of libdevice erff's ~30.  The fp32 parity path
+// (gemm_simt.cu) keeps erff.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = ptx::rcp_ftz(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float pe = poly * ptx::ex2_ftz(z * (z * -1.4426950408889634f));   // 1 - erf(|z|)
+  const float hx = 0.5f * x * pe;
+  return x >= 0.f ? x - hx : hx;
+}
+
 template <int EPI, typename OutT>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TcGemmParams p) {
@@ -145,7 +163,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + TG_STAGES * TG_A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TG_STAGES * TG_STAGE_BYTES);
+  uint8_t* staging = smem + TG_STAGES * TG_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + TG_STAGING_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + TG_STAGES;       // [STAGES]
   uint64_t* acc_full = bars + 2 * TG_STAGES;    // [2]
@@ -162,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TG_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], TG_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -217,73 +236,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+    // ===== epilogue warps 2..9 =====
+    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the eight
+    // 32-column chunks of the tile (even / odd).  Per chunk: tcgen05.ld (thread = row) -> 4 KB
+    // XOR-swizzled transpose buffer -> re-read with lanes along the row, so every global access
+    // of the epilogue is a full 128 B (fp32) / 64 B (bf16) row segment per 8 lanes.
     const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    uint8_t* stg = staging + (warp - 2) * 4096;
+    const int jl = lane & 7, rl = lane >> 3;          // coalesced phase: lane -> (16 B piece, row within a group of 4)
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * TG_BM, n0 = (tile % p.tiles_n) * TG_BN;
+      const int m0 = (tile / p.tiles_n) * TG_BM + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
       ptx::mbar_wait(&acc_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      size_t orow = (size_t)m;
-      const float* pos_row = nullptr;
-      if constexpr (EPI == TPAT_EPI_BIAS_POS) {
-        const int b = m / p.P, pp = m - b * p.P;
-        orow = (size_t)b * (p.num_extra + p.P) + p.num_extra + pp;
-        pos_row = p.pos + (size_t)(p.num_extra + pp) * p.ldc;
-      }
-      OutT* crow = reinterpret_cast<OutT*>(p.C) + orow * p.ldc;
-      const float* rrow = (EPI == TPAT_EPI_BIAS_RESIDUAL) ? p.residual + (size_t)m * p.ldr : nullptr;
       const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
-#pragma unroll 1
-      for (int c = 0; c < TG_BN / 32; ++c) {
+      uint32_t rbuf[2][32];
+      bool released = false;
+      ptx::tmem_ld_32x32b_x32(taddr_row + cg * 32, rbuf[0]);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = cg + 2 * ci;
         const int n = n0 + c * 32;
-        if (n >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(taddr_row + c * 32, r);
+        uint32_t (&r)[32] = rbuf[ci & 1];
         ptx::tmem_ld_wait();
-        if (row_ok) {
-          float v[32];
+        const bool more = ci + 1 < 4 && (n + 64) < p.N;
+        if (more) {
+          ptx::tmem_ld_32x32b_x32(taddr_row + (c + 2) * 32, rbuf[(ci + 1) & 1]);
+        } else if (!released) {
+          // last TMEM read of this tile is complete: hand the accumulator back to the MMA warp
+          released = true;
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+        }
+        if (n < p.N) {
+          // transpose through shared memory: thread = row writes 8 x 16 B, swizzled by row
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[j] = __uint_as_float(r[j]) + bb.x; v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + bb.z; v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
-          }
-          if constexpr (EPI == TPAT_EPI_BIAS_GELU) {
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          const int ncol = n + jl * 4;
+          const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 extra[8];
+          if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 rr = *reinterpret_cast<const float4*>(rrow + n + j);
-              v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+            for (int it = 0; it < 8; ++it) {
+              const int m = m0 + it * 4 + rl;
+              extra[it] = m < p.M ? *reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + ncol) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-          } else if constexpr (EPI == TPAT_EPI_BIAS_POS) {
+          }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 pe = __ldg(reinterpret_cast<const float4*>(pos_row + n + j));
-              v[j] += pe.x; v[j + 1] += pe.y; v[j + 2] += pe.z; v[j + 3] += pe.w;
+          for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + rl;
+            const int m = m0 + row;
+            const float4 a = *reinterpret_cast<const float4*>(stg + row * 128 + ((jl ^ (row & 7)) << 4));
+            float v0 = a.x + bb.x, v1 = a.y + bb.y, v2 = a.z + bb.z, v3 = a.w + bb.w;
+            size_t orow = (size_t)m;
+            if constexpr (EPI == TPAT_EPI_BIAS_GELU) {
+              v0 = gelu_erf_fast(v0); v1 = gelu_erf_fast(v1); v2 = gelu_erf_fast(v2); v3 = gelu_erf_fast(v3);
+            } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
+              v0 += extra[it].x; v1 += extra[it].y; v2 += extra[it].z; v3 += extra[it].w;
+            } else if constexpr (EPI == TPAT_EPI_BIAS_POS) {
+              if (m < p.M) {
+                const int b = m / p.P, pp = m - b * p.P;
+                orow = (size_t)b * (p.num_extra + p.P) + p.num_extra + pp;
+                const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(p.num_extra + pp) * p.ldc + ncol));
+                v0 += pe.x; v1 += pe.y; v2 += pe.z; v3 += pe.w;
+              }
+            }
+            if (m < p.M) {
+              if constexpr (sizeof(OutT) == 4) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + ncol) = make_float4(v0, v1, v2, v3);
+              } else {
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + ncol) =
+                    make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
+              }
             }
           }
-          if constexpr (sizeof(OutT) == 4) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(crow) + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + n + j) =
-                  make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
-                             pack_bf16x2(v[j + 6], v[j + 7]));
-          }
+          __syncwarp();   // the transpose buffer is rewritten by the next chunk
         }
       }
-      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
