@@ -152,6 +152,13 @@ int tpat_pool_norm(const float* x, float* pooled, const float* g1, const float* 
                    const float* g2, const float* b2, float eps2, int B, int N, int D, int variant,
                    tpat_stream_t stream);
 
+/*
+ * Classifier head: logits[B, C] = pooled[B, D] W[C, D]^T + bias, fp32 CUDA cores (tiny, latency-bound).
+ * Replaces self.head (models_vit.py:522) / mlp_head[1] (ast_models.py:503).  D % 128 == 0, D <= 1024.
+ */
+int tpat_head(const float* pooled, const float* W, const float* bias, float* logits, int B, int D, int C,
+              tpat_stream_t stream);
+
 /* ---- whole forward (the hot loop of models_vit.py:365-385 / ast_models.py:470-497 in native code) ---- */
 
 typedef struct {

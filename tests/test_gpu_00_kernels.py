@@ -159,6 +159,17 @@ def test_pool_norm_both_variants():
     assert rel_err(out, ref) < 2e-6
 
 
+@pytest.mark.parametrize("B,C", [(64, 527), (3, 35), (1, 50)])
+def test_head(B, C):
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(9)
+    pooled = torch.randn(B, 768, generator=g).to(dev())
+    w = (torch.randn(C, 768, generator=g) * 0.02).to(dev())
+    bias = torch.randn(C, generator=g).to(dev())
+    out = ops.head(pooled, w, bias)
+    assert rel_err(out, pooled.double() @ w.double().T + bias.double()) < 2e-6
+
+
 def test_errors_surface_as_runtime_error():
     ops, _lib = _ops()
     with pytest.raises(RuntimeError, match="head dim|CUDA tensor|contiguous|libtpat"):

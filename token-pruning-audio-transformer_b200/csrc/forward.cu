@@ -149,6 +149,5 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
   // pooled head (models_vit.py:387-389,522 / ast_models.py:500-503); always fp32 CUDA cores (tiny)
   if (int rc = tpat_pool_norm(w.x[xi], w.pooled, a->norm_g, a->norm_b, a->norm_eps, a->head_ln_g, a->head_ln_b,
                               a->head_ln_eps, B, extra + cur, D, a->variant, stream)) return rc;
-  return tpat_gemm(w.pooled, TPAT_F32, D, a->head_w, TPAT_F32, a->head_b, a->logits, TPAT_F32, a->num_classes, nullptr, 0,
-                   nullptr, 0, 0, B, a->num_classes, D, TPAT_EPI_BIAS, TPAT_IMPL_SIMT, stream);
+  return tpat_head(w.pooled, a->head_w, a->head_b, a->logits, B, D, a->num_classes, stream);
 }

@@ -18,4 +18,8 @@ int gemm_simt(const void* A, int a_dtype, int lda, const void* W, void* C, int c
 int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc, int M, int N, int K,
             const EpiParams& ep, cudaStream_t st);
 
+// CTA-pair (cta_group::2) variant, 256 x 256 tiles (gemm_tc2.cu); arguments validated by gemm_tc
+int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc, int M, int N, int K,
+             const EpiParams& ep, cudaStream_t st);
+
 }  // namespace tpat

@@ -15,9 +15,9 @@
 //            so the epilogue of tile i overlaps the main loop of tile i+1.
 // Tiles are walked n-fastest so the CTAs in flight share A k-blocks through L2.
 // Roofline: tensor pipe.  Algorithmic FLOPs = 2*M*N*K per launch.
-#include "gemm.cuh"
-#include "ptx_sm100.cuh"
+#include "gemm_tc_common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -122,39 +122,14 @@ int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld,
 }
 
 // ---------------- kernel ----------------
-constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_STAGES = 4, TG_UMMA_K = 16;
+constexpr int TG_STAGES = 4;
+constexpr int TG_EPI_WARPS = 8;
+constexpr int TG_STAGING_BYTES = tg_staging_bytes(TG_EPI_WARPS);
+constexpr int TG_THREADS = tg_threads(TG_EPI_WARPS);
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;   // 16 KB
 constexpr int TG_B_BYTES = TG_BN * TG_BK * 2;   // 32 KB
 constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
-constexpr int TG_EPI_WARPS = 8;
-constexpr int TG_STAGING_BYTES = TG_EPI_WARPS * 4096;   // one 32-row x 128 B transpose buffer per epilogue warp
 constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + TG_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TG_THREADS = 64 + 32 * TG_EPI_WARPS;      // TMA warp + MMA warp + 8 epilogue warps
-
-struct TcGemmParams {
-  int M, N, K;
-  void* C; int ldc;
-  const float* bias;
-  const float* residual; int ldr;
-  const float* pos; int P, num_extra;
-  int tiles_m, tiles_n;
-};
-
-// erf-form GELU for the bf16 tensor-core path: Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7)
-// with MUFU rcp / ex2 -- ~16 instructions instead of libdevice erff's ~30.  The fp32 parity path
-// (gemm_simt.cu) keeps erff.
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = ptx::rcp_ftz(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float pe = poly * ptx::ex2_ftz(z * (z * -1.4426950408889634f));   // 1 - erf(|z|)
-  const float hx = 0.5f * x * pe;
-  return x >= 0.f ? x - hx : hx;
-}
 
 template <int EPI, typename OutT>
 __global__ void __launch_bounds__(TG_THREADS, 1)
@@ -236,87 +211,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue warps 2..9 =====
-    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the eight
-    // 32-column chunks of the tile (even / odd).  Per chunk: tcgen05.ld (thread = row) -> 4 KB
-    // XOR-swizzled transpose buffer -> re-read with lanes along the row, so every global access
-    // of the epilogue is a full 128 B (fp32) / 64 B (bf16) row segment per 8 lanes.
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4; the two warps of a quarter split the chunks =====
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     uint8_t* stg = staging + (warp - 2) * 4096;
-    const int jl = lane & 7, rl = lane >> 3;          // coalesced phase: lane -> (16 B piece, row within a group of 4)
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.tiles_n) * TG_BM + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
+      TcEpiPrefetch<TG_EPI_WARPS> pf;
+      tc_epilogue_prefetch<TG_EPI_WARPS>(p, n0, cg, lane, pf);
       ptx::mbar_wait(&acc_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
-      uint32_t rbuf[2][32];
-      bool released = false;
-      ptx::tmem_ld_32x32b_x32(taddr_row + cg * 32, rbuf[0]);
-#pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c = cg + 2 * ci;
-        const int n = n0 + c * 32;
-        uint32_t (&r)[32] = rbuf[ci & 1];
-        ptx::tmem_ld_wait();
-        const bool more = ci + 1 < 4 && (n + 64) < p.N;
-        if (more) {
-          ptx::tmem_ld_32x32b_x32(taddr_row + (c + 2) * 32, rbuf[(ci + 1) & 1]);
-        } else if (!released) {
-          // last TMEM read of this tile is complete: hand the accumulator back to the MMA warp
-          released = true;
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
-        }
-        if (n < p.N) {
-          // transpose through shared memory: thread = row writes 8 x 16 B, swizzled by row
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          __syncwarp();
-          const int ncol = n + jl * 4;
-          const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 extra[8];
-          if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int m = m0 + it * 4 + rl;
-              extra[it] = m < p.M ? *reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + ncol) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int row = it * 4 + rl;
-            const int m = m0 + row;
-            const float4 a = *reinterpret_cast<const float4*>(stg + row * 128 + ((jl ^ (row & 7)) << 4));
-            float v0 = a.x + bb.x, v1 = a.y + bb.y, v2 = a.z + bb.z, v3 = a.w + bb.w;
-            size_t orow = (size_t)m;
-            if constexpr (EPI == TPAT_EPI_BIAS_GELU) {
-              v0 = gelu_erf_fast(v0); v1 = gelu_erf_fast(v1); v2 = gelu_erf_fast(v2); v3 = gelu_erf_fast(v3);
-            } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
-              v0 += extra[it].x; v1 += extra[it].y; v2 += extra[it].z; v3 += extra[it].w;
-            } else if constexpr (EPI == TPAT_EPI_BIAS_POS) {
-              if (m < p.M) {
-                const int b = m / p.P, pp = m - b * p.P;
-                orow = (size_t)b * (p.num_extra + p.P) + p.num_extra + pp;
-                const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(p.num_extra + pp) * p.ldc + ncol));
-                v0 += pe.x; v1 += pe.y; v2 += pe.z; v3 += pe.w;
-              }
-            }
-            if (m < p.M) {
-              if constexpr (sizeof(OutT) == 4) {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + ncol) = make_float4(v0, v1, v2, v3);
-              } else {
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + ncol) =
-                    make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3));
-              }
-            }
-          }
-          __syncwarp();   // the transpose buffer is rewritten by the next chunk
-        }
-      }
+      uint64_t* rel_bar = &acc_empty[acc];
+      tc_epilogue_tile<EPI, OutT, TG_EPI_WARPS>(p, taddr_row, m0, n0, cg, stg, lane, pf, [&]() { if (lane == 0) ptx::mbar_arrive(rel_bar); });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -350,6 +258,16 @@ int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc
   TPAT_CHECK(N % 32 == 0, "tpat_gemm(tc): need N %% 32 == 0 (N=%d)", N);
   TPAT_CHECK(aligned16(C) && (ldc * dtype_size(c_dtype)) % 16 == 0, "tpat_gemm(tc): C must be 16-byte aligned with a 16-byte multiple pitch");
   TPAT_CHECK(ep.bias == nullptr || aligned16(ep.bias), "tpat_gemm(tc): bias must be 16-byte aligned");
+  if (ep.epilogue == TPAT_EPI_BIAS_RESIDUAL)
+    TPAT_CHECK(c_dtype == TPAT_F32 && ep.residual && aligned16(ep.residual) && ep.ldr % 4 == 0, "tpat_gemm(tc): residual epilogue needs fp32 C and an aligned fp32 residual");
+  if (ep.epilogue == TPAT_EPI_BIAS_POS)
+    TPAT_CHECK(c_dtype == TPAT_F32 && ep.pos && aligned16(ep.pos) && ep.P > 0, "tpat_gemm(tc): pos epilogue needs fp32 C, pos and P");
+  {
+    // CTA-pair kernel (cta_group::2) unless TPAT_GEMM_2CTA=0; read per call so tests can A/B both kernels
+    const char* e = getenv("TPAT_GEMM_2CTA");
+    const bool two_cta = e == nullptr || e[0] != '0';
+    if (two_cta && sm_count() >= 2) return gemm_tc2(A, lda, W, C, c_dtype, ldc, M, N, K, ep, st);
+  }
   CUtensorMap ta, tw;
   if (int rc = encode_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, TG_BM, TG_BK, true)) return rc;
   if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, TG_BN, TG_BK, true)) return rc;
@@ -357,16 +275,15 @@ int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + TG_BN - 1) / TG_BN;
+  p.debug_skip = 0;
   switch (ep.epilogue) {
     case TPAT_EPI_BIAS:
       return c_dtype == TPAT_BF16 ? launch_tc<TPAT_EPI_BIAS, __nv_bfloat16>(ta, tw, p, st) : launch_tc<TPAT_EPI_BIAS, float>(ta, tw, p, st);
     case TPAT_EPI_BIAS_GELU:
       return c_dtype == TPAT_BF16 ? launch_tc<TPAT_EPI_BIAS_GELU, __nv_bfloat16>(ta, tw, p, st) : launch_tc<TPAT_EPI_BIAS_GELU, float>(ta, tw, p, st);
     case TPAT_EPI_BIAS_RESIDUAL:
-      TPAT_CHECK(c_dtype == TPAT_F32 && ep.residual && aligned16(ep.residual) && ep.ldr % 4 == 0, "tpat_gemm(tc): residual epilogue needs fp32 C and an aligned fp32 residual");
       return launch_tc<TPAT_EPI_BIAS_RESIDUAL, float>(ta, tw, p, st);
     case TPAT_EPI_BIAS_POS:
-      TPAT_CHECK(c_dtype == TPAT_F32 && ep.pos && aligned16(ep.pos) && ep.P > 0, "tpat_gemm(tc): pos epilogue needs fp32 C, pos and P");
       return launch_tc<TPAT_EPI_BIAS_POS, float>(ta, tw, p, st);
   }
   set_error("tpat_gemm(tc): bad epilogue %d", ep.epilogue);

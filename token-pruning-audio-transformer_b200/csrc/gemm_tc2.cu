@@ -1,0 +1,182 @@
+// CTA-pair tcgen05 GEMM (cta_group::2): C = epilogue(A W^T + bias), bf16 operands, fp32 accumulate.
+//
+// Same role as gemm_tc.cu (reference nn.Linear call sites: audiomae/models_vit.py:41-45,76,96,198,205)
+// but two CTAs on the SM pair of one TPC cooperate on a 256 x 256 output tile:
+//   * each CTA TMA-loads ITS 128 rows of A and ITS 128 of the 256 W rows per k-block (32 KB / stage
+//     instead of 48 KB, so 5 stages + twelve epilogue transpose buffers fit) -- the tensor cores of the pair share the W halves, which
+//     halves the shared-memory read traffic per SM, the limiter of the 1-CTA kernel (ncu: tensor
+//     pipe 67 % active at 1300 TF/s; 96 B/clk UMMA reads + 96 B/clk TMA writes vs a 128 B/clk port);
+//   * one thread of the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 (M256 N256 K16);
+//     each CTA's TMEM receives its own 128 rows of the accumulator;
+//   * TMA completions of both CTAs are credited to the leader's full barrier; tcgen05.commit
+//     multicasts "stage free" / "accumulator ready" to both CTAs; both CTAs' epilogue warps arrive
+//     remotely on the leader's accumulator-empty barrier.
+// Warp roles per CTA and the epilogue are those of gemm_tc.cu (gemm_tc_common.cuh).
+#include "gemm_tc_common.cuh"
+
+#include <cstdlib>
+
+namespace tpat {
+
+constexpr int T2_STAGES = 5;
+constexpr int T2_EPI_WARPS = 12;
+constexpr int T2_THREADS = tg_threads(T2_EPI_WARPS);   // 448
+constexpr int T2_A_BYTES = 128 * TG_BK * 2;    // 16 KB: this CTA's 128 rows of A
+constexpr int T2_B_BYTES = 128 * TG_BK * 2;    // 16 KB: this CTA's 128 rows of W
+constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
+constexpr int T2_STAGING_BYTES = tg_staging_bytes(T2_EPI_WARPS);
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + T2_STAGING_BYTES + 1024 + 256;
+
+template <int EPI, typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TcGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + T2_STAGES * T2_A_BYTES;
+  uint8_t* staging = smem + T2_STAGES * T2_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + T2_STAGING_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]  (used in the leader CTA)
+  uint64_t* empty_bar = bars + T2_STAGES;       // [STAGES]  (one per CTA, multicast commit)
+  uint64_t* acc_full = bars + 2 * T2_STAGES;    // [2]       (one per CTA, multicast commit)
+  uint64_t* acc_empty = acc_full + 2;           // [2]       (used in the leader CTA, 2 x 12 remote arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.tiles_m * p.tiles_n;   // 256 x 256 tiles
+  const int nkb = p.K / TG_BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], 2 * T2_EPI_WARPS); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta<512>(tmem_slot);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();          // barrier inits + TMEM allocation visible to both CTAs of the pair
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows + own half of the W rows, credited to the leader's barrier =====
+    if (ptx::elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128;
+        const int n0 = (tile % p.tiles_n) * TG_BN + (int)rank * 128;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
+          const bool first_fill = tile == cluster_id && kb < T2_STAGES;
+          const bool load_a = p.debug_skip != 1 || first_fill;
+          const bool load_b = p.debug_skip == 0 || first_fill;
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * ((load_a ? T2_A_BYTES : 0) + (load_b ? T2_B_BYTES : 0)));
+          if (load_a) ptx::tma_load_2d_2cta(smem_a + stage * T2_A_BYTES, &tmap_a, full_leader, kb * TG_BK, m0);
+          if (load_b) ptx::tma_load_2d_2cta(smem_b + stage * T2_B_BYTES, &tmap_w, full_leader, kb * TG_BK, n0);
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: leader CTA only =====
+    if (leader && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(256, TG_BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TG_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_a + stage * T2_A_BYTES), 16, 1024);
+          const uint64_t b_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * T2_B_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < TG_BK / TG_UMMA_K; ++k)
+            ptx::mma_f16_ss_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          ptx::tc_commit_2cta(&empty_bar[stage], 0b11);   // stage free in both CTAs
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit_2cta(&acc_full[acc], 0b11);        // accumulator halves ready in both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..13 (both CTAs): this CTA's 128 rows of the 256 x 256 tile =====
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    uint8_t* stg = staging + (warp - 2) * 4096;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128 + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
+      TcEpiPrefetch<T2_EPI_WARPS> pf;
+      tc_epilogue_prefetch<T2_EPI_WARPS>(p, n0, cg, lane, pf);
+      ptx::mbar_wait(&acc_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
+      const uint32_t rel_leader = ptx::mapa_shared(ptx::smem_u32(&acc_empty[acc]), 0);
+      tc_epilogue_tile<EPI, OutT, T2_EPI_WARPS>(p, taddr_row, m0, n0, cg, stg, lane, pf, [&]() { if (lane == 0) ptx::mbar_arrive_cluster(rel_leader); });
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();          // neither CTA may exit (or free TMEM) while the peer can still touch it
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
+template <int EPI, typename OutT>
+static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const TcGemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = gemm_tc2_kernel<EPI, OutT>;
+  if (!attr_set) {
+    TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  int clusters = sm_count() / 2;
+  if (tiles < clusters) clusters = tiles;
+  kern<<<2 * clusters, T2_THREADS, T2_SMEM_BYTES, st>>>(ta, tw, p);
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc, int M, int N, int K,
+             const EpiParams& ep, cudaStream_t st) {
+  CUtensorMap ta, tw;
+  if (int rc = encode_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 128, TG_BK, true)) return rc;
+  if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, 128, TG_BK, true)) return rc;
+  TcGemmParams p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
+  p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
+  p.tiles_m = (M + 255) / 256; p.tiles_n = (N + TG_BN - 1) / TG_BN;
+  { const char* e = getenv("TPAT_GEMM_DEBUG_SKIP"); p.debug_skip = e ? atoi(e) : 0; }
+  switch (ep.epilogue) {
+    case TPAT_EPI_BIAS:
+      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS, __nv_bfloat16>(ta, tw, p, st) : launch_tc2<TPAT_EPI_BIAS, float>(ta, tw, p, st);
+    case TPAT_EPI_BIAS_GELU:
+      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16>(ta, tw, p, st) : launch_tc2<TPAT_EPI_BIAS_GELU, float>(ta, tw, p, st);
+    case TPAT_EPI_BIAS_RESIDUAL:
+      return launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float>(ta, tw, p, st);
+    case TPAT_EPI_BIAS_POS:
+      return launch_tc2<TPAT_EPI_BIAS_POS, float>(ta, tw, p, st);
+  }
+  set_error("tpat_gemm(tc2): bad epilogue %d", ep.epilogue);
+  return 1;
+}
+
+}  // namespace tpat

@@ -1,0 +1,149 @@
+// Pieces shared by the 1-CTA (gemm_tc.cu) and CTA-pair (gemm_tc2.cu) tcgen05 GEMM kernels:
+// tile constants, kernel parameters, the fast erf GELU and the epilogue of one 128 x 256 accumulator.
+#pragma once
+#include "gemm.cuh"
+#include "ptx_sm100.cuh"
+
+namespace tpat {
+
+int encode_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                   uint32_t box_rows, uint32_t box_cols, bool swizzle128);
+
+constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_UMMA_K = 16;
+// EW epilogue warps (8 or 16): warp e -> TMEM lane quarter (e + 2) % 4 (hardware rule: warp id % 4), group e / 4;
+// the EW/4 warps of a quarter interleave the eight 32-column chunks of the 256-column accumulator.
+constexpr int tg_staging_bytes(int EW) { return EW * 4096; }   // one 32-row x 128 B transpose buffer per epilogue warp
+constexpr int tg_threads(int EW) { return 64 + 32 * EW; }      // TMA warp + MMA warp + EW epilogue warps
+
+struct TcGemmParams {
+  int M, N, K;
+  void* C; int ldc;
+  const float* bias;
+  const float* residual; int ldr;
+  const float* pos; int P, num_extra;
+  int tiles_m, tiles_n;
+  int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
+};
+
+// GELU for the bf16 tensor-core epilogue: x * sigmoid(x * (c1 + c3 x^2 + c5 x^4)), coefficients fitted
+// (minimax, tools/probes/fit_gelu.py) to the erf form nn.GELU() uses: |error| <= 8.2e-5 absolute over
+// all x, i.e. about one bf16 ulp at worst (x ~ -3) and far below it elsewhere -- invisible once the
+// result is rounded to bf16.  9 instructions (2 MUFU) instead of ~30 for libdevice erff: the fc1
+// epilogue was instruction-issue bound (ncu: 97 M warp instructions, 660 -> 940 TF/s with an
+// Abramowitz-Stegun erf, -> see profiles/ with this form).  The fp32 parity path keeps erff.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float x2 = fminf(x * x, 81.0f);              // the fit is valid for |x| <= 9; beyond it the sigmoid is saturated
+  float p = fmaf(x2, 8.2617402e-4f, -0.10563205f);   // -log2(e) * (c5 x^2 + c3)
+  p = fmaf(p, x2, -2.3019710f);                      // -log2(e) * c1
+  const float e = ptx::ex2_ftz(p * x);               // exp(-x (c1 + c3 x^2 + c5 x^4))
+  return x * ptx::rcp_ftz(1.0f + e);
+}
+
+// Per-tile epilogue state that does not depend on the accumulator: loaded BEFORE waiting for the MMA
+// so that the global-load latency (bias) is off the critical path.
+template <int EW> struct TcEpiPrefetch {
+  static constexpr int CSTRIDE = EW / 4;                       // warps per lane quarter
+  static constexpr int NCH = (8 + CSTRIDE - 1) / CSTRIDE;      // chunks per warp (the last may be dead)
+  float4 bias[NCH];
+};
+
+template <int EW>
+__device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmParams& p, int n0, int cg, int lane, TcEpiPrefetch<EW>& pf) {
+  const int jl = lane & 7;
+#pragma unroll
+  for (int ci = 0; ci < TcEpiPrefetch<EW>::NCH; ++ci) {
+    const int c = cg + TcEpiPrefetch<EW>::CSTRIDE * ci;
+    const int ncol = n0 + c * 32 + jl * 4;
+    pf.bias[ci] = (p.bias != nullptr && c < 8 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// Epilogue of one accumulator for one epilogue warp.
+//   taddr_row : TMEM address of this warp's lane quarter at column 0 of the accumulator
+//   m0        : global row of this warp's first TMEM lane;  n0 : first global column of the tile
+//   cg        : group of this warp within its lane quarter: it owns chunks cg, cg + EW/4, ...
+//   stg       : this warp's 4 KB transpose buffer
+//   release() : called once (warp-uniformly) when the last tcgen05.ld of the tile has completed
+// Per chunk: tcgen05.ld (thread = row) -> XOR-swizzled transpose buffer -> re-read with lanes along
+// the row, so every global access is a full 128 B (fp32) / 64 B (bf16) row segment per 8 lanes.
+// Residual rows are requested before the TMEM read of the chunk so their latency overlaps it.
+template <int EPI, typename OutT, int EW, typename ReleaseFn>
+__device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t taddr_row, int m0, int n0, int cg,
+                                                 uint8_t* stg, int lane, const TcEpiPrefetch<EW>& pf, ReleaseFn release) {
+  constexpr int NCH = TcEpiPrefetch<EW>::NCH, CSTRIDE = TcEpiPrefetch<EW>::CSTRIDE;
+  const int jl = lane & 7, rl = lane >> 3;   // coalesced phase: lane -> (16 B piece, row within a group of 4)
+  bool released = false;
+#pragma unroll
+  for (int ci = 0; ci < NCH; ++ci) {
+    const int c = cg + CSTRIDE * ci;
+    const int n = n0 + c * 32;
+    const bool live = c < 8 && n < p.N;      // warp-uniform
+    const int ncol = n + jl * 4;
+    float4 extra[8];
+    if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
+      if (live) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = m0 + it * 4 + rl;
+          extra[it] = m < p.M ? *reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + ncol) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    uint32_t r[32];
+    if (live) {
+      ptx::tmem_ld_32x32b_x32(taddr_row + c * 32, r);
+      ptx::tmem_ld_wait();
+    }
+    if (!released && (ci == NCH - 1 || c + CSTRIDE >= 8 || n + CSTRIDE * 32 >= p.N)) {
+      // last TMEM read of this tile is complete: hand the accumulator back to the MMA warp
+      released = true;
+      ptx::tc_fence_before();
+      __syncwarp();
+      release();
+    }
+    if (!live) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    const float4 bb = pf.bias[ci];
+    float4 v[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + rl;
+      const float4 a = *reinterpret_cast<const float4*>(stg + row * 128 + ((jl ^ (row & 7)) << 4));
+      v[it] = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+    }
+    __syncwarp();   // all lanes have read the transpose buffer: the next chunk may overwrite it
+    if constexpr (EPI == TPAT_EPI_BIAS_GELU) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        v[it].x = gelu_erf_fast(v[it].x); v[it].y = gelu_erf_fast(v[it].y);
+        v[it].z = gelu_erf_fast(v[it].z); v[it].w = gelu_erf_fast(v[it].w);
+      }
+    } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) { v[it].x += extra[it].x; v[it].y += extra[it].y; v[it].z += extra[it].z; v[it].w += extra[it].w; }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int m = m0 + it * 4 + rl;
+      if (m >= p.M) continue;
+      size_t orow = (size_t)m;
+      if constexpr (EPI == TPAT_EPI_BIAS_POS) {
+        const int b = m / p.P, pp = m - b * p.P;
+        orow = (size_t)b * (p.num_extra + p.P) + p.num_extra + pp;
+        const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(p.num_extra + pp) * p.ldc + ncol));
+        v[it].x += pe.x; v[it].y += pe.y; v[it].z += pe.z; v[it].w += pe.w;
+      }
+      if constexpr (sizeof(OutT) == 4) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + ncol) = v[it];
+      } else {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + ncol) =
+            make_uint2(pack_bf16x2(v[it].x, v[it].y), pack_bf16x2(v[it].z, v[it].w));
+      }
+    }
+  }
+}
+
+}  // namespace tpat

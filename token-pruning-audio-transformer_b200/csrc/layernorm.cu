@@ -97,14 +97,14 @@ gather_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__
   }
 }
 
-// ---- pooled classifier input: one CTA (256 threads) per clip ----
-__device__ __forceinline__ float block_sum_256(float v, float* red) {
+// ---- pooled classifier input: one CTA per clip ----
+__device__ __forceinline__ float block_sum_256(float v, float* red) {   // any block size up to 1024 threads
   v = warp_sum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __syncthreads();
   if (l == 0) red[w] = v;
   __syncthreads();
-  float t = (l < 8) ? red[l] : 0.f;
+  float t = (l < (int)(blockDim.x >> 5)) ? red[l] : 0.f;
   t = warp_sum(t);
   return t;
 }
@@ -123,21 +123,50 @@ __device__ void block_layernorm_inplace(float* vec, int D, const float* __restri
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
+// grid = B clips, block = 1024 threads.  AudioMAE: thread (tg, c4) sums the float4 column c4 over
+// tokens t = 1 + tg, 1 + tg + TG, ... (coalesced 3 KB rows, 4 independent accumulators per thread for
+// memory-level parallelism), the TG partial sums are combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(1024)
 pool_norm_kernel(const float* __restrict__ x, float* __restrict__ pooled, const float* __restrict__ g1,
                  const float* __restrict__ b1, float eps1, const float* __restrict__ g2,
                  const float* __restrict__ b2, float eps2, int N, int D, int variant) {
-  extern __shared__ float sm[];  // [2*D + 8]
-  float* v0 = sm;
-  float* v1 = sm + D;
-  float* red = sm + 2 * D;
+  extern __shared__ float sm[];  // [TG*D (pool partials) | 2*D | 8]
   const float* xb = x + (size_t)blockIdx.x * N * D;
+  const int nv = D / 4;                       // float4 columns
+  const int TG = blockDim.x / nv;             // token groups (>= 1)
+  float* part = sm;                           // [TG][D]
+  float* v0 = sm + (size_t)TG * D;
+  float* v1 = v0 + D;
+  float* red = v1 + D;
   if (variant == TPAT_VARIANT_AUDIOMAE) {
     // x[:, 1:, :].mean(dim=1) -> fc_norm   (models_vit.py:388-389)
+    const int tg = threadIdx.x / nv, c4 = threadIdx.x - tg * nv;
+    if (tg < TG) {
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+      int t = 1 + tg;
+      for (; t + 3 * TG < N; t += 4 * TG) {
+        const float4 u0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)t * D) + c4);
+        const float4 u1 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)(t + TG) * D) + c4);
+        const float4 u2 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)(t + 2 * TG) * D) + c4);
+        const float4 u3 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)(t + 3 * TG) * D) + c4);
+        a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+        a1.x += u1.x; a1.y += u1.y; a1.z += u1.z; a1.w += u1.w;
+        a2.x += u2.x; a2.y += u2.y; a2.z += u2.z; a2.w += u2.w;
+        a3.x += u3.x; a3.y += u3.y; a3.z += u3.z; a3.w += u3.w;
+      }
+      for (; t < N; t += TG) {
+        const float4 u0 = __ldg(reinterpret_cast<const float4*>(xb + (size_t)t * D) + c4);
+        a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+      }
+      reinterpret_cast<float4*>(part + (size_t)tg * D)[c4] =
+          make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                      (a0.w + a1.w) + (a2.w + a3.w));
+    }
+    __syncthreads();
     const float inv = 1.0f / (float)(N - 1);
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
       float s = 0.f;
-      for (int t = 1; t < N; ++t) s += __ldg(xb + (size_t)t * D + c);
+      for (int g = 0; g < TG; ++g) s += part[(size_t)g * D + c];
       v0[c] = s * inv;
     }
     __syncthreads();
@@ -154,6 +183,34 @@ pool_norm_kernel(const float* __restrict__ x, float* __restrict__ pooled, const 
     block_layernorm_inplace(v0, D, g2, b2, eps2, red);
   }
   for (int c = threadIdx.x; c < D; c += blockDim.x) pooled[(size_t)blockIdx.x * D + c] = v0[c];
+}
+
+// Classifier head: logits[b, c] = pooled[b, :] . W[c, :] + bias[c].  One warp per class keeps W[c, :] in
+// registers (D <= 1024 -> 32 floats per lane) and loops over the clips; pooled rows come from L1/L2.
+// Replaces self.head / mlp_head[1] (models_vit.py:522; ast_models.py:503).  fp32, fixed summation order.
+template <int NV>
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ pooled, const float* __restrict__ W, const float* __restrict__ bias,
+            float* __restrict__ logits, int B, int C) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= C) return;
+  float4 w[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)c * D) + lane + 32 * i);
+  const float bc = bias ? __ldg(bias + c) : 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float4* pr = reinterpret_cast<const float4*>(pooled + (size_t)b * D);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 pv = __ldg(pr + lane + 32 * i);
+      s = fmaf(pv.x, w[i].x, s); s = fmaf(pv.y, w[i].y, s); s = fmaf(pv.z, w[i].z, s); s = fmaf(pv.w, w[i].w, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) logits[(size_t)b * C + c] = s + bc;
+  }
 }
 
 template <typename OutT>
@@ -228,10 +285,35 @@ extern "C" int tpat_pool_norm(const float* x, float* pooled, const float* g1, co
   TPAT_CHECK(x && pooled && g1 && b1, "tpat_pool_norm: null pointer");
   TPAT_CHECK(variant == TPAT_VARIANT_AUDIOMAE || variant == TPAT_VARIANT_AST, "tpat_pool_norm: bad variant %d", variant);
   TPAT_CHECK(variant == TPAT_VARIANT_AUDIOMAE || (g2 && b2), "tpat_pool_norm: AST needs the mlp_head LayerNorm parameters");
-  TPAT_CHECK(B >= 0 && N >= 2 && D > 0 && D <= 4096, "tpat_pool_norm: bad sizes N=%d D=%d", N, D);
+  TPAT_CHECK(B >= 0 && N >= 2 && D > 0 && D <= 2048, "tpat_pool_norm: bad sizes N=%d D=%d", N, D);
   if (B == 0) return 0;
-  const size_t smem = (size_t)(2 * D + 8) * sizeof(float);
-  pool_norm_kernel<<<B, 256, smem, as_stream(stream)>>>(x, pooled, g1, b1, eps1, g2, b2, eps2, N, D, variant);
+  TPAT_CHECK(D % 4 == 0 && D <= 2048, "tpat_pool_norm: D must be a multiple of 4 and <= 2048");
+  const int threads = 1024;
+  const int TG = threads / (D / 4);
+  const size_t smem = ((size_t)TG * D + 2 * D + 32) * sizeof(float);
+  pool_norm_kernel<<<B, threads, smem, as_stream(stream)>>>(x, pooled, g1, b1, eps1, g2, b2, eps2, N, D, variant);
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tpat_head(const float* pooled, const float* W, const float* bias, float* logits, int B, int D, int C,
+                         tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(pooled && W && logits, "tpat_head: null pointer");
+  TPAT_CHECK(B >= 0 && C > 0 && D > 0 && D % 128 == 0 && D <= 1024, "tpat_head: need D %% 128 == 0, D <= 1024 (D=%d)", D);
+  TPAT_CHECK(aligned16(pooled) && aligned16(W), "tpat_head: pooled and W must be 16-byte aligned");
+  if (B == 0) return 0;
+  const int grid = (C + 7) / 8;
+  cudaStream_t st = as_stream(stream);
+  switch (D / 128) {
+    case 1: head_kernel<1><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
+    case 2: head_kernel<2><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
+    case 3: head_kernel<3><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
+    case 4: head_kernel<4><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
+    case 6: head_kernel<6><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
+    case 8: head_kernel<8><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
+    default: set_error("tpat_head: unsupported D=%d", D); return 1;
+  }
   TPAT_LAUNCH_CHECK();
   return 0;
 }

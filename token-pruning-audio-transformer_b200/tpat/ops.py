@@ -125,3 +125,13 @@ def pool_norm(x: torch.Tensor, variant: int, g1, b1, eps1: float, g2=None, b2=No
     check(lib.tpat_pool_norm(x.data_ptr(), out.data_ptr(), g1.data_ptr(), b1.data_ptr(), float(eps1), _ptr(g2), _ptr(b2),
                              float(eps2), B, N, D, variant, _stream()), "tpat_pool_norm")
     return out
+
+
+def head(pooled: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """logits = pooled @ w.T + bias (fp32)."""
+    _req(pooled, torch.float32, "pooled"); _req(w, torch.float32, "w")
+    B, D = pooled.shape
+    C = w.shape[0]
+    out = torch.empty(B, C, device=pooled.device, dtype=torch.float32)
+    check(lib.tpat_head(pooled.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), B, D, C, _stream()), "tpat_head")
+    return out
