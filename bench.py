@@ -64,7 +64,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the first warm-up step to the end of
+    the end-to-end region (the GPU is under the benchmark's load for that whole window)."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -74,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -198,7 +199,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU per step")
@@ -238,14 +239,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     with torch.no_grad():
         for i in range(args.warmup):
             model(resident[i % NROT])
         launches_per_step = model._engine.last_launch_count
         # ---- timed region 1: inputs resident in HBM ----
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -254,7 +255,6 @@ def main():
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
 
         # ---- timed region 2: end to end (pinned host -> device, forward, logits + kept indices -> host) ----
         stage = [torch.empty_like(resident[0]) for _ in range(2)]
@@ -291,6 +291,7 @@ def main():
         e2e_loop(args.steps)
         barrier()
         e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([ms_total, e2e_s], device=device, dtype=torch.float64)
     if world > 1:

@@ -101,3 +101,25 @@ def test_attention_tc(N, extra, mode):
         assert rel_err(score, ref) < 2e-5
         score_simt, _ = ops.score_topk(simt_partial, div, extra, 0)
         assert rel_err(score, score_simt) < 2e-5
+
+
+@pytest.mark.parametrize("N,extra", [(513, 1), (514, 2), (200, 1)])
+def test_attention_tc_online_softmax_rescale(N, extra):
+    """Single-pass tiles: keys whose scores grow with the key index force the lazily rescaled online
+    softmax to raise its reference max (and rescale O in TMEM) several times per row."""
+    from tpat import ops, _lib
+    g = torch.Generator().manual_seed(22)
+    B, H = 2, 12
+    x = torch.randn(B, N, 3, H, 64, generator=g) * 1.5
+    ramp = 1.0 + 6.0 * torch.arange(N, dtype=torch.float32) / N
+    x[:, :, 1] *= ramp[None, :, None, None]                      # K rows get larger with the key index
+    qkv = x.reshape(B * N, 3 * H * 64).to(dev()).to(torch.bfloat16)
+    out, _ = ops.attention(qkv, B, N, H, extra, _lib.SCORE_NONE, _lib.IMPL_TC)
+    ref_out, attn = ref_attention(qkv, B, N, H, extra)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.float(), ref_out) < 1e-2
+    # the same inputs through the two-pass (score) tiles must agree with the single-pass tiles
+    out2, partial = ops.attention(qkv, B, N, H, extra, _lib.SCORE_COLMEAN, _lib.IMPL_TC)
+    assert rel_err(out.float(), out2.float()) < 1e-2
+    score, _ = ops.score_topk(partial, H * (N - extra), extra, 0)
+    assert rel_err(score, ref_score(attn, extra, "colmean")) < 2e-5

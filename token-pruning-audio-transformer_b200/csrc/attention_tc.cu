@@ -9,15 +9,23 @@
 //   warp 1   MMA issuer (one elected thread): S = Q K^T (M=128,N=64,K=64) into one of two TMEM
 //            buffers; O += P V (M=128,N=64,K<=64) with P from 128B-swizzled smem, V as MN-major B
 //   warps 2-5 softmax: thread = query row = TMEM lane; 64 scores per thread per key block.
-// Exact softmax in two passes over the keys (the score needs the final row normaliser before
-// any column can be accumulated):
-//   pass 1  S -> running row max (+ running sum of exp only in warps that must emit normalised P)
-//   pass 2  S recomputed -> P = 2^(s*c - m*c - log2 l) in fp32 (one FFMA + one MUFU.EX2 per element)
-//           -> score partials (fp32 warp transpose-reduce, fixed order, no atomics) -> bf16 P -> O += P V
-// Warps that do not emit scores track the max only in pass 1, use unnormalised P and divide O by
-// the row sum at the end.  The N x N matrix never leaves the SM; O leaves through one TMA store.
+//
+// Two instantiations:
+//  TWO_PASS = true  (tiles that must emit NORMALISED probabilities for the importance score; the
+//            score needs the final row normaliser before any column can be accumulated)
+//            pass 1: S -> running row max and sum of exp;  pass 2: S recomputed ->
+//            P = 2^(s*c - m*c - log2 l) (one FFMA + one MUFU.EX2 per element) -> score partials from
+//            the fp32 probabilities (warp transpose-reduce, fixed order, no atomics) -> bf16 P -> O += P V.
+//  TWO_PASS = false (every other tile) single pass with a lazily rescaled online softmax: the
+//            reference max m_ref is only raised when a tile's max exceeds it by more than 2^8 (P stays
+//            <= 256, exact in bf16/fp32 range); then O (TMEM) and the running sum are rescaled once by
+//            the softmax warp itself.  O is divided by the row sum at the end.  One exp and one QK^T
+//            per element, K streamed once.
+// The N x N matrix never leaves the SM; O leaves through one TMA store.
 #include "attention.cuh"
 #include "ptx_sm100.cuh"
+
+#include <cstdlib>
 
 namespace tpat {
 
@@ -26,21 +34,62 @@ int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld,
 constexpr int AT_BM = 128;          // queries per CTA
 constexpr int AT_BK = 64;           // keys per block
 constexpr int AT_HD = 64;
-constexpr int AT_SLOTS = 6;         // K/V ring slots
+#ifndef AT_CTAS_PER_SM
+#define AT_CTAS_PER_SM 2            // resident CTAs per SM (2: two S buffers, 6 ring slots; 3: one S buffer, 3 ring slots)
+#endif
+constexpr int AT_SBUF = AT_CTAS_PER_SM >= 3 ? 1 : 2;      // S accumulators in TMEM
+constexpr int AT_SLOTS = AT_CTAS_PER_SM >= 3 ? 3 : 6;     // K/V ring slots
 constexpr int AT_Q_BYTES = AT_BM * AT_HD * 2;    // 16 KB (also one P buffer / the O staging tile)
 constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;   // 8 KB
 constexpr int AT_P_BYTES = AT_BM * AT_BK * 2;    // 16 KB
 constexpr int AT_THREADS = 192;
-constexpr int AT_TMEM_COLS = 256;   // S0 [0,64) S1 [64,128) O [128,192)
+constexpr int AT_TMEM_COLS = AT_SBUF == 1 ? 128 : 256;   // S buffers [0, 64*SBUF), then O (64 columns)
+constexpr int AT_SMEM_LIMIT = 113 * 1024;   // per-CTA cap (two CTAs / SM); single-pass tiles need 74 KB, so three fit
+constexpr float AT_RESCALE_LOG2 = 8.0f;   // online softmax: raise the reference max only past 2^8
+#ifndef AT_POLY_EVERY
+#define AT_POLY_EVERY 0                   // every AT_POLY_EVERY-th probability of a full single-pass tile uses exp2_poly (0 = none;
+                                          // measured r01: 2/4/8 are all SLOWER than 0 -- the kernel is latency-, not MUFU-bound)
+#endif
+
+#ifdef TPAT_ATTN_TRACE
+#define ATTN_TRACE(slot) do { if (tracing && trace_n < 120) p.trace[trace_n++] = clock64() - t_start + ((long long)(slot) << 48); } while (0)
+#else
+#define ATTN_TRACE(slot) do { } while (0)
+#endif
 
 struct AttnTcParams {
+  long long* trace;   // debug only (TPAT_ATTN_TRACE builds): clock stamps of one softmax thread
   float* score_partial;
   int score_mode;
-  int N, H, num_extra, n_qt, nb;
+  int N, H, num_extra, n_qt, nb, qt_offset;
   float scale_log2;  // scale * log2(e)
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// bf16 row segment (32 probabilities) -> 128B-swizzled K-major tile row
+__device__ __forceinline__ void store_p_half(uint8_t* p_row, int hf, int r_local, const float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(p_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) =
+        make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                   pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+}
+
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic minimax for 2^f
+// (relative error <= 2.4e-4, far below the bf16 rounding of P), exponent n added into the float's bits.
+// Used for every other probability of the single-pass tiles so that the 16-lane/clk MUFU.EX2 pipe and the
+// FMA pipes work in parallel (the exp count, not the tensor core, bounds this kernel).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.0574900442f, 0.242630517f);
+  p = fmaf(p, f, 0.692895364f);
+  p = fmaf(p, f, 0.999916112f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <bool TWO_PASS>
+__global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -52,7 +101,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t* q_full = bars;                 // [1]
   uint64_t* kv_full = bars + 1;            // [SLOTS]
   uint64_t* kv_empty = kv_full + AT_SLOTS; // [SLOTS]
-  uint64_t* s_full = kv_empty + AT_SLOTS;  // [2]
+  uint64_t* s_full = kv_empty + AT_SLOTS;  // [2] (AT_SBUF used)
   uint64_t* s_empty = s_full + 2;          // [2]
   uint64_t* p_full = s_empty + 2;          // [2]
   uint64_t* p_empty = p_full + 2;          // [2]
@@ -61,7 +110,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   float* colsum_s = reinterpret_cast<float*>(bars + 32);  // [4][nb*64] when COLMEAN
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qt = blockIdx.x + p.qt_offset, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * AT_BM;
   const int nb = p.nb;
 
@@ -75,7 +124,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int s = 0; s < AT_SLOTS; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&s_empty[i], 4);
-      ptx::mbar_init(&p_full[i], 128); ptx::mbar_init(&p_empty[i], 1);
+      ptx::mbar_init(&p_full[i], 4); ptx::mbar_init(&p_empty[i], 1);
     }
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
@@ -88,7 +137,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 2 * AT_BK;
+  const uint32_t tmem_o = tmem_base + AT_SBUF * AT_BK;
 
   const int col_q = h * AT_HD, col_k = (p.H + h) * AT_HD, col_v = (2 * p.H + h) * AT_HD;
 
@@ -104,8 +153,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::tma_load_3d(kv_s + slot * AT_KV_BYTES, &tmap_kv, &kv_full[slot], col, key0, b);
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
       };
-      for (int j = 0; j < nb; ++j) load_tile(col_k, j * AT_BK);      // pass 1: K_0 .. K_{nb-1}
-      // pass 2, in the order the MMA warp consumes them: K_0, K_1, V_0, K_2, V_1, ..., V_{nb-1}
+      if (TWO_PASS)
+        for (int j = 0; j < nb; ++j) load_tile(col_k, j * AT_BK);    // pass 1: K_0 .. K_{nb-1}
+      // main pass, in the order the MMA warp consumes them: K_0, K_1, V_0, K_2, V_1, ..., V_{nb-1}
       load_tile(col_k, 0);
       for (int j = 0; j < nb; ++j) {
         if (j + 1 < nb) load_tile(col_k, (j + 1) * AT_BK);
@@ -118,12 +168,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(128, AT_BK, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = ptx::idesc_bf16_f32(128, AT_HD, 0, 1);  // P (K-major) x V (MN-major)
       int slot = 0; uint32_t phase = 0;
-      int sidx = 0;  // running S-tile counter: buffer = sidx & 1, use count = sidx >> 1
+      int sidx = 0;  // running S-tile counter: buffer = sidx % AT_SBUF, use count = sidx / AT_SBUF
       const uint64_t q_desc = ptx::smem_desc_sw128(ptx::smem_u32(q_s), 16, 1024);
       auto issue_s = [&]() {
-        const int sb = sidx & 1;
+        const int sb = sidx % AT_SBUF;
         ptx::mbar_wait(&kv_full[slot], phase);
-        ptx::mbar_wait(&s_empty[sb], ((sidx >> 1) & 1) ^ 1);
+        ptx::mbar_wait(&s_empty[sb], ((sidx / AT_SBUF) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint64_t k_desc = ptx::smem_desc_sw128(ptx::smem_u32(kv_s + slot * AT_KV_BYTES), 16, 1024);
 #pragma unroll
@@ -135,8 +185,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ++sidx;
       };
       ptx::mbar_wait(q_full, 0);
-      for (int j = 0; j < nb; ++j) issue_s();            // pass 1
-      issue_s();                                         // pass 2: S(0)
+      if (TWO_PASS)
+        for (int j = 0; j < nb; ++j) issue_s();          // pass 1
+      issue_s();                                         // main pass: S(0)
       for (int j = 0; j < nb; ++j) {
         if (j + 1 < nb) issue_s();                       // S(j+1) overlaps the softmax of block j
         const int pb = j & 1;
@@ -166,24 +217,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int row = q0 + r_local;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float c = p.scale_log2;
-    // warps that must emit NORMALISED probabilities need the row sum before pass 2 (warp-uniform)
-    const bool norm_in_pass2 = (p.score_mode == TPAT_SCORE_COLMEAN) ||
-                               (p.score_mode == TPAT_SCORE_CLS_ROW && qt == 0 && quarter == 0);
     float m_run = -INFINITY, l_run = 0.f;
     int sidx = 0;
-    // ---- pass 1: row max (+ sum of exp where needed) ----
-    for (int j = 0; j < nb; ++j, ++sidx) {
-      const int sb = sidx & 1;
-      ptx::mbar_wait(&s_full[sb], (sidx >> 1) & 1);
-      ptx::tc_fence_after();
-      const int valid = p.N - j * AT_BK;                 // > 0
-      uint32_t r0[32], r1[32];
+#ifdef TPAT_ATTN_TRACE
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == (gridDim.z >> 1) && threadIdx.x == 64;
+    int trace_n = 0;
+    long long t_start = 0;
+    if (tracing) { t_start = clock64(); }
+    ATTN_TRACE(1);
+#endif
+
+    // load one 64-column S tile (only the 32-column halves that hold valid keys), release the TMEM
+    // buffer as soon as the values are in registers, mask the columns >= N of a boundary tile to -inf
+    auto load_s = [&](int sb, int valid, uint32_t (&r0)[32], uint32_t (&r1)[32]) {
       ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK, r0);
       if (valid > 32) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + 32, r1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);     // values are in registers: release the buffer early
+      if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);
       if (valid < 32) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) if (i >= valid) r0[i] = 0xff800000u;   // -inf
@@ -191,15 +243,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) if (32 + i >= valid) r1[i] = 0xff800000u;
       }
-      float mx0 = m_run, mx1 = -INFINITY;
+    };
+    auto tile_max = [&](int valid, const uint32_t (&r0)[32], const uint32_t (&r1)[32], float seed) {
+      float mx0 = seed, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1])); }
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r0[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r0[i + 3]));
+      }
       if (valid > 32) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(r1[i])); mx1 = fmaxf(mx1, __uint_as_float(r1[i + 1])); }
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(r1[i])); mx1 = fmaxf(mx1, __uint_as_float(r1[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(r1[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r1[i + 3]));
+        }
       }
-      const float mx = fmaxf(mx0, mx1);
-      if (norm_in_pass2) {
+      return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    };
+
+    if (TWO_PASS) {
+      // ---- pass 1: row max and sum of exp ----
+      for (int j = 0; j < nb; ++j, ++sidx) {
+        const int sb = sidx % AT_SBUF;
+        ptx::mbar_wait(&s_full[sb], (sidx / AT_SBUF) & 1);
+        ptx::tc_fence_after();
+        const int valid = p.N - j * AT_BK;                 // > 0
+        uint32_t r0[32], r1[32];
+        load_s(sb, valid, r0, r1);
+        const float mx = tile_max(valid, r0, r1, m_run);
         const float mc = mx * c;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -219,29 +290,58 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
         }
         l_run = l_run * ptx::ex2_ftz((m_run - mx) * c) + ((a0 + a1) + (a2 + a3));
+        m_run = mx;
       }
-      m_run = mx;
     }
-    // exponent offset: p = 2^(s*c - off);  normalised warps fold log2(l) into the offset
-    const float off = norm_in_pass2 ? fmaf(m_run, c, __log2f(l_run)) : m_run * c;
+    // exponent offset: p = 2^(s*c - off).  Two-pass tiles fold log2(l) in (normalised probabilities).
+    float off = TWO_PASS ? fmaf(m_run, c, __log2f(l_run)) : 0.f;
     const float row_w = (row >= p.num_extra && row < p.N) ? 1.0f : 0.f;
-    const bool cls_writer = (p.score_mode == TPAT_SCORE_CLS_ROW) && (row == 0);
+    const bool cls_writer = TWO_PASS && (p.score_mode == TPAT_SCORE_CLS_ROW) && (row == 0);
     float* colsum_w = colsum_s + (size_t)quarter * nb * AT_BK;
     float l2a = 0.f, l2b = 0.f, l2c = 0.f, l2d = 0.f;
-    // ---- pass 2: probabilities, score partials, P -> smem ----
+    // ---- main pass: probabilities, score partials, P -> smem ----
     for (int j = 0; j < nb; ++j, ++sidx) {
-      const int sb = sidx & 1, pb = j & 1;
-      ptx::mbar_wait(&s_full[sb], (sidx >> 1) & 1);
+      const int sb = sidx % AT_SBUF, pb = j & 1;
+      ATTN_TRACE(2);
+      ptx::mbar_wait(&s_full[sb], (sidx / AT_SBUF) & 1);
       ptx::tc_fence_after();
+      ATTN_TRACE(3);
       const int valid = p.N - j * AT_BK;                 // > 0
       uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK, r0);
-      if (valid > 32) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + 32, r1);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);
-      ptx::mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);  // PV(j-2) has consumed this P buffer
+      load_s(sb, valid, r0, r1);
+      ATTN_TRACE(4);
+      if (!TWO_PASS) {
+        // lazily rescaled online softmax
+        const float mx = tile_max(valid, r0, r1, -INFINITY);
+        if (j == 0) {
+          m_run = mx;                                    // O is still uninitialised: nothing to rescale
+        } else {
+          const bool need = (mx - m_run) * c > AT_RESCALE_LOG2;
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = need ? ptx::ex2_ftz((m_run - mx) * c) : 1.0f;
+            if (need) m_run = mx;
+            l2a *= f; l2b *= f; l2c *= f; l2d *= f;
+            // every PV issued so far (up to block j-1) must have retired before O is touched
+            ptx::mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int oh = 0; oh < 2; ++oh) {
+              uint32_t o0[32];
+              ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + oh * 32, o0);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * f);
+              ptx::tmem_st_32x32b_x32(tmem_o + lane_off + oh * 32, o0);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+          }
+        }
+        off = m_run * c;
+      }
+      ATTN_TRACE(5);
+      // P buffer pb was last read by PV(j-2), which the MMA thread issued BEFORE S(j); tcgen05 operations retire
+      // in issue order and s_full(j) is a commit of everything issued before it, so the buffer is already free.
       uint8_t* p_row = p_s + pb * AT_P_BYTES + r_local * 128;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -257,67 +357,68 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           continue;
         }
         float v[32];
+        if (!TWO_PASS && AT_POLY_EVERY > 0 && vh >= 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));
-        if (vh < 32) {
+          for (int i = 0; i < 32; ++i) {
+            const float x = fmaf(__uint_as_float(r[i]), c, -off);
+            v[i] = (AT_POLY_EVERY > 0 && (i % (AT_POLY_EVERY > 0 ? AT_POLY_EVERY : 1)) == (AT_POLY_EVERY - 1)) ? exp2_poly(x) : ptx::ex2_ftz(x);
+          }
+        } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (i >= vh) v[i] = 0.f;
+          for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));   // -inf -> 0
         }
-        if (!norm_in_pass2) {
+        if (!TWO_PASS) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
         }
-        // bf16 P row segment -> 128B-swizzled K-major tile
+        store_p_half(p_row, hf, r_local, v);
+        if (TWO_PASS) {
+          if (p.score_mode == TPAT_SCORE_COLMEAN) {
+            // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<uint4*>(p_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) =
-              make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                         pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
-        if (p.score_mode == TPAT_SCORE_COLMEAN) {
-          // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
+            for (int i = 0; i < 32; ++i) v[i] *= row_w;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= row_w;
+            for (int o = 16; o >= 1; o >>= 1) {
+              const bool upper = (lane & o) != 0;
 #pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) {
-            const bool upper = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < o; ++i) {
-              const float send = upper ? v[i] : v[i + o];
-              const float keep = upper ? v[i + o] : v[i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              for (int i = 0; i < o; ++i) {
+                const float send = upper ? v[i] : v[i + o];
+                const float keep = upper ? v[i + o] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              }
             }
+            colsum_w[col0 + lane] = v[0];
+          } else if (cls_writer) {
+            float* dst = p.score_partial + ((size_t)b * p.H + h) * p.N;
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) dst[col0 + i] = v[i];
           }
-          colsum_w[col0 + lane] = v[0];
-        } else if (cls_writer) {
-          float* dst = p.score_partial + ((size_t)b * p.H + h) * p.N;
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) dst[col0 + i] = v[i];
         }
       }
-      ptx::fence_proxy_async_smem();   // make the generic-proxy P writes visible to the tensor core
-      ptx::mbar_arrive(&p_full[pb]);
+      ATTN_TRACE(7);
+      ptx::fence_proxy_async_smem();   // make this thread's generic-proxy P writes visible to the tensor core
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
+      ATTN_TRACE(8);
     }
     // ---- epilogue: O (TMEM) -> bf16 -> swizzled smem tile -> one TMA store ----
+    ATTN_TRACE(9);
     ptx::mbar_wait(o_full, 0);         // every PV MMA retired: the P buffers are free as well
     ptx::tc_fence_after();
-    const float o_scale = norm_in_pass2 ? 1.0f : 1.0f / ((l2a + l2b) + (l2c + l2d));
+    ATTN_TRACE(10);
+    const float o_scale = TWO_PASS ? 1.0f : 1.0f / ((l2a + l2b) + (l2c + l2d));
     {
       uint32_t r0[32], r1[32];
       ptx::tmem_ld_32x32b_x32(tmem_o + lane_off, r0);
       ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + 32, r1);
       ptx::tmem_ld_wait();
-      uint8_t* o_row = p_s + r_local * 128;
+      float v[32];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t (&r)[32] = hf == 0 ? r0 : r1;
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) * o_scale;
+      store_p_half(p_s + r_local * 128, 0, r_local, v);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<uint4*>(o_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) =
-              make_uint4(pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * o_scale, __uint_as_float(r[g * 8 + 1]) * o_scale),
-                         pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * o_scale, __uint_as_float(r[g * 8 + 3]) * o_scale),
-                         pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * o_scale, __uint_as_float(r[g * 8 + 5]) * o_scale),
-                         pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * o_scale, __uint_as_float(r[g * 8 + 7]) * o_scale));
-      }
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r1[i]) * o_scale;
+      store_p_half(p_s + r_local * 128, 1, r_local, v);
     }
     ptx::fence_proxy_async_smem();
     asm volatile("bar.sync 1, 128;\n" ::: "memory");
@@ -325,7 +426,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       ptx::tma_store_3d(&tmap_o, p_s, h * AT_HD, q0, b);   // rows >= N are clipped by the tensor map
       ptx::tma_store_commit();
     }
-    if (p.score_mode == TPAT_SCORE_COLMEAN) {
+    if (TWO_PASS && p.score_mode == TPAT_SCORE_COLMEAN) {
       // sum the four warps' column sums in a fixed order and publish this tile's partial row
       float* dstp = p.score_partial + ((size_t)b * p.H * p.n_qt + (size_t)h * p.n_qt + qt) * p.N;
       const int ldc = nb * AT_BK;
@@ -333,6 +434,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         dstp[jcol] = ((colsum_s[jcol] + colsum_s[ldc + jcol]) + colsum_s[2 * ldc + jcol]) + colsum_s[3 * ldc + jcol];
     }
     if (warp == 2 && lane == 0) ptx::tma_store_wait_read<0>();   // smem must outlive the bulk store's reads
+    ATTN_TRACE(11);
+#ifdef TPAT_ATTN_TRACE
+    if (tracing) p.trace[127] = trace_n;
+#endif
   }
 
   ptx::tc_fence_before();
@@ -343,7 +448,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
+#ifdef TPAT_ATTN_TRACE
+long long* g_attn_trace_buf = nullptr;
+extern "C" int tpat_debug_attn_trace(long long* host_out) {   // debug builds only: copy the 128 stamps to the host
+  if (!g_attn_trace_buf) return 1;
+  return cudaMemcpy(host_out, g_attn_trace_buf, 128 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
+#endif
+
 int attention_tc_qtiles(int N) { return (N + AT_BM - 1) / AT_BM; }
+
+template <bool TWO_PASS>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to, const AttnTcParams& p,
+                       dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = attention_tc_kernel<TWO_PASS>;
+  if (!attr_set) {
+    TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_LIMIT));
+    TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("TPAT_DEBUG")) {
+      int nblk = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, AT_THREADS, smem);
+      fprintf(stderr, "[tpat] attention_tc_kernel<%d>: %d CTAs/SM at %zu B smem\n", (int)TWO_PASS, nblk, smem);
+    }
+    attr_set = true;
+  }
+  kern<<<grid, AT_THREADS, smem, st>>>(tq, tkv, to, p);
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
 
 int attention_tc(const void* qkv, void* out, float* score_partial, int score_mode, int B, int N, int H,
                  int num_extra, float scale, cudaStream_t st) {
@@ -353,24 +486,31 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
   if (int rc = encode_tmap_3d_qkv(&tm_kv, qkv, B, N, 3 * H * AT_HD, AT_BK)) return rc;
   if (int rc = encode_tmap_3d_qkv(&tm_o, out, B, N, H * AT_HD, AT_BM)) return rc;
   AttnTcParams p;
+  p.trace = nullptr;
+#ifdef TPAT_ATTN_TRACE
+  { static long long* dbg = nullptr; if (!dbg) { cudaMalloc(&dbg, 128 * sizeof(long long)); } cudaMemsetAsync(dbg, 0, 128 * sizeof(long long), st); p.trace = dbg;
+    extern long long* g_attn_trace_buf; g_attn_trace_buf = dbg; }
+#endif
   p.score_partial = score_partial;
   p.score_mode = score_mode;
   p.N = N; p.H = H; p.num_extra = num_extra;
   p.n_qt = attention_tc_qtiles(N);
   p.nb = (N + AT_BK - 1) / AT_BK;
+  p.qt_offset = 0;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const size_t colsum_bytes = score_mode == TPAT_SCORE_COLMEAN ? (size_t)4 * p.nb * AT_BK * sizeof(float) : 0;
-  const size_t smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_SLOTS * AT_KV_BYTES + 256 + colsum_bytes;
-  TPAT_CHECK(smem <= 227 * 1024, "tpat_attention(tc): N=%d needs %zu bytes of shared memory", N, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    TPAT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  const size_t base_smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_SLOTS * AT_KV_BYTES + 256;
+  const size_t colsum_bytes = (size_t)4 * p.nb * AT_BK * sizeof(float);
+  TPAT_CHECK(base_smem + (score_mode == TPAT_SCORE_COLMEAN ? colsum_bytes : 0) <= (size_t)AT_SMEM_LIMIT,
+             "tpat_attention(tc): N=%d needs %zu bytes of shared memory", N, base_smem + colsum_bytes);
+  if (score_mode == TPAT_SCORE_COLMEAN)       // every tile contributes normalised column sums
+    return launch_attn<true>(tm_q, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem + colsum_bytes, st);
+  if (score_mode == TPAT_SCORE_CLS_ROW) {     // only the tile holding query row 0 must normalise
+    if (int rc = launch_attn<true>(tm_q, tm_kv, tm_o, p, dim3(1, H, B), base_smem, st)) return rc;
+    if (p.n_qt == 1) return 0;
+    p.qt_offset = 1;
+    return launch_attn<false>(tm_q, tm_kv, tm_o, p, dim3(p.n_qt - 1, H, B), base_smem, st);
   }
-  dim3 grid(p.n_qt, H, B);
-  attention_tc_kernel<<<grid, AT_THREADS, smem, st>>>(tm_q, tm_kv, tm_o, p);
-  TPAT_LAUNCH_CHECK();
-  return 0;
+  return launch_attn<false>(tm_q, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem, st);
 }
 
 }  // namespace tpat

@@ -76,11 +76,17 @@ extern "C" size_t tpat_forward_workspace_bytes(const tpat_forward_args* a) {
 extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
   if (tpat::validate(a) != 0) return -1;
   int n = 2;  // patchify + patch GEMM
+  const int extra = a->variant == TPAT_VARIANT_AST ? 2 : 1;
+  int cur = (a->T / 16) * (a->F / 16);
   for (int i = 0; i < a->depth; ++i) {
     const bool prune = a->prune[i] != 0;
+    const bool score = prune || a->want_all_scores;
     n += 4;                                   // LN1, QKV, attention, proj
-    if (prune || a->want_all_scores) n += 1;  // score / top-k
+    // AST score blocks on the tensor-core path: the cls tile (two-pass) and the other tiles are separate launches
+    if (score && a->variant == TPAT_VARIANT_AST && a->impl == TPAT_IMPL_TC && tpat_attention_qtiles(extra + cur, a->impl) > 1) n += 1;
+    if (score) n += 1;                        // score / top-k
     n += 3;                                   // (gather+)LN2, fc1, fc2
+    cur = a->keep[i];
   }
   return n + 2;  // pool/norm + head
 }

@@ -10,7 +10,7 @@ import sys
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libtpat.so")
+LIB_PATH = os.environ.get("TPAT_LIB_PATH") or os.path.join(_PKG_ROOT, "lib", "libtpat.so")   # override: kernel experiments
 
 TPAT_MAX_DEPTH = 32
 F32, BF16 = 0, 1
