@@ -26,21 +26,30 @@ constexpr int T2_B_BYTES = 128 * TG_BK * 2;    // 16 KB: this CTA's 128 rows of 
 constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 constexpr int T2_STAGING_BYTES = tg_staging_bytes(T2_EPI_WARPS);
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + T2_STAGING_BYTES + 1024 + 256;
+// residual epilogue (proj, fc2): the fp32 residual chunk is TMA-prefetched into a second 4 KB buffer per warp
+constexpr int T2R_STAGES = 4;
+constexpr int T2R_STAGING_BYTES = 2 * T2_STAGING_BYTES;
+constexpr int T2R_SMEM_BYTES = T2R_STAGES * T2_STAGE_BYTES + T2R_STAGING_BYTES + 1024 + 512;
 
-template <int EPI, typename OutT>
+template <int EPI, typename OutT, bool RES_TMA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TcGemmParams p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_c, const TcGemmParams p) {
+  constexpr bool kResTma = RES_TMA && EPI == TPAT_EPI_BIAS_RESIDUAL;   // TMA-fed residual epilogue (short-K GEMMs)
+  constexpr int NSTAGES = kResTma ? T2R_STAGES : T2_STAGES;
+  constexpr int STAGING = kResTma ? T2R_STAGING_BYTES : T2_STAGING_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + T2_STAGES * T2_A_BYTES;
-  uint8_t* staging = smem + T2_STAGES * T2_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + T2_STAGING_BYTES);
+  uint8_t* smem_b = smem + NSTAGES * T2_A_BYTES;
+  uint8_t* staging = smem + NSTAGES * T2_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING);
   uint64_t* full_bar = bars;                    // [STAGES]  (used in the leader CTA)
-  uint64_t* empty_bar = bars + T2_STAGES;       // [STAGES]  (one per CTA, multicast commit)
-  uint64_t* acc_full = bars + 2 * T2_STAGES;    // [2]       (one per CTA, multicast commit)
+  uint64_t* empty_bar = bars + NSTAGES;         // [STAGES]  (one per CTA, multicast commit)
+  uint64_t* acc_full = bars + 2 * NSTAGES;      // [2]       (one per CTA, multicast commit)
   uint64_t* acc_empty = acc_full + 2;           // [2]       (used in the leader CTA, 2 x 12 remote arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* res_bar = acc_empty + 4;            // [EPI_WARPS][2] residual-chunk arrival (kResTma)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -54,7 +63,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     ptx::prefetch_tensormap(&tmap_w);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < T2_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NSTAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    if (kResTma) for (int i = 0; i < 2 * T2_EPI_WARPS; ++i) ptx::mbar_init(&res_bar[i], 1);
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], 2 * T2_EPI_WARPS); }
     ptx::fence_barrier_init();
   }
@@ -77,13 +87,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full_leader = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
-          const bool first_fill = tile == cluster_id && kb < T2_STAGES;
+          const bool first_fill = tile == cluster_id && kb < NSTAGES;
           const bool load_a = p.debug_skip != 1 || first_fill;
           const bool load_b = p.debug_skip == 0 || first_fill;
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * ((load_a ? T2_A_BYTES : 0) + (load_b ? T2_B_BYTES : 0)));
           if (load_a) ptx::tma_load_2d_2cta(smem_a + stage * T2_A_BYTES, &tmap_a, full_leader, kb * TG_BK, m0);
           if (load_b) ptx::tma_load_2d_2cta(smem_b + stage * T2_B_BYTES, &tmap_w, full_leader, kb * TG_BK, n0);
-          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -106,7 +116,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           for (int k = 0; k < TG_BK / TG_UMMA_K; ++k)
             ptx::mma_f16_ss_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           ptx::tc_commit_2cta(&empty_bar[stage], 0b11);   // stage free in both CTAs
-          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
         ptx::tc_commit_2cta(&acc_full[acc], 0b11);        // accumulator halves ready in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -116,18 +126,103 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===== epilogue warps 2..13 (both CTAs): this CTA's 128 rows of the 256 x 256 tile =====
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
-    uint8_t* stg = staging + (warp - 2) * 4096;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128 + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
-      TcEpiPrefetch<T2_EPI_WARPS> pf;
-      tc_epilogue_prefetch<T2_EPI_WARPS>(p, n0, cg, lane, pf);
-      ptx::mbar_wait(&acc_full[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
-      const uint32_t rel_leader = ptx::mapa_shared(ptx::smem_u32(&acc_empty[acc]), 0);
-      tc_epilogue_tile<EPI, OutT, T2_EPI_WARPS>(p, taddr_row, m0, n0, cg, stg, lane, pf, [&]() { if (lane == 0) ptx::mbar_arrive_cluster(rel_leader); });
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    if constexpr (!kResTma) {
+      uint8_t* stg = staging + (warp - 2) * 4096;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128 + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
+        TcEpiPrefetch<T2_EPI_WARPS> pf;
+        tc_epilogue_prefetch<T2_EPI_WARPS>(p, n0, cg, lane, pf);
+        ptx::mbar_wait(&acc_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
+        const uint32_t rel_leader = ptx::mapa_shared(ptx::smem_u32(&acc_empty[acc]), 0);
+        tc_epilogue_tile<EPI, OutT, T2_EPI_WARPS>(p, taddr_row, m0, n0, cg, stg, lane, pf, [&]() { if (lane == 0) ptx::mbar_arrive_cluster(rel_leader); });
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else {
+      // Residual epilogue: C = R + acc + bias with fp32 R / C.  Each warp walks its (tile, chunk) items with two
+      // 4 KB 128B-swizzled buffers: lane 0 TMA-loads the NEXT item's 32 x 32 residual block while the current one
+      // is combined (thread = row: read own swizzled row, add the tcgen05.ld fragment + bias, write back) and
+      // TMA-stored.  Loads do not depend on the MMA, so the first block of a tile is in flight before acc_full.
+      constexpr int CS = T2_EPI_WARPS / 4, NCH = (8 + CS - 1) / CS;
+      uint8_t* stg = staging + (warp - 2) * 8192;
+      uint64_t* rb = res_bar + (warp - 2) * 2;
+      int buf = 0; uint32_t rph0 = 0, rph1 = 0;
+      auto item_cols = [&](int tile, int ci) { return (tile % p.tiles_n) * TG_BN + (cg + CS * ci) * 32; };
+      auto item_live = [&](int tile, int ci) { return ci < NCH && cg + CS * ci < 8 && item_cols(tile, ci) < p.N; };
+      // first live item at or after (tile, ci) in this warp's walk order; tile >= num_tiles when there is none
+      auto next_live = [&](int& tile, int& ci) {
+        while (tile < num_tiles) {
+          if (ci >= NCH) { tile += num_clusters; ci = 0; continue; }
+          if (item_live(tile, ci)) return;
+          ++ci;
+        }
+      };
+      auto issue_load = [&](int tile, int ci, int b) {   // lane 0 only
+        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128 + q * 32;
+        ptx::tma_store_wait_read<0>();                   // the store that last read this buffer has drained its smem reads
+        ptx::mbar_arrive_expect_tx(&rb[b], 4096);
+        ptx::tma_load_2d(stg + b * 4096, &tmap_r, &rb[b], item_cols(tile, ci), m0);
+      };
+      {
+        int t0 = cluster_id, c0 = 0;
+        next_live(t0, c0);
+        if (t0 < num_tiles && lane == 0) issue_load(t0, c0, 0);
+      }
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128 + q * 32;
+        const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
+        const uint32_t rel_leader = ptx::mapa_shared(ptx::smem_u32(&acc_empty[acc]), 0);
+        ptx::mbar_wait(&acc_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        bool released = false;
+#pragma unroll 1
+        for (int ci = 0; ci < NCH; ++ci) {
+          const bool live = item_live(tile, ci);
+          uint32_t r[32];
+          if (live) {
+            ptx::tmem_ld_32x32b_x32(taddr_row + (cg + CS * ci) * 32, r);
+            ptx::tmem_ld_wait();
+          }
+          bool later = false;                            // does this warp read more of this accumulator?
+          for (int c2 = ci + 1; c2 < NCH; ++c2) later |= item_live(tile, c2);
+          if (!released && !later) {
+            released = true;
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(rel_leader);
+          }
+          if (!live) continue;
+          if (lane == 0) {                               // prefetch the residual block of this warp's next item
+            int nt = tile, nc = ci + 1;
+            next_live(nt, nc);
+            if (nt < num_tiles) issue_load(nt, nc, buf ^ 1);
+          }
+          const int n = item_cols(tile, ci);
+          ptx::mbar_wait(&rb[buf], buf ? rph1 : rph0);
+          if (buf) rph1 ^= 1; else rph0 ^= 1;
+          uint8_t* rowp = stg + buf * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* cell = reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4));
+            const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 x = *cell;
+            x.x += __uint_as_float(r[4 * j]) + bb.x; x.y += __uint_as_float(r[4 * j + 1]) + bb.y;
+            x.z += __uint_as_float(r[4 * j + 2]) + bb.z; x.w += __uint_as_float(r[4 * j + 3]) + bb.w;
+            *cell = x;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_c, stg + buf * 4096, n, m0);   // rows >= M are clipped by the tensor map
+            ptx::tma_store_commit();
+          }
+          buf ^= 1;
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) ptx::tma_store_wait<0>();           // all output blocks written before the CTA retires
     }
   }
 
@@ -139,18 +234,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int EPI, typename OutT>
-static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const TcGemmParams& p, cudaStream_t st) {
+template <int EPI, typename OutT, bool RES_TMA = false>
+static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr, const CUtensorMap& tc,
+                      const TcGemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = gemm_tc2_kernel<EPI, OutT>;
+  auto kern = gemm_tc2_kernel<EPI, OutT, RES_TMA>;
+  constexpr int smem_bytes = (RES_TMA && EPI == TPAT_EPI_BIAS_RESIDUAL) ? T2R_SMEM_BYTES : T2_SMEM_BYTES;
   if (!attr_set) {
-    TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, T2_THREADS, T2_SMEM_BYTES, st>>>(ta, tw, p);
+  kern<<<2 * clusters, T2_THREADS, smem_bytes, st>>>(ta, tw, tr, tc, p);
   TPAT_LAUNCH_CHECK();
   return 0;
 }
@@ -167,13 +264,22 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   { const char* e = getenv("TPAT_GEMM_DEBUG_SKIP"); p.debug_skip = e ? atoi(e) : 0; }
   switch (ep.epilogue) {
     case TPAT_EPI_BIAS:
-      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS, __nv_bfloat16>(ta, tw, p, st) : launch_tc2<TPAT_EPI_BIAS, float>(ta, tw, p, st);
+      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS, __nv_bfloat16>(ta, tw, ta, ta, p, st) : launch_tc2<TPAT_EPI_BIAS, float>(ta, tw, ta, ta, p, st);
     case TPAT_EPI_BIAS_GELU:
-      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16>(ta, tw, p, st) : launch_tc2<TPAT_EPI_BIAS_GELU, float>(ta, tw, p, st);
-    case TPAT_EPI_BIAS_RESIDUAL:
-      return launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float>(ta, tw, p, st);
+      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16>(ta, tw, ta, ta, p, st) : launch_tc2<TPAT_EPI_BIAS_GELU, float>(ta, tw, ta, ta, p, st);
+    case TPAT_EPI_BIAS_RESIDUAL: {
+      // Long-K GEMMs (fc2, K = 3072) hide the register-path epilogue behind the main loop and prefer the fifth
+      // pipeline stage; short-K ones (proj, K = 768) are bound by the residual read-modify-write and use the
+      // TMA-fed epilogue (measured r01: proj 0.081 -> 0.064 ms, fc2 0.129 -> 0.140 ms with it).
+      if (K > 1536) return launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, false>(ta, tw, ta, ta, p, st);
+      // fp32 residual in / C out as 32 x 32 blocks (128 B rows, 128B swizzle)
+      CUtensorMap tr, tc;
+      if (int rc = encode_tmap_2d(&tr, ep.residual, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldr * 4, 32, 32, true)) return rc;
+      if (int rc = encode_tmap_2d(&tc, C, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ldc * 4, 32, 32, true)) return rc;
+      return launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, true>(ta, tw, tr, tc, p, st);
+    }
     case TPAT_EPI_BIAS_POS:
-      return launch_tc2<TPAT_EPI_BIAS_POS, float>(ta, tw, p, st);
+      return launch_tc2<TPAT_EPI_BIAS_POS, float>(ta, tw, ta, ta, p, st);
   }
   set_error("tpat_gemm(tc2): bad epilogue %d", ep.epilogue);
   return 1;
