@@ -178,6 +178,11 @@ def micro_kernels(device, peaks):
     return out
 
 
+def workload_name(batch):
+    return (f"AudioMAE ViT-B/16 1024x128, 512 patches, TopK keep 0.7 @ blocks 3/6/9, {batch} clips/GPU/step "
+            f"(BASELINE.json configs[1])")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -186,8 +191,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": round(cps, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"AudioMAE ViT-B/16 1024x128, 512 patches, TopK keep 0.7 @ blocks 3/6/9, "
-                               f"{BATCH_PER_GPU} clips/GPU", "parallelism": "host CPU threads"},
+        "config": {"workload": workload_name(BATCH_PER_GPU), "parallelism": "host CPU threads (rank 0 only)"},
         "cpu_baseline": {"value": round(cps, 3), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{CPU_SAMPLE_CLIPS} clips per step (of the {BATCH_PER_GPU}-clip batch), oracle port of "
                                    f"the reference forward, fp32, torch CPU"},
@@ -309,8 +313,7 @@ def main():
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"AudioMAE ViT-B/16 1024x128, 512 patches, TopK keep 0.7 @ blocks 3/6/9, "
-                                   f"{B} clips/GPU/step (BASELINE.json configs[1])",
+            "config": {"workload": workload_name(B),
                        "global_batch": B * world, "parallelism": f"batch-sharded dp{world}, weights replicated",
                        "l2": f"inputs rotate over {NROT} batches ({NROT * B * T_FRAMES * F_BINS * 4 >> 20} MiB) and the "
                              f"~0.7 GB activation workspace is rewritten every step (> 126 MB L2)",

@@ -186,3 +186,32 @@ def test_weights_are_repacked_after_an_update():
         model.mlp_head[1].bias.add_(1.0)               # in-place update bumps the parameter version
         b = model(x.to(dev()))
     assert torch.allclose(b, a + 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("factory,dim,depth,heads", [("vit_small_patch16", 384, 12, 6), ("vit_large_patch16", 1024, 24, 16)])
+def test_other_vit_sizes_match_the_oracle(factory, dim, depth, heads):
+    """The reference also ships vit_small / vit_large factories (models_vit.py:531-548): same kernels, D = 64 * H."""
+    from oracle import weights
+    from tpat import models_vit
+    T, C, B = 256, 20, 2
+    sd = weights.make_audiomae_state_dict(C, T, seed=7, flavour="perturbed", depth=depth, dim=dim)
+    x = weights.make_spectrogram("audiomae", B, T, seed=8)
+    drop_loc = (1, 3, depth - 2)
+    with torch.no_grad():
+        ref_logits, ref_feats = vo.forward("audiomae", sd, x, None, drop_loc, 0.7, num_heads=heads)
+    for precision, tol in (("fp32", 2e-5), ("bf16", 1e-1)):
+        m = getattr(models_vit, factory)(num_classes=C, drop_path_rate=0.0, mean_pooling=True, mask_2d=True,
+                                         target_length=T, drop_loc=drop_loc, base_keep_rate=0.7, precision=precision)
+        m.patch_embed = models_vit.PatchEmbed((T, 128), 16, 1, dim)
+        m.pos_embed = nn.Parameter(torch.zeros(1, m.patch_embed.num_patches + 1, dim), requires_grad=False)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev()).eval()
+        with torch.no_grad():
+            logits = m(x.to(dev()))
+        err = rel_err(logits.cpu(), ref_logits)
+        print(f"[{precision}] {factory}: logits err {err:.2e}")
+        assert err < tol
+        if precision == "fp32":
+            first = f"block-{drop_loc[0]}.topk_idx"
+            for a, b in zip(m.last_topk_idx[drop_loc[0]].cpu().tolist(), ref_feats[first].tolist()):
+                assert set(a) == set(b)
