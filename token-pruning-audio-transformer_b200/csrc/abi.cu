@@ -1,6 +1,7 @@
 // Error plumbing and the trivial entry points of the C-ABI (include/tpat.h).
 #include "common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace tpat {
@@ -29,6 +30,12 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) { const char* e = getenv("TPAT_PDL"); cached = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  return cached == 1;
 }
 
 }  // namespace tpat

@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(256)
 attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ score_partial, int score_mode,
                       int N, int H, int num_extra, float scale, int n_qt) {
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   const int Npad = (N + AS_KC - 1) / AS_KC * AS_KC;
   const int lds = Npad + 4;
   float* Ss = sm;                              // [QT][lds]
@@ -178,11 +180,11 @@ int attention_simt(const void* qkv, void* out, int dtype, float* score_partial, 
   if (dtype == TPAT_F32) {
     auto kern = attention_simt_kernel<float>;
     TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    kern<<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, score_partial, score_mode, N, H, num_extra, scale, n_qt);
+    TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, (const float*)qkv, (float*)out, score_partial, score_mode, N, H, num_extra, scale, n_qt));
   } else {
     auto kern = attention_simt_kernel<__nv_bfloat16>;
     TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    kern<<<grid, 256, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, score_partial, score_mode, N, H, num_extra, scale, n_qt);
+    TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, score_partial, score_mode, N, H, num_extra, scale, n_qt));
   }
   TPAT_LAUNCH_CHECK();
   return 0;

@@ -109,6 +109,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
   float* colsum_s = reinterpret_cast<float*>(bars + 32);  // [4][nb*64] when COLMEAN
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x + p.qt_offset, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * AT_BM;
@@ -138,6 +139,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + AT_SBUF * AT_BK;
+  pdl_wait();   // everything above touched only on-chip state; global memory from here on
 
   const int col_q = h * AT_HD, col_k = (p.H + h) * AT_HD, col_v = (2 * p.H + h) * AT_HD;
 
@@ -473,7 +475,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUte
     }
     attr_set = true;
   }
-  kern<<<grid, AT_THREADS, smem, st>>>(tq, tkv, to, p);
+  TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(AT_THREADS), smem, st, tq, tkv, to, p));
   TPAT_LAUNCH_CHECK();
   return 0;
 }

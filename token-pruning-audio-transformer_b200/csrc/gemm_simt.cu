@@ -50,6 +50,8 @@ gemm_simt_kernel(const InT* __restrict__ A, int lda, const InT* __restrict__ W, 
                  int M, int N, int K, EpiParams ep) {
   __shared__ float As[2][SG_BK][SG_BM + SG_PAD];
   __shared__ float Ws[2][SG_BK][SG_BN + SG_PAD];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
   const int tx = tid & 15, ty = tid >> 4;
@@ -127,13 +129,13 @@ int gemm_simt(const void* A, int a_dtype, int lda, const void* W, void* C, int c
   TPAT_CHECK(aligned16(A) && aligned16(W) || a_dtype == TPAT_BF16, "tpat_gemm(simt): fp32 operands must be 16-byte aligned");
   dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
   if (a_dtype == TPAT_F32 && c_dtype == TPAT_F32)
-    gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>((const float*)A, lda, (const float*)W, (float*)C, ldc, M, N, K, ep);
+    TPAT_CUDA(launch_kernel(gemm_simt_kernel<float, float>, dim3(grid), dim3(256), 0, st, (const float*)A, lda, (const float*)W, (float*)C, ldc, M, N, K, ep));
   else if (a_dtype == TPAT_F32 && c_dtype == TPAT_BF16)
-    gemm_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)A, lda, (const float*)W, (__nv_bfloat16*)C, ldc, M, N, K, ep);
+    TPAT_CUDA(launch_kernel(gemm_simt_kernel<float, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const float*)A, lda, (const float*)W, (__nv_bfloat16*)C, ldc, M, N, K, ep));
   else if (a_dtype == TPAT_BF16 && c_dtype == TPAT_F32)
-    gemm_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, (float*)C, ldc, M, N, K, ep);
+    TPAT_CUDA(launch_kernel(gemm_simt_kernel<__nv_bfloat16, float>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, (float*)C, ldc, M, N, K, ep));
   else
-    gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, (__nv_bfloat16*)C, ldc, M, N, K, ep);
+    TPAT_CUDA(launch_kernel(gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, (__nv_bfloat16*)C, ldc, M, N, K, ep));
   TPAT_LAUNCH_CHECK();
   return 0;
 }

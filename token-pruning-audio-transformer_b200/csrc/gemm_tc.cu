@@ -146,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int nkb = p.K / TG_BK;
@@ -167,6 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched only on-chip state; global memory from here on
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -247,7 +249,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const TcGemmP
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(ta, tw, p);
+  TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(TG_THREADS), TG_SMEM_BYTES, st, ta, tw, p));
   TPAT_LAUNCH_CHECK();
   return 0;
 }

@@ -51,6 +51,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint64_t* res_bar = acc_empty + 4;            // [EPI_WARPS][2] residual-chunk arrival (kResTma)
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
@@ -76,6 +77,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   ptx::cluster_sync();          // barrier inits + TMEM allocation visible to both CTAs of the pair
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched only on-chip state; global memory from here on
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own A rows + own half of the W rows, credited to the leader's barrier =====
@@ -247,7 +249,7 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
   const int tiles = p.tiles_m * p.tiles_n;
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, T2_THREADS, smem_bytes, st>>>(ta, tw, tr, tc, p);
+  TPAT_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(T2_THREADS), smem_bytes, st, ta, tw, tr, tc, p));
   TPAT_LAUNCH_CHECK();
   return 0;
 }

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(32 * LN_WARPS)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  OutT* __restrict__ y, int rows, float eps) {
   constexpr int D = NV * 128;
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -78,6 +80,8 @@ gather_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__
                         const float* __restrict__ gamma, const float* __restrict__ beta, OutT* __restrict__ y_out,
                         int B, int N_in, int k, int num_extra, float eps) {
   constexpr int D = NV * 128;
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int N_out = num_extra + k;
   const int orow = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -131,6 +135,8 @@ pool_norm_kernel(const float* __restrict__ x, float* __restrict__ pooled, const 
                  const float* __restrict__ b1, float eps1, const float* __restrict__ g2,
                  const float* __restrict__ b2, float eps2, int N, int D, int variant) {
   extern __shared__ float sm[];  // [TG*D (pool partials) | 2*D | 8]
+  pdl_trigger();
+  pdl_wait();
   const float* xb = x + (size_t)blockIdx.x * N * D;
   const int nv = D / 4;                       // float4 columns
   const int TG = blockDim.x / nv;             // token groups (>= 1)
@@ -193,6 +199,8 @@ __global__ void __launch_bounds__(256)
 head_kernel(const float* __restrict__ pooled, const float* __restrict__ W, const float* __restrict__ bias,
             float* __restrict__ logits, int B, int C) {
   constexpr int D = NV * 128;
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
@@ -218,7 +226,7 @@ static int launch_layernorm(const float* x, const float* g, const float* b, OutT
                             cudaStream_t st) {
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
 #define TPAT_LN_CASE(nv) \
-  case nv: layernorm_kernel<nv, OutT><<<grid, 32 * LN_WARPS, 0, st>>>(x, g, b, y, rows, eps); break;
+  case nv: TPAT_CUDA(launch_kernel(layernorm_kernel<nv, OutT>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, g, b, y, rows, eps)); break;
   switch (D / 128) {
     TPAT_LN_CASE(1) TPAT_LN_CASE(2) TPAT_LN_CASE(3) TPAT_LN_CASE(4) TPAT_LN_CASE(5) TPAT_LN_CASE(6)
     TPAT_LN_CASE(8) TPAT_LN_CASE(10) TPAT_LN_CASE(12) TPAT_LN_CASE(16)
@@ -235,7 +243,7 @@ static int launch_gather_ln(const float* x, const int64_t* idx, float* xo, const
   const int rows = B * (extra + k);
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
 #define TPAT_GLN_CASE(nv) \
-  case nv: gather_layernorm_kernel<nv, OutT><<<grid, 32 * LN_WARPS, 0, st>>>(x, idx, xo, g, b, yo, B, N_in, k, extra, eps); break;
+  case nv: TPAT_CUDA(launch_kernel(gather_layernorm_kernel<nv, OutT>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, idx, xo, g, b, yo, B, N_in, k, extra, eps)); break;
   switch (D / 128) {
     TPAT_GLN_CASE(1) TPAT_GLN_CASE(2) TPAT_GLN_CASE(3) TPAT_GLN_CASE(4) TPAT_GLN_CASE(5) TPAT_GLN_CASE(6)
     TPAT_GLN_CASE(8) TPAT_GLN_CASE(10) TPAT_GLN_CASE(12) TPAT_GLN_CASE(16)
@@ -291,7 +299,7 @@ extern "C" int tpat_pool_norm(const float* x, float* pooled, const float* g1, co
   const int threads = 1024;
   const int TG = threads / (D / 4);
   const size_t smem = ((size_t)TG * D + 2 * D + 32) * sizeof(float);
-  pool_norm_kernel<<<B, threads, smem, as_stream(stream)>>>(x, pooled, g1, b1, eps1, g2, b2, eps2, N, D, variant);
+  TPAT_CUDA(launch_kernel(pool_norm_kernel, dim3(B), dim3(threads), smem, as_stream(stream), x, pooled, g1, b1, eps1, g2, b2, eps2, N, D, variant));
   TPAT_LAUNCH_CHECK();
   return 0;
 }
@@ -306,12 +314,12 @@ extern "C" int tpat_head(const float* pooled, const float* W, const float* bias,
   const int grid = (C + 7) / 8;
   cudaStream_t st = as_stream(stream);
   switch (D / 128) {
-    case 1: head_kernel<1><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
-    case 2: head_kernel<2><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
-    case 3: head_kernel<3><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
-    case 4: head_kernel<4><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
-    case 6: head_kernel<6><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
-    case 8: head_kernel<8><<<grid, 256, 0, st>>>(pooled, W, bias, logits, B, C); break;
+    case 1: TPAT_CUDA(launch_kernel(head_kernel<1>, dim3(grid), dim3(256), 0, st, pooled, W, bias, logits, B, C)); break;
+    case 2: TPAT_CUDA(launch_kernel(head_kernel<2>, dim3(grid), dim3(256), 0, st, pooled, W, bias, logits, B, C)); break;
+    case 3: TPAT_CUDA(launch_kernel(head_kernel<3>, dim3(grid), dim3(256), 0, st, pooled, W, bias, logits, B, C)); break;
+    case 4: TPAT_CUDA(launch_kernel(head_kernel<4>, dim3(grid), dim3(256), 0, st, pooled, W, bias, logits, B, C)); break;
+    case 6: TPAT_CUDA(launch_kernel(head_kernel<6>, dim3(grid), dim3(256), 0, st, pooled, W, bias, logits, B, C)); break;
+    case 8: TPAT_CUDA(launch_kernel(head_kernel<8>, dim3(grid), dim3(256), 0, st, pooled, W, bias, logits, B, C)); break;
     default: set_error("tpat_head: unsupported D=%d", D); return 1;
   }
   TPAT_LAUNCH_CHECK();

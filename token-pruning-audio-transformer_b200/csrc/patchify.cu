@@ -17,6 +17,8 @@ patchify_kernel(const float* __restrict__ spec, OutT* __restrict__ patches, floa
                 const float* __restrict__ extra_tok, const float* __restrict__ pos,
                 int T, int F, int D, int num_extra, int order) {
   extern __shared__ float tile[];  // [16][F+1]
+  pdl_trigger();
+  pdl_wait();
   const int tb = blockIdx.x, b = blockIdx.y;
   const int TB = T / 16, FB = F / 16, P = TB * FB;
   const int ld = F + 1;
@@ -67,9 +69,9 @@ extern "C" int tpat_patchify(const float* spec, void* patches, int out_dtype, fl
   dim3 grid(T / 16, B);
   const size_t smem = (size_t)16 * (F + 1) * sizeof(float);
   if (out_dtype == TPAT_F32)
-    patchify_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(spec, (float*)patches, tokens, extra_tok, pos, T, F, D, num_extra, order);
+    TPAT_CUDA(launch_kernel(patchify_kernel<float>, dim3(grid), dim3(256), smem, as_stream(stream), spec, (float*)patches, tokens, extra_tok, pos, T, F, D, num_extra, order));
   else
-    patchify_kernel<__nv_bfloat16><<<grid, 256, smem, as_stream(stream)>>>(spec, (__nv_bfloat16*)patches, tokens, extra_tok, pos, T, F, D, num_extra, order);
+    TPAT_CUDA(launch_kernel(patchify_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, as_stream(stream), spec, (__nv_bfloat16*)patches, tokens, extra_tok, pos, T, F, D, num_extra, order));
   TPAT_LAUNCH_CHECK();
   return 0;
 }

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(TK_THREADS)
 score_topk_kernel(const float* __restrict__ partial, int R, float divisor, float* __restrict__ score,
                   int64_t* __restrict__ topk_idx, int N, int num_extra, int k, int npad) {
   extern __shared__ unsigned long long keys[];  // [npad]
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const int n = N - num_extra;
   const float* pb = partial + (size_t)b * R * N;
@@ -72,7 +74,7 @@ extern "C" int tpat_score_topk(const float* partial, int R, float divisor, float
   while (npad < n) npad <<= 1;
   const size_t smem = (size_t)npad * sizeof(unsigned long long);
   if (smem > 48 * 1024) TPAT_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  score_topk_kernel<<<B, TK_THREADS, smem, as_stream(stream)>>>(partial, R, divisor, score, topk_idx, N, num_extra, k, npad);
+  TPAT_CUDA(launch_kernel(score_topk_kernel, dim3(B), dim3(TK_THREADS), smem, as_stream(stream), partial, R, divisor, score, topk_idx, N, num_extra, k, npad));
   TPAT_LAUNCH_CHECK();
   return 0;
 }
