@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment computed as an OFFSET from the __shared__ array so that the compiler keeps the shared
+  // address space (a round trip through uintptr_t turns every staging access into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* q_s = smem;                                   // 16 KB
   uint8_t* p_s = q_s + AT_Q_BYTES;                       // 2 x 16 KB
   uint8_t* kv_s = p_s + 2 * AT_P_BYTES;                  // AT_SLOTS x 8 KB

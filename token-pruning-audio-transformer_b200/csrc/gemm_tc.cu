@@ -135,7 +135,9 @@ template <int EPI, typename OutT>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const TcGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment computed as an OFFSET from the __shared__ array so that the compiler keeps the shared
+  // address space (a round trip through uintptr_t turns every staging access into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + TG_STAGES * TG_A_BYTES;
   uint8_t* staging = smem + TG_STAGES * TG_STAGE_BYTES;

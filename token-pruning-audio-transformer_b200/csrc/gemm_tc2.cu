@@ -39,7 +39,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   constexpr int NSTAGES = kResTma ? T2R_STAGES : T2_STAGES;
   constexpr int STAGING = kResTma ? T2R_STAGING_BYTES : T2_STAGING_BYTES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment computed as an OFFSET from the __shared__ array so that the compiler keeps the shared
+  // address space (a round trip through uintptr_t turns every staging access into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + NSTAGES * T2_A_BYTES;
   uint8_t* staging = smem + NSTAGES * T2_STAGE_BYTES;
