@@ -111,7 +111,7 @@ def test_attention_tc_online_softmax_rescale(N, extra):
     g = torch.Generator().manual_seed(22)
     B, H = 2, 12
     x = torch.randn(B, N, 3, H, 64, generator=g) * 1.5
-    ramp = 1.0 + 6.0 * torch.arange(N, dtype=torch.float32) / N
+    ramp = 1.0 + 24.0 * torch.arange(N, dtype=torch.float32) / N
     x[:, :, 1] *= ramp[None, :, None, None]                      # K rows get larger with the key index
     qkv = x.reshape(B * N, 3 * H * 64).to(dev()).to(torch.bfloat16)
     out, _ = ops.attention(qkv, B, N, H, extra, _lib.SCORE_NONE, _lib.IMPL_TC)

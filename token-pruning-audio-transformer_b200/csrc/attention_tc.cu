@@ -16,11 +16,12 @@
 //            pass 1: S -> running row max and sum of exp;  pass 2: S recomputed ->
 //            P = 2^(s*c - m*c - log2 l) (one FFMA + one MUFU.EX2 per element) -> score partials from
 //            the fp32 probabilities (warp transpose-reduce, fixed order, no atomics) -> bf16 P -> O += P V.
-//  TWO_PASS = false (every other tile) single pass with a lazily rescaled online softmax: the
-//            reference max m_ref is only raised when a tile's max exceeds it by more than 2^8 (P stays
-//            <= 256, exact in bf16/fp32 range); then O (TMEM) and the running sum are rescaled once by
-//            the softmax warp itself.  O is divided by the row sum at the end.  One exp and one QK^T
-//            per element, K streamed once.
+//  TWO_PASS = false (every other tile) single pass with a lazily rescaled online softmax: tile 0 fixes
+//            the reference max m_ref; later tiles exponentiate against the current m_ref at once (their own
+//            max is evaluated off the critical path) and only when a row's max exceeds m_ref by more than
+//            2^64 is m_ref raised, O (TMEM) and the running sum rescaled by the softmax warp itself and the
+//            tile redone.  P stays <= 2^64 (exact in bf16 / fp32 range).  O is divided by the row sum at the
+//            end.  One exp and one QK^T per element, K streamed once.
 // The N x N matrix never leaves the SM; O leaves through one TMA store.
 #include "attention.cuh"
 #include "ptx_sm100.cuh"
@@ -45,7 +46,7 @@ constexpr int AT_P_BYTES = AT_BM * AT_BK * 2;    // 16 KB
 constexpr int AT_THREADS = 192;
 constexpr int AT_TMEM_COLS = AT_SBUF == 1 ? 128 : 256;   // S buffers [0, 64*SBUF), then O (64 columns)
 constexpr int AT_SMEM_LIMIT = 113 * 1024;   // per-CTA cap (two CTAs / SM); single-pass tiles need 74 KB, so three fit
-constexpr float AT_RESCALE_LOG2 = 8.0f;   // online softmax: raise the reference max only past 2^8
+constexpr float AT_RESCALE_LOG2 = 64.0f;  // online softmax: the reference max is only raised past 2^64 (then the tile is redone)
 #ifndef AT_POLY_EVERY
 #define AT_POLY_EVERY 0                   // every AT_POLY_EVERY-th probability of a full single-pass tile uses exp2_poly (0 = none;
                                           // measured r01: 2/4/8 are all SLOWER than 0 -- the kernel is latency-, not MUFU-bound)
@@ -223,6 +224,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const float c = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     int sidx = 0;
+    // A warp whose 32 query rows all lie beyond N (tail tile of e.g. N = 513: one valid row in 128) only keeps the
+    // barrier protocol going: no TMEM reads, no exps, no P / O writes.  Its P rows stay whatever is in smem and its
+    // O rows are garbage, but rows are independent and rows >= N are never stored.
+    const bool warp_live = q0 + quarter * 32 < p.N;
 #ifdef TPAT_ATTN_TRACE
     const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == (gridDim.z >> 1) && threadIdx.x == 64;
     int trace_n = 0;
@@ -234,9 +239,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // load one 64-column S tile (only the 32-column halves that hold valid keys), release the TMEM
     // buffer as soon as the values are in registers, mask the columns >= N of a boundary tile to -inf
     auto load_s = [&](int sb, int valid, uint32_t (&r0)[32], uint32_t (&r1)[32]) {
-      ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK, r0);
-      if (valid > 32) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + 32, r1);
-      ptx::tmem_ld_wait();
+      if (warp_live) {
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK, r0);
+        if (valid > 32) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + 32, r1);
+        ptx::tmem_ld_wait();
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);
@@ -274,6 +281,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int valid = p.N - j * AT_BK;                 // > 0
         uint32_t r0[32], r1[32];
         load_s(sb, valid, r0, r1);
+        if (!warp_live) continue;
         const float mx = tile_max(valid, r0, r1, m_run);
         const float mc = mx * c;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -314,89 +322,108 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       uint32_t r0[32], r1[32];
       load_s(sb, valid, r0, r1);
       ATTN_TRACE(4);
-      if (!TWO_PASS) {
-        // lazily rescaled online softmax
-        const float mx = tile_max(valid, r0, r1, -INFINITY);
-        if (j == 0) {
-          m_run = mx;                                    // O is still uninitialised: nothing to rescale
-        } else {
-          const bool need = (mx - m_run) * c > AT_RESCALE_LOG2;
-          if (__any_sync(0xffffffffu, need)) {
-            const float f = need ? ptx::ex2_ftz((m_run - mx) * c) : 1.0f;
-            if (need) m_run = mx;
-            l2a *= f; l2b *= f; l2c *= f; l2d *= f;
-            // every PV issued so far (up to block j-1) must have retired before O is touched
-            ptx::mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
-            ptx::tc_fence_after();
-#pragma unroll 1
-            for (int oh = 0; oh < 2; ++oh) {
-              uint32_t o0[32];
-              ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + oh * 32, o0);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * f);
-              ptx::tmem_st_32x32b_x32(tmem_o + lane_off + oh * 32, o0);
-            }
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-          }
+      if (!warp_live) {
+        if (TWO_PASS && p.score_mode == TPAT_SCORE_COLMEAN) {   // this warp's rows contribute nothing to the column sums
+          colsum_w[j * AT_BK + lane] = 0.f;
+          colsum_w[j * AT_BK + 32 + lane] = 0.f;
         }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
+        continue;
+      }
+      if (!TWO_PASS) {
+        // Online softmax with a LAZY reference max: tile 0 fixes m_ref = its row max; later tiles compute their
+        // probabilities against the current m_ref straight away (their own max is evaluated off the critical
+        // path) and only if some row's max exceeds m_ref by more than 2^64 is the tile redone after raising m_ref
+        // and rescaling O (TMEM) and the running sum.  Probabilities stay <= 2^64: exact in bf16 / fp32 range.
+        if (j == 0) m_run = tile_max(valid, r0, r1, -INFINITY);
         off = m_run * c;
       }
       ATTN_TRACE(5);
       // P buffer pb was last read by PV(j-2), which the MMA thread issued BEFORE S(j); tcgen05 operations retire
       // in issue order and s_full(j) is a commit of everything issued before it, so the buffer is already free.
       uint8_t* p_row = p_s + pb * AT_P_BYTES + r_local * 128;
+      const float l2a_in = l2a, l2b_in = l2b, l2c_in = l2c, l2d_in = l2d;
+      auto emit_tile = [&]() {
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t (&r)[32] = hf == 0 ? r0 : r1;
-        const int col0 = j * AT_BK + hf * 32;
-        const int vh = valid - hf * 32;                  // valid columns in this half (may be <= 0)
-        if (vh <= 0) {
-          if (hf * 32 < ((valid + 15) & ~15)) {          // still inside the MMA's K range: zero it
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t (&r)[32] = hf == 0 ? r0 : r1;
+          const int col0 = j * AT_BK + hf * 32;
+          const int vh = valid - hf * 32;                  // valid columns in this half (may be <= 0)
+          if (vh <= 0) {
+            if (hf * 32 < ((valid + 15) & ~15)) {          // still inside the MMA's K range: zero it
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4*>(p_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
-          }
-          continue;
-        }
-        float v[32];
-        if (!TWO_PASS && AT_POLY_EVERY > 0 && vh >= 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = fmaf(__uint_as_float(r[i]), c, -off);
-            v[i] = (AT_POLY_EVERY > 0 && (i % (AT_POLY_EVERY > 0 ? AT_POLY_EVERY : 1)) == (AT_POLY_EVERY - 1)) ? exp2_poly(x) : ptx::ex2_ftz(x);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));   // -inf -> 0
-        }
-        if (!TWO_PASS) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
-        }
-        store_p_half(p_row, hf, r_local, v);
-        if (TWO_PASS) {
-          if (p.score_mode == TPAT_SCORE_COLMEAN) {
-            // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= row_w;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) {
-              const bool upper = (lane & o) != 0;
-#pragma unroll
-              for (int i = 0; i < o; ++i) {
-                const float send = upper ? v[i] : v[i + o];
-                const float keep = upper ? v[i + o] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-              }
+              for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4*>(p_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
             }
-            colsum_w[col0 + lane] = v[0];
-          } else if (cls_writer) {
-            float* dst = p.score_partial + ((size_t)b * p.H + h) * p.N;
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N) dst[col0 + i] = v[i];
+            continue;
           }
+          float v[32];
+          if (!TWO_PASS && AT_POLY_EVERY > 0 && vh >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = fmaf(__uint_as_float(r[i]), c, -off);
+              v[i] = (AT_POLY_EVERY > 0 && (i % (AT_POLY_EVERY > 0 ? AT_POLY_EVERY : 1)) == (AT_POLY_EVERY - 1)) ? exp2_poly(x) : ptx::ex2_ftz(x);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));   // -inf -> 0
+          }
+          if (!TWO_PASS) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
+          }
+          store_p_half(p_row, hf, r_local, v);
+          if (TWO_PASS) {
+            if (p.score_mode == TPAT_SCORE_COLMEAN) {
+              // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= row_w;
+#pragma unroll
+              for (int o = 16; o >= 1; o >>= 1) {
+                const bool upper = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < o; ++i) {
+                  const float send = upper ? v[i] : v[i + o];
+                  const float keep = upper ? v[i + o] : v[i];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+              }
+              colsum_w[col0 + lane] = v[0];
+            } else if (cls_writer) {
+              float* dst = p.score_partial + ((size_t)b * p.H + h) * p.N;
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) dst[col0 + i] = v[i];
+            }
+          }
+        }
+      };
+      emit_tile();
+      if (!TWO_PASS && j > 0) {
+        const float mx = tile_max(valid, r0, r1, -INFINITY);
+        const bool need = (mx - m_run) * c > AT_RESCALE_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: raise m_ref, rescale what was accumulated before this tile, redo the tile
+          const float f = need ? ptx::ex2_ftz((m_run - mx) * c) : 1.0f;
+          if (need) m_run = mx;
+          off = m_run * c;
+          l2a = l2a_in * f; l2b = l2b_in * f; l2c = l2c_in * f; l2d = l2d_in * f;
+          // every PV issued so far (up to block j-1) must have retired before O is touched
+          ptx::mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int oh = 0; oh < 2; ++oh) {
+            uint32_t o0[32];
+            ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + oh * 32, o0);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * f);
+            ptx::tmem_st_32x32b_x32(tmem_o + lane_off + oh * 32, o0);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          emit_tile();
         }
       }
       ATTN_TRACE(7);
@@ -411,7 +438,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     ptx::tc_fence_after();
     ATTN_TRACE(10);
     const float o_scale = TWO_PASS ? 1.0f : 1.0f / ((l2a + l2b) + (l2c + l2d));
-    {
+    if (warp_live) {
       uint32_t r0[32], r1[32];
       ptx::tmem_ld_32x32b_x32(tmem_o + lane_off, r0);
       ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + 32, r1);
