@@ -45,7 +45,7 @@ constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;   // 8 KB
 constexpr int AT_P_BYTES = AT_BM * AT_BK * 2;    // 16 KB
 constexpr int AT_THREADS = 192;
 constexpr int AT_TMEM_COLS = AT_SBUF == 1 ? 128 : 256;   // S buffers [0, 64*SBUF), then O (64 columns)
-constexpr int AT_SMEM_LIMIT = 113 * 1024;   // per-CTA cap (two CTAs / SM); single-pass tiles need 74 KB, so three fit
+constexpr int AT_SMEM_LIMIT = 227 * 1024;   // hard cap; <= 113 KB keeps two CTAs per SM (N <= 960 with the column-sum buffer)
 constexpr float AT_RESCALE_LOG2 = 64.0f;  // online softmax: the reference max is only raised past 2^64 (then the tile is redone)
 #ifndef AT_POLY_EVERY
 #define AT_POLY_EVERY 0                   // every AT_POLY_EVERY-th probability of a full single-pass tile uses exp2_poly (0 = none;

@@ -208,16 +208,25 @@ head_kernel(const float* __restrict__ pooled, const float* __restrict__ W, const
 #pragma unroll
   for (int i = 0; i < NV; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)c * D) + lane + 32 * i);
   const float bc = bias ? __ldg(bias + c) : 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float4* pr = reinterpret_cast<const float4*>(pooled + (size_t)b * D);
-    float s = 0.f;
+  // four clips per step: four independent load / FMA / shuffle chains in flight
+  for (int b0 = 0; b0 < B; b0 += 4) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 pv = __ldg(pr + lane + 32 * i);
-      s = fmaf(pv.x, w[i].x, s); s = fmaf(pv.y, w[i].y, s); s = fmaf(pv.z, w[i].z, s); s = fmaf(pv.w, w[i].w, s);
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + u < B ? b0 + u : B - 1;
+      const float4* pr = reinterpret_cast<const float4*>(pooled + (size_t)b * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 pv = __ldg(pr + lane + 32 * i);
+        s[u] = fmaf(pv.x, w[i].x, s[u]); s[u] = fmaf(pv.y, w[i].y, s[u]); s[u] = fmaf(pv.z, w[i].z, s[u]); s[u] = fmaf(pv.w, w[i].w, s[u]);
+      }
     }
-    s = warp_sum(s);
-    if (lane == 0) logits[(size_t)b * C + c] = s + bc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    }
+    if (lane < 4 && b0 + lane < B) logits[(size_t)(b0 + lane) * C + c] = (lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3]) + bc;
   }
 }
 
