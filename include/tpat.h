@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 1
+#define TPAT_VERSION 2
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -126,9 +126,11 @@ int tpat_attention(const void* qkv, void* out, int dtype, float* score_partial, 
  *   topk_idx [B, k] int64, descending score; ties: lower index first (torch leaves ties
  *            unspecified).  NaN ranks above every number, like torch.topk.
  *            k == 0 or topk_idx == NULL: only the score is written.
+ *   rest_idx [B, (N - extra) - k] int32 or NULL: the tokens that were NOT kept, in descending-score order
+ *            (input of tpat_fuse_token).
  */
 int tpat_score_topk(const float* partial, int R, float divisor, float* score, int64_t* topk_idx,
-                    int B, int N, int num_extra, int k, tpat_stream_t stream);
+                    int32_t* rest_idx, int B, int N, int num_extra, int k, tpat_stream_t stream);
 
 /*
  * Token gather / compaction fused with the LayerNorm that follows it.
@@ -136,10 +138,22 @@ int tpat_score_topk(const float* partial, int R, float divisor, float* score, in
  *   x      [B, N_in, D] fp32   residual stream after the attention residual add
  *   x_out  [B, extra + k, D] fp32: rows < extra copied, row extra+j = x[b, extra + idx[b, j]]
  *   y_out  [B, extra + k, D] (y_dtype) = LayerNorm(x_out) ; NULL to skip
+ *   out_rows  rows per clip of x_out / y_out (0 = extra + k); extra + k + 1 leaves room for the fused token
  */
 int tpat_gather_layernorm(const float* x, const int64_t* topk_idx, float* x_out, const float* gamma,
                           const float* beta, void* y_out, int y_dtype, int B, int N_in, int k,
-                          int num_extra, int D, float eps, tpat_stream_t stream);
+                          int num_extra, int out_rows, int D, float eps, tpat_stream_t stream);
+
+/*
+ * EViT "fused inattentive token": x_out[b, out_row] = sum_r score[b, rest_idx[b, r]] * x[b, extra + rest_idx[b, r]]
+ * (un-normalised weighted sum over the tokens that were not kept) and y_out[b, out_row] = LayerNorm of it.
+ * NOT in the reference forward (only util/token_reduction_utils.py:8-19 knows a fuse_token flag);
+ * semantics follow upstream EViT (Block.forward: extra_token = sum(non_topk * non_topk_attn)).  Parity unpinned.
+ *   score [B, N_in - extra] fp32 (tpat_score_topk output), rest_idx [B, n_rest] int32.
+ */
+int tpat_fuse_token(const float* x, const float* score, const int32_t* rest_idx, float* x_out,
+                    const float* gamma, const float* beta, void* y_out, int y_dtype, int B, int N_in,
+                    int n_rest, int out_rows, int out_row, int num_extra, int D, float eps, tpat_stream_t stream);
 
 /*
  * Pooled classifier input.  Replaces
@@ -176,7 +190,9 @@ typedef struct {
   int B, T, F;        /* clips, time frames, mel bins (F == 128 in the reference)              */
   int depth, D, H, Dh, num_classes;
   int prune[TPAT_MAX_DEPTH]; /* 1: block i runs top-k + gather (reference: keep_rate < 1.0)        */
-  int keep[TPAT_MAX_DEPTH];  /* non-extra tokens leaving block i (k of the top-k when prune[i])   */
+  int keep[TPAT_MAX_DEPTH];  /* k of the top-k when prune[i], else the (unchanged) non-extra token count;
+                                with fuse_token a pruning block hands keep[i] + 1 tokens to the next one   */
+  int fuse_token;            /* EViT fused inattentive token appended after the kept tokens (unpinned)    */
   int want_all_scores;       /* extract mode: emit the score of every block                    */
   float ln_eps;              /* 1e-6 for every block norm                                      */
   /* weights: matrices in the impl's operand dtype, vectors fp32 */

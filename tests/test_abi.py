@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_struct_layout():
     from tpat import _lib
-    assert _lib.lib.tpat_version() == 1
+    assert _lib.lib.tpat_version() == 2
     assert _lib.lib.tpat_sizeof_forward_args() == ctypes.sizeof(_lib.ForwardArgs)
 
 
@@ -40,7 +40,7 @@ def test_argument_validation_sets_error_message():
     assert rc != 0 and "dtype" in _lib.last_error()
     rc = lib.tpat_attention(1 << 12, 1 << 12, 1, None, 0, 2, 65, 12, 80, 1, 0.125, 1, None)
     assert rc != 0 and "head dim" in _lib.last_error()
-    rc = lib.tpat_score_topk(1 << 12, 12, 12.0, None, 1 << 12, 2, 66, 2, 65, None)
+    rc = lib.tpat_score_topk(1 << 12, 12, 12.0, None, 1 << 12, None, 2, 66, 2, 65, None)
     assert rc != 0 and "out of range" in _lib.last_error()
     args = _lib.ForwardArgs()
     assert lib.tpat_forward_workspace_bytes(ctypes.byref(args)) == 0

@@ -144,6 +144,29 @@ def test_gather_layernorm(out_dtype):
     assert none is None and torch.equal(xo2, ref_x)
 
 
+def test_fused_token_kernel():
+    """EViT fused inattentive token (parity unpinned: upstream EViT semantics, restated in the oracle)."""
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(17)
+    B, N, D, extra, R = 3, 514, 768, 2, 12
+    k = 359
+    x = torch.randn(B, N, D, generator=g).to(dev())
+    partial = torch.rand(B, R, N, generator=g).to(dev())
+    w = (1 + 0.1 * torch.randn(D, generator=g)).to(dev())
+    b = (0.05 * torch.randn(D, generator=g)).to(dev())
+    score, idx, rest = ops.score_topk(partial, float(R), extra, k, want_rest=True)
+    assert rest.dtype == torch.int32 and rest.shape == (B, N - extra - k)
+    for c in range(B):   # kept and rest partition the candidates
+        assert sorted(idx[c].tolist() + rest[c].tolist()) == list(range(N - extra))
+    xo, yo = ops.gather_layernorm(x, idx, extra, w, b, 1e-6, torch.float32, score=score, rest_idx=rest)
+    assert xo.shape == (B, extra + k + 1, D)
+    from oracle import vit_oracle as vo
+    ref = vo.gather_tokens(x.cpu(), idx.cpu(), extra, score.cpu(), fuse_token=True)
+    assert torch.equal(xo[:, :extra + k].cpu(), ref[:, :extra + k])
+    assert rel_err(xo[:, -1].cpu(), ref[:, -1].double()) < 2e-6
+    assert rel_err(yo.cpu(), F.layer_norm(ref.double(), (D,), w.cpu().double(), b.cpu().double(), 1e-6)) < 5e-6
+
+
 def test_pool_norm_both_variants():
     ops, _lib = _ops()
     g = torch.Generator().manual_seed(8)

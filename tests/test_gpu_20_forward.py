@@ -215,3 +215,47 @@ def test_other_vit_sizes_match_the_oracle(factory, dim, depth, heads):
             first = f"block-{drop_loc[0]}.topk_idx"
             for a, b in zip(m.last_topk_idx[drop_loc[0]].cpu().tolist(), ref_feats[first].tolist()):
                 assert set(a) == set(b)
+
+
+@pytest.mark.parametrize("variant,T,kr", [("ast", 1024, 0.5), ("ast", 128, 0.7), ("audiomae", 1024, 0.7), ("ast", 1024, 0.9)])
+def test_fused_inattentive_token_matches_the_oracle(variant, T, kr):
+    """BASELINE configs[2] names the EViT fused inattentive token; the reference forward does not implement it
+    (SURVEY.md F8), so this is checked against the oracle's restatement of upstream EViT -- parity UNPINNED."""
+    from oracle import weights
+    from tpat import models_vit, ASTModel
+    C, B = 35, 2
+    if variant == "ast":
+        sd = weights.make_ast_state_dict(C, T, seed=11, flavour="perturbed")
+        m32 = ASTModel(label_dim=C, input_tdim=T, imagenet_pretrain=False, audioset_pretrain=False, verbose=False,
+                       drop_loc=(3, 6, 9), base_keep_rate=kr, precision="fp32", fuse_token=True)
+        m32.load_state_dict(sd, strict=False)
+    else:
+        sd = weights.make_audiomae_state_dict(C, T, seed=11, flavour="perturbed")
+        m32 = models_vit.vit_base_patch16(num_classes=C, drop_path_rate=0.0, mean_pooling=True, mask_2d=True, target_length=T,
+                                          drop_loc=(3, 6, 9), base_keep_rate=kr, precision="fp32", fuse_token=True)
+        m32.patch_embed = models_vit.PatchEmbed((T, 128), 16, 1, 768)
+        m32.pos_embed = nn.Parameter(torch.zeros(1, m32.patch_embed.num_patches + 1, 768), requires_grad=False)
+        m32.load_state_dict(sd, strict=True)
+    m32 = m32.to(dev()).eval()
+    x = weights.make_spectrogram(variant, B, T, seed=12)
+    with torch.no_grad():
+        ref_logits, ref = vo.forward(variant, sd, x, None, (3, 6, 9), kr, flag_extract_features=True, fuse_token=True)
+        logits, feats = m32(x.to(dev()), flag_extract_features=True)
+    assert sorted(k for k in feats if k != "mel") == sorted(ref)
+    for k in ref:
+        assert feats[k].shape == ref[k].shape, k
+    for a, b in zip(feats["block-3.topk_idx"].tolist(), ref["block-3.topk_idx"].tolist()):
+        assert set(a) == set(b)
+    # block-4 scores include the fused token's.  Exactly tied block-3 scores may be ordered differently than torch.topk
+    # does (SURVEY.md F15), which permutes the kept tokens, so the kept part is compared as a multiset; the fused
+    # token is always last.
+    got4, ref4 = feats["block-4.attn_score"], ref["block-4.attn_score"]
+    assert rel_err(torch.sort(got4[:, :-1], dim=1).values, torch.sort(ref4[:, :-1], dim=1).values) < 2e-5
+    assert rel_err(got4[:, -1], ref4[:, -1]) < 2e-5
+    err = rel_err(logits.cpu(), ref_logits)
+    print(f"[fp32 fuse] {variant} T={T} kr={kr}: logits err {err:.2e}")
+    assert err < 2e-5
+    m32.precision = "bf16"
+    with torch.no_grad():
+        lb = m32(x.to(dev()))
+    assert rel_err(lb.cpu(), ref_logits) < 1e-1

@@ -91,3 +91,26 @@ def test_shard_bounds_cover_batch():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [e - s for s, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_pruning_schedule_with_fused_token():
+    """EViT fused token (not in the reference forward): a block that drops tokens hands k + 1 tokens on."""
+    from tpat.engine import pruning_schedule, tokens_entering
+    rates = vo.default_keep_rate_list(12, (3, 6, 9), 0.7)
+    prune, keep = pruning_schedule(512, 2, rates, fuse_token=True)
+    assert keep[3] == 359 and keep[6] == math.ceil(0.7 * 360) and keep[9] == math.ceil(0.7 * (keep[6] + 1))
+    ent = tokens_entering(512, prune, keep, True)
+    assert ent[:4] == [512] * 4 and ent[4] == 360 and ent[7] == keep[6] + 1 and ent[10] == keep[9] + 1
+    # keep_rate < 1 that drops nothing (k == n) appends no fused token
+    prune, keep = pruning_schedule(4, 1, [0.99] + [1.0] * 11, fuse_token=True)
+    assert prune[0] == 1 and keep[0] == 4 and tokens_entering(4, prune, keep, True)[1] == 4
+
+
+def test_oracle_fused_token_shapes():
+    sd = weights.make_ast_state_dict(35, 128, 0, "perturbed")
+    x = weights.make_spectrogram("ast", 2, 128, 3)
+    with torch.no_grad():
+        logits, feats = vo.forward("ast", sd, x, None, (3, 6, 9), 0.7, flag_extract_features=True, fuse_token=True)
+    assert logits.shape == (2, 35)
+    assert feats["block-3.topk_idx"].shape == (2, 45) and feats["block-4.attn_score"].shape == (2, 46)
+    assert feats["block-6.topk_idx"].shape == (2, math.ceil(0.7 * 46))

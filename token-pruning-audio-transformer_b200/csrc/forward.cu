@@ -20,6 +20,8 @@ struct Workspace {
   void* ao;           // attention output        [B*Nmax*D]
   void* hid;          // MLP hidden / patch matrix [B*Nmax*Dh]
   float* partial;     // score partials          [B*R*Nmax]
+  float* score_tmp;   // block score when the caller does not ask for it but the fused token needs it [B*Nmax]
+  int32_t* rest;      // not-kept token indices (fused token) [B*Nmax]
   float* pooled;      // [B*D]
   size_t bytes;
 };
@@ -39,7 +41,7 @@ static int validate(const tpat_forward_args* a) {
     TPAT_CHECK(a->keep[i] > 0 && a->keep[i] <= n, "tpat_forward: keep[%d]=%d must be in (0, %d]", i, a->keep[i], n);
     TPAT_CHECK(a->prune[i] || a->keep[i] == n, "tpat_forward: block %d drops tokens (%d -> %d) but prune[%d] is 0", i, n, a->keep[i], i);
     if (a->prune[i]) TPAT_CHECK(a->topk_idx[i] != nullptr, "tpat_forward: block %d prunes but topk_idx[%d] is NULL", i, i);
-    n = a->keep[i];
+    n = a->keep[i] + ((a->prune[i] && a->fuse_token && a->keep[i] < n) ? 1 : 0);
   }
   return 0;
 }
@@ -61,6 +63,8 @@ static Workspace carve(const tpat_forward_args* a, uint8_t* base) {
   size_t hid = B * Nmax * (size_t)a->Dh * act, pat = B * P * 256 * act;
   w.hid = take(hid > pat ? hid : pat);
   w.partial = (float*)take(B * R * Nmax * 4);
+  w.score_tmp = (float*)take(B * Nmax * 4);
+  w.rest = (int32_t*)take(B * Nmax * 4);
   w.pooled = (float*)take(B * D * 4);
   w.bytes = off;
   return w;
@@ -86,7 +90,8 @@ extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
     if (score && a->variant == TPAT_VARIANT_AST && a->impl == TPAT_IMPL_TC && tpat_attention_qtiles(extra + cur, a->impl) > 1) n += 1;
     if (score) n += 1;                        // score / top-k
     n += 3;                                   // (gather+)LN2, fc1, fc2
-    cur = a->keep[i];
+    if (prune && a->fuse_token && a->keep[i] < cur) { n += 1; cur = a->keep[i] + 1; }   // fused token
+    else cur = a->keep[i];
   }
   return n + 2;  // pool/norm + head
 }
@@ -131,18 +136,27 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
     if (want_score) {
       const int R = ast ? H : H * tpat_attention_qtiles(N, impl);
       const float divisor = ast ? (float)H : (float)H * (float)(N - extra);
-      if (int rc = tpat_score_topk(w.partial, R, divisor, a->scores[i], prune ? a->topk_idx[i] : nullptr, B, N, extra,
-                                   prune ? a->keep[i] : 0, stream)) return rc;
+      const bool fuse_here = prune && a->fuse_token && a->keep[i] < cur;   // something is dropped -> fused token
+      float* score_out = a->scores[i] ? a->scores[i] : (fuse_here ? w.score_tmp : nullptr);
+      if (int rc = tpat_score_topk(w.partial, R, divisor, score_out, prune ? a->topk_idx[i] : nullptr,
+                                   fuse_here ? w.rest : nullptr, B, N, extra, prune ? a->keep[i] : 0, stream)) return rc;
     }
     int M2 = M;
     if (prune) {
       float* xn = w.x[xi ^ 1];
-      if (int rc = tpat_gather_layernorm(x, a->topk_idx[i], xn, bw.ln2_g, bw.ln2_b, w.y, act, B, N, a->keep[i], extra, D,
-                                         a->ln_eps, stream)) return rc;
+      const bool fuse_here = a->fuse_token && a->keep[i] < cur;
+      const int out_rows = extra + a->keep[i] + (fuse_here ? 1 : 0);
+      if (int rc = tpat_gather_layernorm(x, a->topk_idx[i], xn, bw.ln2_g, bw.ln2_b, w.y, act, B, N, a->keep[i], extra, out_rows,
+                                         D, a->ln_eps, stream)) return rc;
+      if (fuse_here) {
+        const float* sc = a->scores[i] ? a->scores[i] : w.score_tmp;
+        if (int rc = tpat_fuse_token(x, sc, w.rest, xn, bw.ln2_g, bw.ln2_b, w.y, act, B, N, cur - a->keep[i], out_rows,
+                                     out_rows - 1, extra, D, a->ln_eps, stream)) return rc;
+      }
       xi ^= 1;
       x = xn;
-      cur = a->keep[i];
-      M2 = B * (extra + cur);
+      cur = out_rows - extra;
+      M2 = B * out_rows;
     } else {
       if (int rc = tpat_layernorm(x, bw.ln2_g, bw.ln2_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
     }

@@ -78,26 +78,27 @@ template <int NV, typename OutT>
 __global__ void __launch_bounds__(32 * LN_WARPS)
 gather_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, float* __restrict__ x_out,
                         const float* __restrict__ gamma, const float* __restrict__ beta, OutT* __restrict__ y_out,
-                        int B, int N_in, int k, int num_extra, float eps) {
+                        int B, int N_in, int k, int num_extra, int out_rows, float eps) {
   constexpr int D = NV * 128;
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int N_out = num_extra + k;
-  const int orow = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (orow >= B * N_out) return;
-  const int b = orow / N_out, j = orow - b * N_out;
+  const int N_out = num_extra + k;                 // rows this kernel writes per clip; the clip stride is out_rows
+  const int grow = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (grow >= B * N_out) return;
+  const int b = grow / N_out, j = grow - b * N_out;
+  const size_t orow = (size_t)b * out_rows + j;
   int src = j;
   if (j >= num_extra) src = num_extra + (int)__ldg(idx + (size_t)b * k + (j - num_extra));
   float4 v[NV];
   ln_row_load<NV>(x + ((size_t)b * N_in + src) * D, lane, v);
-  float4* xo = reinterpret_cast<float4*>(x_out + (size_t)orow * D);
+  float4* xo = reinterpret_cast<float4*>(x_out + orow * D);
 #pragma unroll
   for (int i = 0; i < NV; ++i) xo[lane + 32 * i] = v[i];
   if (y_out != nullptr) {
     float mean, rstd;
     ln_row_stats<NV>(v, 1.0f / D, eps, mean, rstd);
-    ln_row_store<NV, OutT>(v, mean, rstd, gamma, beta, y_out + (size_t)orow * D, lane);
+    ln_row_store<NV, OutT>(v, mean, rstd, gamma, beta, y_out + orow * D, lane);
   }
 }
 
@@ -230,6 +231,83 @@ head_kernel(const float* __restrict__ pooled, const float* __restrict__ W, const
   }
 }
 
+
+// ---- EViT fused inattentive token: one CTA per clip ----
+// fused[b, :] = sum_r score[b, rest[b, r]] * x[b, extra + rest[b, r], :]   (un-normalised weighted sum, as in EViT's
+// Block.forward: extra_token = sum(non_topk * non_topk_attn)), written as output row `out_row` of the clip together
+// with its LayerNorm.  The reference repository does NOT implement this (parity unpinned); the
+// semantics follow upstream EViT and oracle/vit_oracle.py restates them.  Fixed summation order: thread (tg, c4)
+// takes rest rows tg, tg + TG, ...; the TG partials are added in order.
+template <typename OutT>
+__global__ void __launch_bounds__(1024)
+fuse_token_kernel(const float* __restrict__ x, const float* __restrict__ score, const int32_t* __restrict__ rest_idx,
+                  float* __restrict__ x_out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  OutT* __restrict__ y_out, int N_in, int n_rest, int out_rows, int out_row, int num_extra, int D, float eps) {
+  extern __shared__ float sm[];  // [TG*D | D | 32]
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int nv = D / 4, TG = blockDim.x / nv;
+  float* part = sm;
+  float* v0 = sm + (size_t)TG * D;
+  float* red = v0 + D;
+  const float* xb = x + (size_t)b * N_in * D;
+  const float* sb = score + (size_t)b * (N_in - num_extra);
+  const int32_t* rb = rest_idx + (size_t)b * n_rest;
+  const int tg = threadIdx.x / nv, c4 = threadIdx.x - tg * nv;
+  if (tg < TG) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = tg; r < n_rest; r += TG) {
+      const int t = __ldg(rb + r);
+      const float w = __ldg(sb + t);
+      const float4 u = __ldg(reinterpret_cast<const float4*>(xb + (size_t)(num_extra + t) * D) + c4);
+      a.x = fmaf(w, u.x, a.x); a.y = fmaf(w, u.y, a.y); a.z = fmaf(w, u.z, a.z); a.w = fmaf(w, u.w, a.w);
+    }
+    reinterpret_cast<float4*>(part + (size_t)tg * D)[c4] = a;
+  }
+  __syncthreads();
+  float* xo = x_out + ((size_t)b * out_rows + out_row) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < TG; ++g) s += part[(size_t)g * D + c];
+    v0[c] = s;
+    xo[c] = s;
+  }
+  __syncthreads();
+  if (y_out != nullptr) {
+    block_layernorm_inplace(v0, D, gamma, beta, eps, red);
+    OutT* yo = y_out + ((size_t)b * out_rows + out_row) * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) yo[c] = from_f32<OutT>(v0[c]);
+  }
+}
+
+}  // namespace tpat
+
+extern "C" int tpat_fuse_token(const float* x, const float* score, const int32_t* rest_idx, float* x_out,
+                               const float* gamma, const float* beta, void* y_out, int y_dtype, int B, int N_in,
+                               int n_rest, int out_rows, int out_row, int num_extra, int D, float eps,
+                               tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(x && score && rest_idx && x_out, "tpat_fuse_token: null pointer");
+  TPAT_CHECK(y_out == nullptr || (gamma && beta), "tpat_fuse_token: y_out needs gamma and beta");
+  TPAT_CHECK(B >= 0 && n_rest >= 0 && n_rest <= N_in - num_extra && out_row >= 0 && out_row < out_rows,
+             "tpat_fuse_token: bad sizes N_in=%d n_rest=%d out_row=%d out_rows=%d", N_in, n_rest, out_row, out_rows);
+  TPAT_CHECK(D > 0 && D % 4 == 0 && D <= 2048, "tpat_fuse_token: unsupported D=%d", D);
+  TPAT_CHECK(y_dtype == TPAT_F32 || y_dtype == TPAT_BF16, "tpat_fuse_token: bad dtype %d", y_dtype);
+  if (B == 0) return 0;
+  const int threads = 1024, TG = threads / (D / 4);
+  const size_t smem = ((size_t)TG * D + D + 32) * sizeof(float);
+  if (y_dtype == TPAT_F32)
+    TPAT_CUDA(launch_kernel(fuse_token_kernel<float>, dim3(B), dim3(threads), smem, as_stream(stream), x, score, rest_idx, x_out, gamma, beta,
+                            (float*)y_out, N_in, n_rest, out_rows, out_row, num_extra, D, eps));
+  else
+    TPAT_CUDA(launch_kernel(fuse_token_kernel<__nv_bfloat16>, dim3(B), dim3(threads), smem, as_stream(stream), x, score, rest_idx, x_out, gamma, beta,
+                            (__nv_bfloat16*)y_out, N_in, n_rest, out_rows, out_row, num_extra, D, eps));
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace tpat {
 template <typename OutT>
 static int launch_layernorm(const float* x, const float* g, const float* b, OutT* y, int rows, int D, float eps,
                             cudaStream_t st) {
@@ -248,11 +326,11 @@ static int launch_layernorm(const float* x, const float* g, const float* b, OutT
 
 template <typename OutT>
 static int launch_gather_ln(const float* x, const int64_t* idx, float* xo, const float* g, const float* b, OutT* yo,
-                            int B, int N_in, int k, int extra, int D, float eps, cudaStream_t st) {
+                            int B, int N_in, int k, int extra, int out_rows, int D, float eps, cudaStream_t st) {
   const int rows = B * (extra + k);
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
 #define TPAT_GLN_CASE(nv) \
-  case nv: TPAT_CUDA(launch_kernel(gather_layernorm_kernel<nv, OutT>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, idx, xo, g, b, yo, B, N_in, k, extra, eps)); break;
+  case nv: TPAT_CUDA(launch_kernel(gather_layernorm_kernel<nv, OutT>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, idx, xo, g, b, yo, B, N_in, k, extra, out_rows, eps)); break;
   switch (D / 128) {
     TPAT_GLN_CASE(1) TPAT_GLN_CASE(2) TPAT_GLN_CASE(3) TPAT_GLN_CASE(4) TPAT_GLN_CASE(5) TPAT_GLN_CASE(6)
     TPAT_GLN_CASE(8) TPAT_GLN_CASE(10) TPAT_GLN_CASE(12) TPAT_GLN_CASE(16)
@@ -280,7 +358,7 @@ extern "C" int tpat_layernorm(const float* x, const float* gamma, const float* b
 
 extern "C" int tpat_gather_layernorm(const float* x, const int64_t* topk_idx, float* x_out, const float* gamma,
                                      const float* beta, void* y_out, int y_dtype, int B, int N_in, int k,
-                                     int num_extra, int D, float eps, tpat_stream_t stream) {
+                                     int num_extra, int out_rows, int D, float eps, tpat_stream_t stream) {
   using namespace tpat;
   TPAT_CHECK(x && topk_idx && x_out, "tpat_gather_layernorm: null pointer");
   TPAT_CHECK(y_out == nullptr || (gamma && beta), "tpat_gather_layernorm: y_out needs gamma and beta");
@@ -288,9 +366,11 @@ extern "C" int tpat_gather_layernorm(const float* x, const int64_t* topk_idx, fl
   TPAT_CHECK(D > 0 && D % 128 == 0 && D <= 2048, "tpat_gather_layernorm: unsupported D=%d", D);
   TPAT_CHECK(x != x_out, "tpat_gather_layernorm: in-place compaction is not supported");
   TPAT_CHECK(aligned16(x) && aligned16(x_out) && (y_out == nullptr || aligned16(y_out)), "tpat_gather_layernorm: pointers must be 16-byte aligned");
+  if (out_rows == 0) out_rows = num_extra + k;
+  TPAT_CHECK(out_rows >= num_extra + k, "tpat_gather_layernorm: out_rows=%d smaller than extra + k = %d", out_rows, num_extra + k);
   if (B == 0) return 0;
-  if (y_dtype == TPAT_F32) return launch_gather_ln<float>(x, topk_idx, x_out, gamma, beta, (float*)y_out, B, N_in, k, num_extra, D, eps, as_stream(stream));
-  if (y_dtype == TPAT_BF16) return launch_gather_ln<__nv_bfloat16>(x, topk_idx, x_out, gamma, beta, (__nv_bfloat16*)y_out, B, N_in, k, num_extra, D, eps, as_stream(stream));
+  if (y_dtype == TPAT_F32) return launch_gather_ln<float>(x, topk_idx, x_out, gamma, beta, (float*)y_out, B, N_in, k, num_extra, out_rows, D, eps, as_stream(stream));
+  if (y_dtype == TPAT_BF16) return launch_gather_ln<__nv_bfloat16>(x, topk_idx, x_out, gamma, beta, (__nv_bfloat16*)y_out, B, N_in, k, num_extra, out_rows, D, eps, as_stream(stream));
   set_error("tpat_gather_layernorm: bad dtype %d", y_dtype);
   return 1;
 }

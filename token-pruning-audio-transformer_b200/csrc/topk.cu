@@ -21,7 +21,7 @@ __device__ __forceinline__ uint32_t order_bits(float s) {
 
 __global__ void __launch_bounds__(TK_THREADS)
 score_topk_kernel(const float* __restrict__ partial, int R, float divisor, float* __restrict__ score,
-                  int64_t* __restrict__ topk_idx, int N, int num_extra, int k, int npad) {
+                  int64_t* __restrict__ topk_idx, int32_t* __restrict__ rest_idx, int N, int num_extra, int k, int npad) {
   extern __shared__ unsigned long long keys[];  // [npad]
   pdl_trigger();
   pdl_wait();
@@ -56,12 +56,15 @@ score_topk_kernel(const float* __restrict__ partial, int R, float divisor, float
   }
   for (int i = threadIdx.x; i < k; i += TK_THREADS)
     topk_idx[(size_t)b * k + i] = (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
+  if (rest_idx != nullptr)   // the tokens that were NOT kept, still in descending-score order (EViT fused-token input)
+    for (int i = k + threadIdx.x; i < n; i += TK_THREADS)
+      rest_idx[(size_t)b * (n - k) + (i - k)] = (int32_t)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull));
 }
 
 }  // namespace tpat
 
 extern "C" int tpat_score_topk(const float* partial, int R, float divisor, float* score, int64_t* topk_idx,
-                               int B, int N, int num_extra, int k, tpat_stream_t stream) {
+                               int32_t* rest_idx, int B, int N, int num_extra, int k, tpat_stream_t stream) {
   using namespace tpat;
   TPAT_CHECK(partial != nullptr, "tpat_score_topk: null partial");
   const int n = N - num_extra;
@@ -69,12 +72,13 @@ extern "C" int tpat_score_topk(const float* partial, int R, float divisor, float
   TPAT_CHECK(k >= 0 && k <= n, "tpat_score_topk: k=%d out of range for %d candidate tokens", k, n);
   TPAT_CHECK(n <= 8192, "tpat_score_topk: at most 8192 candidate tokens per clip (got %d)", n);
   TPAT_CHECK(divisor != 0.f, "tpat_score_topk: zero divisor");
+  TPAT_CHECK(rest_idx == nullptr || (topk_idx != nullptr && k > 0), "tpat_score_topk: rest_idx needs topk_idx and k > 0");
   if (B == 0) return 0;
   int npad = 2;
   while (npad < n) npad <<= 1;
   const size_t smem = (size_t)npad * sizeof(unsigned long long);
   if (smem > 48 * 1024) TPAT_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TPAT_CUDA(launch_kernel(score_topk_kernel, dim3(B), dim3(TK_THREADS), smem, as_stream(stream), partial, R, divisor, score, topk_idx, N, num_extra, k, npad));
+  TPAT_CUDA(launch_kernel(score_topk_kernel, dim3(B), dim3(TK_THREADS), smem, as_stream(stream), partial, R, divisor, score, topk_idx, rest_idx, N, num_extra, k, npad));
   TPAT_LAUNCH_CHECK();
   return 0;
 }

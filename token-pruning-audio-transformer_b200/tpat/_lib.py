@@ -30,7 +30,7 @@ class ForwardArgs(Structure):
     _fields_ = [
         ("variant", c_int), ("impl", c_int), ("B", c_int), ("T", c_int), ("F", c_int),
         ("depth", c_int), ("D", c_int), ("H", c_int), ("Dh", c_int), ("num_classes", c_int),
-        ("prune", c_int * TPAT_MAX_DEPTH), ("keep", c_int * TPAT_MAX_DEPTH),
+        ("prune", c_int * TPAT_MAX_DEPTH), ("keep", c_int * TPAT_MAX_DEPTH), ("fuse_token", c_int),
         ("want_all_scores", c_int), ("ln_eps", c_float),
         ("patch_w", c_void_p), ("patch_b", c_void_p), ("extra_tok", c_void_p), ("pos", c_void_p),
         ("blocks", BlockWeights * TPAT_MAX_DEPTH),
@@ -56,9 +56,11 @@ SIGNATURES = {
     "tpat_attention_qtiles": (c_int, [c_int, c_int]),
     "tpat_attention": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                c_int, c_void_p]),
-    "tpat_score_topk": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_score_topk": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tpat_gather_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                      c_int, c_int, c_int, c_float, c_void_p]),
+                                      c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "tpat_fuse_token": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "tpat_pool_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int,
                                c_int, c_int, c_int, c_void_p]),
     "tpat_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

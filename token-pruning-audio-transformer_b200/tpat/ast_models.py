@@ -77,7 +77,7 @@ class ASTModel(nn.Module):
     def __init__(self, label_dim=527, fstride=16, tstride=16, input_fdim=128, input_tdim=1024, imagenet_pretrain=True,
                  audioset_pretrain=False, model_size='base384', verbose=True, depth=12,
                  audioset_pretrained_model_path: str = None, drop_path_rate=0.0, drop_loc: tuple = None,
-                 base_keep_rate: tuple = None, precision: Optional[str] = None):
+                 base_keep_rate: tuple = None, precision: Optional[str] = None, fuse_token: bool = False):
         super().__init__()
         assert fstride == 16 and tstride == 16, 'Currently only support fstride=16 and tstride=16.'
         if verbose:
@@ -117,7 +117,7 @@ class ASTModel(nn.Module):
             sd = {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in sd.items()}  # DataParallel prefix
             base = ASTModel(label_dim=527, fstride=16, tstride=16, input_fdim=128, input_tdim=1024,
                             imagenet_pretrain=False, audioset_pretrain=False, model_size=model_size, verbose=False,
-                            drop_loc=drop_loc, base_keep_rate=base_keep_rate, precision=precision)
+                            drop_loc=drop_loc, base_keep_rate=base_keep_rate, precision=precision, fuse_token=fuse_token)
             base.load_state_dict(sd, strict=True)
             self.v = base.v
             self.original_embedding_dim = self.v.pos_embed.shape[2]
@@ -157,6 +157,9 @@ class ASTModel(nn.Module):
             self.v.blocks[blk_id].num_extra_tokens = 2
 
         self.label_dim = label_dim
+        # EViT fused inattentive token (NOT in the reference forward; parity unpinned): a block that drops
+        # tokens appends sum(score * dropped tokens) as one extra token after the kept ones.
+        self.fuse_token = bool(fuse_token)
         self.precision = resolve_precision(precision)
         self.use_cuda_graph = False
         self._engine = ForwardEngine(_lib.VARIANT_AST, depth, 768, 12, 3072)
@@ -197,7 +200,7 @@ class ASTModel(nn.Module):
         rates = resolve_keep_rates(keep_rate_list, self.v.blocks)
         self._engine.pack(self._engine_tensors, self._pack_key())
         logits, scores, idxs = self._engine.run(x, rates, self.label_dim, want_all_scores=flag_extract_features,
-                                                precision=self.precision, use_graph=self.use_cuda_graph)
+                                                precision=self.precision, use_graph=self.use_cuda_graph, fuse_token=self.fuse_token)
         self.last_scores, self.last_topk_idx = scores, idxs
         if flag_extract_features:
             feature_dict = {'mel': x.unsqueeze(1).transpose(2, 3).cpu()}      # ast_models.py:434-439

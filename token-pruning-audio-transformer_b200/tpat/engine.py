@@ -25,10 +25,12 @@ def resolve_precision(p: Optional[str]) -> str:
     return p
 
 
-def pruning_schedule(n_patches: int, num_extra: int, keep_rates: Sequence[float]) -> Tuple[List[int], List[int]]:
-    """(prune flags, non-extra tokens leaving each block), following the reference exactly:
+def pruning_schedule(n_patches: int, num_extra: int, keep_rates: Sequence[float], fuse_token: bool = False
+                     ) -> Tuple[List[int], List[int]]:
+    """(prune flags, k of each block's top-k / unchanged token count), following the reference exactly:
     ``num_left_tokens = math.ceil(keep_rate * (N - num_extra_tokens))`` in Python double arithmetic
-    and top-k only ``if keep_rate < 1.0`` (models_vit.py:104-110; ast_models.py:116-121)."""
+    and top-k only ``if keep_rate < 1.0`` (models_vit.py:104-110; ast_models.py:116-121).  With ``fuse_token``
+    (EViT, not in the reference forward) a block that drops tokens hands k + 1 tokens to the next one."""
     prune, keep, cur = [], [], n_patches
     for kr in keep_rates:
         N = cur + num_extra
@@ -36,11 +38,21 @@ def pruning_schedule(n_patches: int, num_extra: int, keep_rates: Sequence[float]
         assert k > 0, "num_left_tokens should be at least 1"      # models_vit.py:106
         if kr < 1.0:
             prune.append(1)
-            cur = k
+            keep.append(k)
+            cur = k + (1 if (fuse_token and k < cur) else 0)
         else:
             prune.append(0)
-        keep.append(cur)
+            keep.append(cur)
     return prune, keep
+
+
+def tokens_entering(n_patches: int, prune: Sequence[int], keep: Sequence[int], fuse_token: bool) -> List[int]:
+    """Non-extra token count entering each block (= length of that block's score vector)."""
+    out, cur = [], n_patches
+    for p, k in zip(prune, keep):
+        out.append(cur)
+        cur = k + (1 if (p and fuse_token and k < cur) else 0) if p else cur
+    return out
 
 
 class ForwardEngine:
@@ -98,9 +110,11 @@ class ForwardEngine:
         return c
 
     # ---- one forward ---------------------------------------------------------------------
-    def _fill_args(self, spec, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, workspace):
+    def _fill_args(self, spec, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, workspace,
+                   fuse_token=False):
         pk = self._packed
         a = ForwardArgs()
+        a.fuse_token = 1 if fuse_token else 0
         a.variant, a.impl = self.variant, impl
         a.B, a.T, a.F = spec.shape
         a.depth, a.D, a.H, a.Dh, a.num_classes = self.depth, self.D, self.H, self.Dh, num_classes
@@ -130,19 +144,18 @@ class ForwardEngine:
             a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
         return a
 
-    def _alloc_outputs(self, spec, prune, keep, want_all_scores, num_classes):
+    def _alloc_outputs(self, spec, prune, keep, want_all_scores, num_classes, fuse_token=False):
         B, T, F = spec.shape
         dev = spec.device
         logits = torch.empty(B, num_classes, device=dev, dtype=torch.float32)
         scores: List[Optional[torch.Tensor]] = [None] * self.depth
         idxs: List[Optional[torch.Tensor]] = [None] * self.depth
-        cur = (T // 16) * (F // 16)
+        entering = tokens_entering((T // 16) * (F // 16), prune, keep, fuse_token)
         for i in range(self.depth):
             if prune[i] or want_all_scores:
-                scores[i] = torch.empty(B, cur, device=dev, dtype=torch.float32)
+                scores[i] = torch.empty(B, entering[i], device=dev, dtype=torch.float32)
             if prune[i]:
                 idxs[i] = torch.empty(B, keep[i], device=dev, dtype=torch.int64)
-            cur = keep[i]
         return logits, scores, idxs
 
     def _ensure_workspace(self, args: ForwardArgs, device) -> torch.Tensor:
@@ -155,7 +168,7 @@ class ForwardEngine:
         return self._workspace
 
     def run(self, spec: torch.Tensor, keep_rates: Sequence[float], num_classes: int, want_all_scores: bool = False,
-            precision: str = "bf16", use_graph: bool = False):
+            precision: str = "bf16", use_graph: bool = False, fuse_token: bool = False):
         """spec [B,T,F] fp32 CUDA.  Returns (logits [B,C], scores list, topk_idx list) -- device tensors."""
         if not spec.is_cuda:
             raise RuntimeError("tpat: input must be a CUDA tensor; there is no CPU path")
@@ -165,25 +178,27 @@ class ForwardEngine:
             spec = spec.float().contiguous()
         impl = _lib.IMPL_TC if precision == "bf16" else _lib.IMPL_SIMT
         B, T, F = spec.shape
-        prune, keep = pruning_schedule((T // 16) * (F // 16), self.num_extra, keep_rates)
+        prune, keep = pruning_schedule((T // 16) * (F // 16), self.num_extra, keep_rates, fuse_token)
         if use_graph:
-            return self._run_graph(spec, prune, keep, want_all_scores, impl, num_classes)
-        logits, scores, idxs = self._alloc_outputs(spec, prune, keep, want_all_scores, num_classes)
-        args = self._fill_args(spec, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, None)
+            return self._run_graph(spec, prune, keep, want_all_scores, impl, num_classes, fuse_token)
+        logits, scores, idxs = self._alloc_outputs(spec, prune, keep, want_all_scores, num_classes, fuse_token)
+        args = self._fill_args(spec, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, None, fuse_token)
         ws = self._ensure_workspace(args, spec.device)
         args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
         self.last_launch_count = lib.tpat_forward_launch_count(ctypes.byref(args))
         check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
         return logits, scores, idxs
 
-    def _run_graph(self, spec, prune, keep, want_all_scores, impl, num_classes):
-        key = (tuple(spec.shape), tuple(prune), tuple(keep), bool(want_all_scores), impl, num_classes, spec.device.index)
+    def _run_graph(self, spec, prune, keep, want_all_scores, impl, num_classes, fuse_token=False):
+        key = (tuple(spec.shape), tuple(prune), tuple(keep), bool(want_all_scores), impl, num_classes, spec.device.index,
+               bool(fuse_token))
         ent = self._graphs.get(key)
         if ent is None:
             static_in = torch.empty_like(spec)
             static_in.copy_(spec)
-            logits, scores, idxs = self._alloc_outputs(spec, prune, keep, want_all_scores, num_classes)
-            args = self._fill_args(static_in, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, None)
+            logits, scores, idxs = self._alloc_outputs(spec, prune, keep, want_all_scores, num_classes, fuse_token)
+            args = self._fill_args(static_in, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, None,
+                                   fuse_token)
             ws = self._ensure_workspace(args, spec.device)
             args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
             self.last_launch_count = lib.tpat_forward_launch_count(ctypes.byref(args))

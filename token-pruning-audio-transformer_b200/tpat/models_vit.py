@@ -21,6 +21,8 @@ Differences from the reference, stated (not hidden):
     as in the reference's eval mode.  Token masking (mask_t_prob / mask_f_prob > 0), custom_rank
     and drop_token_blk_idx raise NotImplementedError.
   * torch.topk leaves the order of exactly tied scores unspecified; here ties go to the lower index.
+  * extra constructor keyword ``fuse_token`` (default False): EViT's fused inattentive token, which BASELINE.json
+    configs[2] names but the reference forward never implemented -- semantics from upstream EViT.
   * extra constructor keyword ``precision``: "bf16" (tcgen05 tensor-core kernels, default) or
     "fp32" (CUDA-core fp32 kernels, the index-exact parity mode).
 """
@@ -135,7 +137,7 @@ class VisionTransformer(nn.Module):
                  num_heads=12, mlp_ratio=4.0, qkv_bias=False, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0,
                  drop_path_rate=0.0, hybrid_backbone=None, norm_layer=nn.LayerNorm, mean_pooling=False, mask_2d=True,
                  target_length=None, drop_loc: tuple = None, base_keep_rate: tuple = None,
-                 precision: Optional[str] = None, **kwargs):
+                 precision: Optional[str] = None, fuse_token: bool = False, **kwargs):
         super().__init__()
         assert hybrid_backbone is None, "hybrid backbones are not part of the pruning path"
         self.num_classes = num_classes
@@ -173,6 +175,9 @@ class VisionTransformer(nn.Module):
         self.retain_min = None
         self.drop_token_blk_idx = None
 
+        # EViT fused inattentive token (NOT in the reference forward; parity unpinned): a block that drops
+        # tokens appends sum(score * dropped tokens) as one extra token after the kept ones.
+        self.fuse_token = bool(fuse_token)
         self.precision = resolve_precision(precision)
         self.use_cuda_graph = False
         self._mlp_hidden = int(embed_dim * mlp_ratio)
@@ -240,7 +245,7 @@ class VisionTransformer(nn.Module):
         self._engine.pack(self._engine_tensors, self._pack_key())
         spec = x.reshape(B, T, F)
         logits, scores, idxs = self._engine.run(spec, rates, self.num_classes, want_all_scores=flag_extract_features,
-                                                precision=self.precision, use_graph=self.use_cuda_graph)
+                                                precision=self.precision, use_graph=self.use_cuda_graph, fuse_token=self.fuse_token)
         self.last_scores, self.last_topk_idx = scores, idxs
         if flag_extract_features:
             feature_dict = {'mel': x.cpu()}                                   # models_vit.py:338-339

@@ -94,27 +94,37 @@ def attention(qkv: torch.Tensor, B: int, N: int, H: int, num_extra: int, score_m
     return out, partial
 
 
-def score_topk(partial: torch.Tensor, divisor: float, num_extra: int, k: int):
-    """partial [B,R,N] -> (score [B,N-extra] fp32, topk_idx [B,k] int64 or None)."""
+def score_topk(partial: torch.Tensor, divisor: float, num_extra: int, k: int, want_rest: bool = False):
+    """partial [B,R,N] -> (score [B,N-extra] fp32, topk_idx [B,k] int64 or None[, rest_idx [B,n-k] int32])."""
     _req(partial, torch.float32, "partial")
     B, R, N = partial.shape
     score = torch.empty(B, N - num_extra, device=partial.device, dtype=torch.float32)
     idx = torch.empty(B, k, device=partial.device, dtype=torch.int64) if k > 0 else None
-    check(lib.tpat_score_topk(partial.data_ptr(), R, float(divisor), score.data_ptr(), _ptr(idx), B, N, num_extra, k,
-                              _stream()), "tpat_score_topk")
-    return score, idx
+    rest = torch.empty(B, N - num_extra - k, device=partial.device, dtype=torch.int32) if want_rest else None
+    check(lib.tpat_score_topk(partial.data_ptr(), R, float(divisor), score.data_ptr(), _ptr(idx), _ptr(rest), B, N, num_extra,
+                              k, _stream()), "tpat_score_topk")
+    return (score, idx, rest) if want_rest else (score, idx)
 
 
 def gather_layernorm(x: torch.Tensor, idx: torch.Tensor, num_extra: int, gamma: Optional[torch.Tensor],
-                     beta: Optional[torch.Tensor], eps: float, out_dtype: torch.dtype):
-    """x [B,N,D] fp32, idx [B,k] -> (x_out [B,extra+k,D] fp32, LayerNorm(x_out) or None)."""
+                     beta: Optional[torch.Tensor], eps: float, out_dtype: torch.dtype, score: Optional[torch.Tensor] = None,
+                     rest_idx: Optional[torch.Tensor] = None):
+    """x [B,N,D] fp32, idx [B,k] -> (x_out [B,extra+k(+1),D] fp32, LayerNorm(x_out) or None).
+    With ``score`` and ``rest_idx`` the EViT fused inattentive token is appended as the last row."""
     _req(x, torch.float32, "x"); _req(idx, torch.int64, "idx")
     B, N, D = x.shape
     k = idx.shape[1]
-    xo = torch.empty(B, num_extra + k, D, device=x.device, dtype=torch.float32)
-    yo = torch.empty(B, num_extra + k, D, device=x.device, dtype=out_dtype) if gamma is not None else None
+    fuse = rest_idx is not None
+    rows = num_extra + k + (1 if fuse else 0)
+    xo = torch.empty(B, rows, D, device=x.device, dtype=torch.float32)
+    yo = torch.empty(B, rows, D, device=x.device, dtype=out_dtype) if gamma is not None else None
     check(lib.tpat_gather_layernorm(x.data_ptr(), idx.data_ptr(), xo.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(yo),
-                                    _DT[out_dtype], B, N, k, num_extra, D, float(eps), _stream()), "tpat_gather_layernorm")
+                                    _DT[out_dtype], B, N, k, num_extra, rows, D, float(eps), _stream()), "tpat_gather_layernorm")
+    if fuse:
+        _req(score, torch.float32, "score"); _req(rest_idx, torch.int32, "rest_idx")
+        check(lib.tpat_fuse_token(x.data_ptr(), score.data_ptr(), rest_idx.data_ptr(), xo.data_ptr(), _ptr(gamma), _ptr(beta),
+                                  _ptr(yo), _DT[out_dtype], B, N, rest_idx.shape[1], rows, rows - 1, num_extra, D, float(eps),
+                                  _stream()), "tpat_fuse_token")
     return xo, yo
 
 
