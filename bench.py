@@ -208,7 +208,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the forward as a CUDA graph")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the 91 kernels eagerly instead of replaying a CUDA graph")
+    ap.set_defaults(graph=True)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 

@@ -1,5 +1,6 @@
 """CPU: the host-side mirror of the reference model API (names, state-dict keys, errors, schedule)."""
 import math
+import os
 
 import pytest
 import torch
@@ -114,3 +115,30 @@ def test_oracle_fused_token_shapes():
     assert logits.shape == (2, 35)
     assert feats["block-3.topk_idx"].shape == (2, 45) and feats["block-4.attn_score"].shape == (2, 46)
     assert feats["block-6.topk_idx"].shape == (2, math.ceil(0.7 * 46))
+
+
+def test_extract_contract_helpers(tmp_path):
+    """N2: the on-disk / index-composition contract extract_stats.py consumes."""
+    from tpat import extract
+    g = torch.Generator().manual_seed(0)
+    i3 = torch.stack([torch.randperm(64, generator=g)[:45] for _ in range(2)])
+    i6 = torch.stack([torch.randperm(45, generator=g)[:32] for _ in range(2)])
+    i9 = torch.stack([torch.randperm(32, generator=g)[:23] for _ in range(2)])
+    feats = {"mel": torch.randn(2, 1, 128, 128, generator=g), "block-3.attn_score": torch.rand(2, 64),
+             "block-3.topk_idx": i3, "block-6.topk_idx": i6, "block-9.topk_idx": i9}
+    paths = extract.save_feature_dict(feats, str(tmp_path), 7)
+    assert sorted(os.path.basename(p) for p in paths) == sorted(f"{k}.0007.pth" for k in feats)
+    assert torch.equal(torch.load(str(tmp_path / "block-6.topk_idx.0007.pth")), i6)
+    mel = extract.get_melspec_idx(extract.topk_indices_of(feats))
+    assert [t.tolist() for t in mel] == [t.tolist() for t in vo.melspec_indices([i3, i6, i9])]
+    assert torch.equal(mel[2][0], i3[0][i6[0][i9[0]]])
+    # fused-token variant: index len(prev) maps to the dummy 0 column
+    f6 = i6.clone(); f6[:, 0] = 45
+    assert extract.get_melspec_idx([i3, f6], fuse_token=True)[1][:, 0].tolist() == [0, 0]
+    # apply_mask keeps exactly the listed 16x16 patches
+    x = feats["mel"]
+    masked = extract.apply_mask(x, mel[2])
+    patches = x.reshape(2, 1, 8, 16, 8, 16)
+    keep = torch.zeros(2, 64, dtype=torch.bool); keep.scatter_(1, mel[2], True)
+    ref = (patches * keep.reshape(2, 1, 8, 1, 8, 1)).reshape(2, 1, 128, 128)
+    assert torch.equal(masked, ref)
