@@ -3,12 +3,13 @@
 // Replaces q k^T * scale, softmax, attn @ v and the score slice/mean over the materialised
 // [B,H,N,N] matrix (reference audiomae/models_vit.py:79-95,113; ast/src/models/ast_models.py:92-109,124).
 // One CTA per (clip, head, 128-query tile), two CTAs resident per SM (<= 113 KB smem, 256 TMEM
-// columns each) so one CTA's softmax hides the other's prologue / MMA round trips.  192 threads:
+// columns each) so one CTA's softmax hides the other's prologue / MMA round trips.  320 threads:
 //   warp 0   TMA producer: Q tile once, then K / V 64-key tiles into a 6-slot 8 KB ring
 //            (3-D tensor maps over qkv[B][N][3*H*64]: rows >= N are zero-filled, never the next clip)
 //   warp 1   MMA issuer (one elected thread): S = Q K^T (M=128,N=64,K=64) into one of two TMEM
 //            buffers; O += P V (M=128,N=64,K<=64) with P from 128B-swizzled smem, V as MN-major B
-//   warps 2-5 softmax: thread = query row = TMEM lane; 64 scores per thread per key block.
+//   warps 2-9 softmax: thread = (query row = TMEM lane, 32-key half); warps w and w+4 share a row quarter and
+//            split each 64-key block by columns (four softmax warps per SM sub-partition with two CTAs resident).
 //
 // Two instantiations:
 //  TWO_PASS = true  (tiles that must emit NORMALISED probabilities for the importance score; the
@@ -43,7 +44,7 @@ constexpr int AT_SLOTS = AT_CTAS_PER_SM >= 3 ? 3 : 6;     // K/V ring slots
 constexpr int AT_Q_BYTES = AT_BM * AT_HD * 2;    // 16 KB (also one P buffer / the O staging tile)
 constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;   // 8 KB
 constexpr int AT_P_BYTES = AT_BM * AT_BK * 2;    // 16 KB
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps
 constexpr int AT_TMEM_COLS = AT_SBUF == 1 ? 128 : 256;   // S buffers [0, 64*SBUF), then O (64 columns)
 constexpr int AT_SMEM_LIMIT = 227 * 1024;   // hard cap; <= 113 KB keeps two CTAs per SM (N <= 960 with the column-sum buffer)
 constexpr float AT_RESCALE_LOG2 = 64.0f;  // online softmax: the reference max is only raised past 2^64 (then the tile is redone)
@@ -110,7 +111,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t* p_empty = p_full + 2;          // [2]
   uint64_t* o_full = p_empty + 2;          // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* colsum_s = reinterpret_cast<float*>(bars + 32);  // [4][nb*64] when COLMEAN
+  float2* pair_s = reinterpret_cast<float2*>(bars + 32);   // [2][128]: row statistics exchanged between partner warps
+  int* flag_s = reinterpret_cast<int*>(pair_s + 2 * AT_BM);  // [2 tile parities][4 quarters][2 halves]: 'reference max must rise'
+  float* colsum_s = reinterpret_cast<float*>(flag_s + 16);   // [4][nb*64] when COLMEAN
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,8 +130,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < AT_SLOTS; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&s_empty[i], 4);
-      ptx::mbar_init(&p_full[i], 4); ptx::mbar_init(&p_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&s_empty[i], 8);
+      ptx::mbar_init(&p_full[i], 8); ptx::mbar_init(&p_empty[i], 1);
     }
     ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
@@ -216,8 +219,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       ptx::tc_commit(o_full);
     }
   } else {
-    // ===== softmax / epilogue warps: TMEM lane quarter = warp % 4, thread = query row =====
+    // ===== softmax / epilogue warps: 8 warps, TMEM lane quarter = warp % 4, thread = (query row, 32-key half) =====
+    // Two warps share each 32-row quarter and split every 64-key tile by columns, so an SM sub-partition holds
+    // four softmax warps (two per resident CTA): twice the latency hiding around the MUFU.EX2 bursts for the same
+    // number of exponentials.  In the single-pass mode both partners read the FULL score row and reduce its max
+    // (a few FMNMX on the ALU pipe): the lazy-rescale decision below is then a pure function of identical data and
+    // the partners take it together without exchanging a word.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r_local = quarter * 32 + lane;
     const int row = q0 + r_local;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
@@ -228,6 +237,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // barrier protocol going: no TMEM reads, no exps, no P / O writes.  Its P rows stay whatever is in smem and its
     // O rows are garbage, but rows are independent and rows >= N are never stored.
     const bool warp_live = q0 + quarter * 32 < p.N;
+    float2* my_x = pair_s + half * AT_BM + r_local;
+    const float2* other_x = pair_s + (half ^ 1) * AT_BM + r_local;
 #ifdef TPAT_ATTN_TRACE
     const bool tracing = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == (gridDim.z >> 1) && threadIdx.x == 64;
     int trace_n = 0;
@@ -235,74 +246,64 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (tracing) { t_start = clock64(); }
     ATTN_TRACE(1);
 #endif
-
-    // load one 64-column S tile (only the 32-column halves that hold valid keys), release the TMEM
-    // buffer as soon as the values are in registers, mask the columns >= N of a boundary tile to -inf
-    auto load_s = [&](int sb, int valid, uint32_t (&r0)[32], uint32_t (&r1)[32]) {
-      if (warp_live) {
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK, r0);
-        if (valid > 32) ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + 32, r1);
-        ptx::tmem_ld_wait();
-      }
+    auto release_s = [&](int sb) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_empty[sb]);
-      if (valid < 32) {
+    };
+    auto mask_tail = [&](int v, uint32_t (&r)[32]) {     // columns >= v of this half do not exist: -inf
+      if (v < 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) if (i >= valid) r0[i] = 0xff800000u;   // -inf
-      } else if (valid > 32 && valid < 64) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (32 + i >= valid) r1[i] = 0xff800000u;
+        for (int i = 0; i < 32; ++i) if (i >= v) r[i] = 0xff800000u;
       }
     };
-    auto tile_max = [&](int valid, const uint32_t (&r0)[32], const uint32_t (&r1)[32], float seed) {
-      float mx0 = seed, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+    auto max32 = [&](const uint32_t (&r)[32]) {
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(r0[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r0[i + 3]));
-      }
-      if (valid > 32) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(r1[i])); mx1 = fmaxf(mx1, __uint_as_float(r1[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(r1[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r1[i + 3]));
-        }
+        mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
       }
       return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
     };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;\n" ::"r"(2 + quarter) : "memory"); };
 
     if (TWO_PASS) {
-      // ---- pass 1: row max and sum of exp ----
+      // ---- pass 1: max and sum of exp over this thread's columns, merged with the partner's at the end ----
       for (int j = 0; j < nb; ++j, ++sidx) {
         const int sb = sidx % AT_SBUF;
         ptx::mbar_wait(&s_full[sb], (sidx / AT_SBUF) & 1);
         ptx::tc_fence_after();
-        const int valid = p.N - j * AT_BK;                 // > 0
-        uint32_t r0[32], r1[32];
-        load_s(sb, valid, r0, r1);
-        if (!warp_live) continue;
-        const float mx = tile_max(valid, r0, r1, m_run);
+        const int vh = p.N - j * AT_BK - half * 32;      // valid columns in this thread's half (may be <= 0)
+        uint32_t r[32];
+        if (warp_live && vh > 0) {
+          ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + half * 32, r);
+          ptx::tmem_ld_wait();
+        }
+        release_s(sb);
+        if (!warp_live || vh <= 0) continue;
+        mask_tail(vh, r);
+        const float mx = fmaxf(m_run, max32(r));
         const float mc = mx * c;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          a0 += ptx::ex2_ftz(fmaf(__uint_as_float(r0[i]), c, -mc));
-          a1 += ptx::ex2_ftz(fmaf(__uint_as_float(r0[i + 1]), c, -mc));
-          a2 += ptx::ex2_ftz(fmaf(__uint_as_float(r0[i + 2]), c, -mc));
-          a3 += ptx::ex2_ftz(fmaf(__uint_as_float(r0[i + 3]), c, -mc));
-        }
-        if (valid > 32) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            a0 += ptx::ex2_ftz(fmaf(__uint_as_float(r1[i]), c, -mc));
-            a1 += ptx::ex2_ftz(fmaf(__uint_as_float(r1[i + 1]), c, -mc));
-            a2 += ptx::ex2_ftz(fmaf(__uint_as_float(r1[i + 2]), c, -mc));
-            a3 += ptx::ex2_ftz(fmaf(__uint_as_float(r1[i + 3]), c, -mc));
-          }
+          a0 += ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -mc));
+          a1 += ptx::ex2_ftz(fmaf(__uint_as_float(r[i + 1]), c, -mc));
+          a2 += ptx::ex2_ftz(fmaf(__uint_as_float(r[i + 2]), c, -mc));
+          a3 += ptx::ex2_ftz(fmaf(__uint_as_float(r[i + 3]), c, -mc));
         }
         l_run = l_run * ptx::ex2_ftz((m_run - mx) * c) + ((a0 + a1) + (a2 + a3));
         m_run = mx;
+      }
+      if (warp_live) {                                   // both partner warps are live together
+        *my_x = make_float2(m_run, l_run);
+        pair_sync();
+        const float2 o = *other_x;
+        const float m = fmaxf(m_run, o.x);               // finite: key 0 always exists
+        l_run = l_run * ptx::ex2_ftz((m_run - m) * c) + o.y * ptx::ex2_ftz((o.x - m) * c);
+        m_run = m;
+        pair_sync();                                     // pair_s is reused for the row sums below
       }
     }
     // exponent offset: p = 2^(s*c - off).  Two-pass tiles fold log2(l) in (normalised probabilities).
@@ -319,25 +320,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       ptx::tc_fence_after();
       ATTN_TRACE(3);
       const int valid = p.N - j * AT_BK;                 // > 0
-      uint32_t r0[32], r1[32];
-      load_s(sb, valid, r0, r1);
-      ATTN_TRACE(4);
+      const int vh = valid - half * 32;                  // valid columns in this thread's half (may be <= 0)
       if (!warp_live) {
-        if (TWO_PASS && p.score_mode == TPAT_SCORE_COLMEAN) {   // this warp's rows contribute nothing to the column sums
-          colsum_w[j * AT_BK + lane] = 0.f;
-          colsum_w[j * AT_BK + 32 + lane] = 0.f;
-        }
+        if (TWO_PASS && p.score_mode == TPAT_SCORE_COLMEAN)     // this warp's rows contribute nothing to the column sums
+          colsum_w[j * AT_BK + half * 32 + lane] = 0.f;
+        release_s(sb);
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
         continue;
       }
+      uint32_t r[32];
+      if (vh > 0) { ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + half * 32, r); ptx::tmem_ld_wait(); }
+      release_s(sb);
+      if (vh > 0) mask_tail(vh, r);
+      ATTN_TRACE(4);
       if (!TWO_PASS) {
         // Online softmax with a LAZY reference max: tile 0 fixes m_ref = its row max; later tiles compute their
         // probabilities against the current m_ref straight away (their own max is evaluated off the critical
         // path) and only if some row's max exceeds m_ref by more than 2^64 is the tile redone after raising m_ref
         // and rescaling O (TMEM) and the running sum.  Probabilities stay <= 2^64: exact in bf16 / fp32 range.
-        if (j == 0) m_run = tile_max(valid, r0, r1, -INFINITY);
+        if (j == 0) {                                    // the row max of tile 0: one exchange with the partner
+          const float mx_own = vh > 0 ? max32(r) : -INFINITY;
+          my_x->x = mx_own;
+          pair_sync();
+          m_run = fmaxf(mx_own, other_x->x);
+        }
         off = m_run * c;
       }
       ATTN_TRACE(5);
@@ -345,65 +353,61 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // in issue order and s_full(j) is a commit of everything issued before it, so the buffer is already free.
       uint8_t* p_row = p_s + pb * AT_P_BYTES + r_local * 128;
       const float l2a_in = l2a, l2b_in = l2b, l2c_in = l2c, l2d_in = l2d;
-      auto emit_tile = [&]() {
+      auto emit_half = [&]() {
+        const int col0 = j * AT_BK + half * 32;
+        if (vh <= 0) {
+          if (half * 32 < ((valid + 15) & ~15)) {        // still inside the MMA's K range: zero it
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t (&r)[32] = hf == 0 ? r0 : r1;
-          const int col0 = j * AT_BK + hf * 32;
-          const int vh = valid - hf * 32;                  // valid columns in this half (may be <= 0)
-          if (vh <= 0) {
-            if (hf * 32 < ((valid + 15) & ~15)) {          // still inside the MMA's K range: zero it
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                *reinterpret_cast<uint4*>(p_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
-            }
-            continue;
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(p_row + (((half * 4 + g) ^ (r_local & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
           }
-          float v[32];
-          if (!TWO_PASS && AT_POLY_EVERY > 0 && vh >= 32) {
+          return;
+        }
+        float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = fmaf(__uint_as_float(r[i]), c, -off);
-              v[i] = (AT_POLY_EVERY > 0 && (i % (AT_POLY_EVERY > 0 ? AT_POLY_EVERY : 1)) == (AT_POLY_EVERY - 1)) ? exp2_poly(x) : ptx::ex2_ftz(x);
-            }
-          } else {
+        for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));   // -inf -> 0
+        if (!TWO_PASS) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));   // -inf -> 0
-          }
-          if (!TWO_PASS) {
+          for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
+        }
+        store_p_half(p_row, half, r_local, v);
+        if (TWO_PASS) {
+          if (p.score_mode == TPAT_SCORE_COLMEAN) {
+            // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
-          }
-          store_p_half(p_row, hf, r_local, v);
-          if (TWO_PASS) {
-            if (p.score_mode == TPAT_SCORE_COLMEAN) {
-              // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
+            for (int i = 0; i < 32; ++i) v[i] *= row_w;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= row_w;
+            for (int o = 16; o >= 1; o >>= 1) {
+              const bool upper = (lane & o) != 0;
 #pragma unroll
-              for (int o = 16; o >= 1; o >>= 1) {
-                const bool upper = (lane & o) != 0;
-#pragma unroll
-                for (int i = 0; i < o; ++i) {
-                  const float send = upper ? v[i] : v[i + o];
-                  const float keep = upper ? v[i + o] : v[i];
-                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-                }
+              for (int i = 0; i < o; ++i) {
+                const float send = upper ? v[i] : v[i + o];
+                const float keep = upper ? v[i + o] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
               }
-              colsum_w[col0 + lane] = v[0];
-            } else if (cls_writer) {
-              float* dst = p.score_partial + ((size_t)b * p.H + h) * p.N;
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) dst[col0 + i] = v[i];
             }
+            colsum_w[col0 + lane] = v[0];
+          } else if (cls_writer) {
+            float* dst = p.score_partial + ((size_t)b * p.H + h) * p.N;
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) dst[col0 + i] = v[i];
           }
         }
       };
-      emit_tile();
+      emit_half();
       if (!TWO_PASS && j > 0) {
-        const float mx = tile_max(valid, r0, r1, -INFINITY);
-        const bool need = (mx - m_run) * c > AT_RESCALE_LOG2;
-        if (__any_sync(0xffffffffu, need)) {
+        // does any row of this quarter need a higher reference?  Each partner knows its own columns only: the
+        // warp-level verdicts are swapped through shared memory (slot = tile parity) around a 64-thread barrier
+        const float mx_own = vh > 0 ? max32(r) : -INFINITY;
+        const bool need_w = __any_sync(0xffffffffu, (mx_own - m_run) * c > AT_RESCALE_LOG2);
+        if (lane == 0) flag_s[(j & 1) * 8 + quarter * 2 + half] = need_w ? 1 : 0;
+        pair_sync();
+        if (need_w || flag_s[(j & 1) * 8 + quarter * 2 + (half ^ 1)] != 0) {
+          my_x->x = mx_own;
+          pair_sync();
+          const float mx = fmaxf(mx_own, other_x->x);    // the full row's max: same value in both partners
+          pair_sync();
+          const bool need = (mx - m_run) * c > AT_RESCALE_LOG2;
           // rare: raise m_ref, rescale what was accumulated before this tile, redo the tile
           const float f = need ? ptx::ex2_ftz((m_run - mx) * c) : 1.0f;
           if (need) m_run = mx;
@@ -412,18 +416,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           // every PV issued so far (up to block j-1) must have retired before O is touched
           ptx::mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
           ptx::tc_fence_after();
-#pragma unroll 1
-          for (int oh = 0; oh < 2; ++oh) {
-            uint32_t o0[32];
-            ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + oh * 32, o0);
+          {
+            uint32_t o0[32];                             // this thread's 32 of the row's 64 output columns
+            ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + half * 32, o0);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * f);
-            ptx::tmem_st_32x32b_x32(tmem_o + lane_off + oh * 32, o0);
+            ptx::tmem_st_32x32b_x32(tmem_o + lane_off + half * 32, o0);
           }
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
-          emit_tile();
+          emit_half();
         }
       }
       ATTN_TRACE(7);
@@ -432,36 +435,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
       ATTN_TRACE(8);
     }
+    // the row sum is split between the partners
+    float o_scale = 1.0f;
+    if (!TWO_PASS && warp_live) {
+      const float l_own = (l2a + l2b) + (l2c + l2d);
+      my_x->y = l_own;
+      pair_sync();
+      o_scale = 1.0f / (l_own + other_x->y);
+    }
     // ---- epilogue: O (TMEM) -> bf16 -> swizzled smem tile -> one TMA store ----
     ATTN_TRACE(9);
     ptx::mbar_wait(o_full, 0);         // every PV MMA retired: the P buffers are free as well
     ptx::tc_fence_after();
     ATTN_TRACE(10);
-    const float o_scale = TWO_PASS ? 1.0f : 1.0f / ((l2a + l2b) + (l2c + l2d));
     if (warp_live) {
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32b_x32(tmem_o + lane_off, r0);
-      ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + 32, r1);
+      uint32_t r0[32];
+      ptx::tmem_ld_32x32b_x32(tmem_o + lane_off + half * 32, r0);
       ptx::tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) * o_scale;
-      store_p_half(p_s + r_local * 128, 0, r_local, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r1[i]) * o_scale;
-      store_p_half(p_s + r_local * 128, 1, r_local, v);
+      store_p_half(p_s + r_local * 128, half, r_local, v);
     }
     ptx::fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
     if (warp == 2 && lane == 0) {
       ptx::tma_store_3d(&tmap_o, p_s, h * AT_HD, q0, b);   // rows >= N are clipped by the tensor map
       ptx::tma_store_commit();
     }
     if (TWO_PASS && p.score_mode == TPAT_SCORE_COLMEAN) {
-      // sum the four warps' column sums in a fixed order and publish this tile's partial row
+      // sum the four quarters' column sums in a fixed order and publish this tile's partial row
       float* dstp = p.score_partial + ((size_t)b * p.H * p.n_qt + (size_t)h * p.n_qt + qt) * p.N;
       const int ldc = nb * AT_BK;
-      for (int jcol = threadIdx.x - 64; jcol < p.N; jcol += 128)
+      for (int jcol = threadIdx.x - 64; jcol < p.N; jcol += 256)
         dstp[jcol] = ((colsum_s[jcol] + colsum_s[ldc + jcol]) + colsum_s[2 * ldc + jcol]) + colsum_s[3 * ldc + jcol];
     }
     if (warp == 2 && lane == 0) ptx::tma_store_wait_read<0>();   // smem must outlive the bulk store's reads
@@ -529,7 +535,7 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
   p.nb = (N + AT_BK - 1) / AT_BK;
   p.qt_offset = 0;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const size_t base_smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_SLOTS * AT_KV_BYTES + 256;
+  const size_t base_smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_SLOTS * AT_KV_BYTES + 256 + 2 * AT_BM * sizeof(float2) + 64;
   const size_t colsum_bytes = (size_t)4 * p.nb * AT_BK * sizeof(float);
   TPAT_CHECK(base_smem + (score_mode == TPAT_SCORE_COLMEAN ? colsum_bytes : 0) <= (size_t)AT_SMEM_LIMIT,
              "tpat_attention(tc): N=%d needs %zu bytes of shared memory", N, base_smem + colsum_bytes);
