@@ -20,6 +20,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return 2;
 }
 
+thread_local int g_walk_desc = 0;
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;

@@ -64,6 +64,7 @@ struct AttnTcParams {
   float* score_partial;
   int score_mode;
   int N, H, num_extra, n_qt, nb, qt_offset;
+  int desc;          // 1 = clips are visited from the last one down (see g_walk_desc)
   float scale_log2;  // scale * log2(e)
 };
 
@@ -117,7 +118,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x + p.qt_offset, h = blockIdx.y, b = blockIdx.z;
+  const int qt = blockIdx.x + p.qt_offset, h = blockIdx.y;
+  const int b = p.desc ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
   const int q0 = qt * AT_BM;
   const int nb = p.nb;
 
@@ -365,7 +367,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));   // -inf -> 0
+        for (int i = 0; i < 32; ++i) {
+          const float x = fmaf(__uint_as_float(r[i]), c, -off);                                   // -inf -> 0
+          v[i] = (AT_POLY_EVERY > 0 && (i % (AT_POLY_EVERY > 0 ? AT_POLY_EVERY : 1)) == AT_POLY_EVERY - 1) ? exp2_poly(x) : ptx::ex2_ftz(x);
+        }
         if (!TWO_PASS) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
@@ -534,6 +539,7 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
   p.n_qt = attention_tc_qtiles(N);
   p.nb = (N + AT_BK - 1) / AT_BK;
   p.qt_offset = 0;
+  p.desc = g_walk_desc;
   p.scale_log2 = scale * 1.4426950408889634f;
   const size_t base_smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_SLOTS * AT_KV_BYTES + 256 + 2 * AT_BM * sizeof(float2) + 64;
   const size_t colsum_bytes = (size_t)4 * p.nb * AT_BK * sizeof(float);

@@ -37,6 +37,12 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 int sm_count();  // cached multiprocessor count of the current device
 bool pdl_enabled();  // programmatic dependent launch when TPAT_PDL=1 (measured r01: 11.18k vs 11.46k clips/s -> off by default)
 
+// Walk direction of the next launches made by this thread (library-internal, set by tpat_forward only; the per-kernel
+// entry points default to ascending).  1 = the kernel visits its rows / row tiles / clips from the END.  A kernel
+// that starts on the rows its producer wrote last finds them still in the 126 MB L2, and leaves the other end of its
+// own output hot for the next kernel, so tpat_forward alternates the direction along the producer -> consumer chain.
+extern thread_local int g_walk_desc;
+
 // Every kernel CAN be launched with programmatic stream serialization (TPAT_PDL=1): the next kernel's CTAs may be
 // scheduled (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the tail of the
 // previous kernel drains; each kernel calls pdl_wait() before its first access to global memory and

@@ -112,6 +112,13 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
   const int P = (a->T / 16) * (a->F / 16);
   const float scale = 0.125f;  // head_dim ** -0.5 with head_dim == 64 (models_vit.py:58)
 
+  // Alternate the walk direction of the big kernels along the producer -> consumer chain (see g_walk_desc):
+  // each one starts on the rows the previous one wrote last.  TPAT_WALK=0 keeps every kernel ascending.
+  static const bool alternate = [] { const char* e = getenv("TPAT_WALK"); return !(e && e[0] == '0'); }();
+  struct WalkGuard { ~WalkGuard() { g_walk_desc = 0; } } walk_guard;
+  g_walk_desc = 0;
+  auto flip = [&]() { if (alternate) g_walk_desc ^= 1; };
+
   // patch embed + pos + cls/dist rows (models_vit.py:357-362 / ast_models.py:460-466)
   if (int rc = tpat_patchify(a->spec, w.hid, act, w.x[0], a->extra_tok, a->pos, B, a->T, a->F, D, extra,
                              ast ? TPAT_TOKENS_FREQ_MAJOR : TPAT_TOKENS_TIME_MAJOR, stream)) return rc;
@@ -126,11 +133,15 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
     const bool prune = a->prune[i] != 0;
     const bool want_score = prune || a->want_all_scores;
     float* x = w.x[xi];
+    flip();
     if (int rc = tpat_layernorm(x, bw.ln1_g, bw.ln1_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
+    flip();
     if (int rc = tpat_gemm(w.y, act, D, bw.qkv_w, act, bw.qkv_b, w.qkv, act, 3 * D, nullptr, 0, nullptr, 0, 0,
                            M, 3 * D, D, TPAT_EPI_BIAS, impl, stream)) return rc;
     const int smode = !want_score ? TPAT_SCORE_NONE : (ast ? TPAT_SCORE_CLS_ROW : TPAT_SCORE_COLMEAN);
+    flip();
     if (int rc = tpat_attention(w.qkv, w.ao, act, w.partial, smode, B, N, H, 64, extra, scale, impl, stream)) return rc;
+    flip();
     if (int rc = tpat_gemm(w.ao, act, D, bw.proj_w, act, bw.proj_b, x, TPAT_F32, D, x, D, nullptr, 0, 0,
                            M, D, D, TPAT_EPI_BIAS_RESIDUAL, impl, stream)) return rc;
     if (want_score) {
@@ -142,6 +153,7 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
                                    fuse_here ? w.rest : nullptr, B, N, extra, prune ? a->keep[i] : 0, stream)) return rc;
     }
     int M2 = M;
+    flip();
     if (prune) {
       float* xn = w.x[xi ^ 1];
       const bool fuse_here = a->fuse_token && a->keep[i] < cur;
@@ -160,8 +172,10 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
     } else {
       if (int rc = tpat_layernorm(x, bw.ln2_g, bw.ln2_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
     }
+    flip();
     if (int rc = tpat_gemm(w.y, act, D, bw.fc1_w, act, bw.fc1_b, w.hid, act, Dh, nullptr, 0, nullptr, 0, 0,
                            M2, Dh, D, TPAT_EPI_BIAS_GELU, impl, stream)) return rc;
+    flip();
     if (int rc = tpat_gemm(w.hid, act, Dh, bw.fc2_w, act, bw.fc2_b, x, TPAT_F32, D, x, D, nullptr, 0, 0,
                            M2, D, Dh, TPAT_EPI_BIAS_RESIDUAL, impl, stream)) return rc;
   }

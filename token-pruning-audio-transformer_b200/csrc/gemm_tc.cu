@@ -177,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (ptx::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.tiles_n) * TG_BM, n0 = (tile % p.tiles_n) * TG_BN;
+        const int m0 = tc_tile_m(p, tile) * TG_BM, n0 = (tile % p.tiles_n) * TG_BN;
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], TG_STAGE_BYTES);
@@ -221,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* stg = staging + (warp - 2) * 4096;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * TG_BM + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
+      const int m0 = tc_tile_m(p, tile) * TG_BM + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
       TcEpiPrefetch<TG_EPI_WARPS> pf;
       tc_epilogue_prefetch<TG_EPI_WARPS>(p, n0, cg, lane, pf);
       ptx::mbar_wait(&acc_full[acc], acc_phase);
@@ -279,6 +279,7 @@ int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + TG_BN - 1) / TG_BN;
+  p.desc = g_walk_desc;
   p.debug_skip = 0;
   switch (ep.epilogue) {
     case TPAT_EPI_BIAS:

@@ -86,7 +86,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (ptx::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128;
+        const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128;
         const int n0 = (tile % p.tiles_n) * TG_BN + (int)rank * 128;
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -134,7 +134,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if constexpr (!kResTma) {
       uint8_t* stg = staging + (warp - 2) * 4096;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128 + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
+        const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
         TcEpiPrefetch<T2_EPI_WARPS> pf;
         tc_epilogue_prefetch<T2_EPI_WARPS>(p, n0, cg, lane, pf);
         ptx::mbar_wait(&acc_full[acc], acc_phase);
@@ -164,7 +164,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       };
       auto issue_load = [&](int tile, int ci, int b) {   // lane 0 only
-        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128 + q * 32;
+        const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32;
         ptx::tma_store_wait_read<0>();                   // the store that last read this buffer has drained its smem reads
         ptx::mbar_arrive_expect_tx(&rb[b], 4096);
         ptx::tma_load_2d(stg + b * 4096, &tmap_r, &rb[b], item_cols(tile, ci), m0);
@@ -175,7 +175,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (t0 < num_tiles && lane == 0) issue_load(t0, c0, 0);
       }
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / p.tiles_n) * 256 + (int)rank * 128 + q * 32;
+        const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32;
         const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
         const uint32_t rel_leader = ptx::mapa_shared(ptx::smem_u32(&acc_empty[acc]), 0);
         ptx::mbar_wait(&acc_full[acc], acc_phase);
@@ -265,6 +265,7 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.tiles_m = (M + 255) / 256; p.tiles_n = (N + TG_BN - 1) / TG_BN;
+  p.desc = g_walk_desc;
   { const char* e = getenv("TPAT_GEMM_DEBUG_SKIP"); p.debug_skip = e ? atoi(e) : 0; }
   switch (ep.epilogue) {
     case TPAT_EPI_BIAS:

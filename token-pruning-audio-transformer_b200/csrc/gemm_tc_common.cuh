@@ -22,8 +22,15 @@ struct TcGemmParams {
   const float* residual; int ldr;
   const float* pos; int P, num_extra;
   int tiles_m, tiles_n;
+  int desc;         // 1 = walk the row tiles from the last one down (see g_walk_desc)
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
 };
+
+// row-tile index of linear tile `tile` (tiles are numbered row-tile-major)
+__device__ __forceinline__ int tc_tile_m(const TcGemmParams& p, int tile) {
+  const int mt = tile / p.tiles_n;
+  return p.desc ? p.tiles_m - 1 - mt : mt;
+}
 
 // GELU for the bf16 tensor-core epilogue: x * sigmoid(x * (c1 + c3 x^2 + c5 x^4)), coefficients fitted
 // (minimax, tools/probes/fit_gelu.py) to the erf form nn.GELU() uses: |error| <= 8.2e-5 absolute over

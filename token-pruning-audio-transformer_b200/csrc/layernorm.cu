@@ -59,13 +59,14 @@ __device__ __forceinline__ void ln_row_store(const float4 (&v)[NV], float mean, 
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(32 * LN_WARPS)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 OutT* __restrict__ y, int rows, float eps) {
+                 OutT* __restrict__ y, int rows, float eps, int desc) {
   constexpr int D = NV * 128;
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (desc) row = rows - 1 - row;        // walk from the end (see g_walk_desc)
   float4 v[NV];
   ln_row_load<NV>(x + (size_t)row * D, lane, v);
   float mean, rstd;
@@ -78,14 +79,15 @@ template <int NV, typename OutT>
 __global__ void __launch_bounds__(32 * LN_WARPS)
 gather_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx, float* __restrict__ x_out,
                         const float* __restrict__ gamma, const float* __restrict__ beta, OutT* __restrict__ y_out,
-                        int B, int N_in, int k, int num_extra, int out_rows, float eps) {
+                        int B, int N_in, int k, int num_extra, int out_rows, float eps, int desc) {
   constexpr int D = NV * 128;
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int N_out = num_extra + k;                 // rows this kernel writes per clip; the clip stride is out_rows
-  const int grow = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  int grow = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (grow >= B * N_out) return;
+  if (desc) grow = B * N_out - 1 - grow;
   const int b = grow / N_out, j = grow - b * N_out;
   const size_t orow = (size_t)b * out_rows + j;
   int src = j;
@@ -313,7 +315,7 @@ static int launch_layernorm(const float* x, const float* g, const float* b, OutT
                             cudaStream_t st) {
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
 #define TPAT_LN_CASE(nv) \
-  case nv: TPAT_CUDA(launch_kernel(layernorm_kernel<nv, OutT>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, g, b, y, rows, eps)); break;
+  case nv: TPAT_CUDA(launch_kernel(layernorm_kernel<nv, OutT>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, g, b, y, rows, eps, g_walk_desc)); break;
   switch (D / 128) {
     TPAT_LN_CASE(1) TPAT_LN_CASE(2) TPAT_LN_CASE(3) TPAT_LN_CASE(4) TPAT_LN_CASE(5) TPAT_LN_CASE(6)
     TPAT_LN_CASE(8) TPAT_LN_CASE(10) TPAT_LN_CASE(12) TPAT_LN_CASE(16)
@@ -330,7 +332,7 @@ static int launch_gather_ln(const float* x, const int64_t* idx, float* xo, const
   const int rows = B * (extra + k);
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
 #define TPAT_GLN_CASE(nv) \
-  case nv: TPAT_CUDA(launch_kernel(gather_layernorm_kernel<nv, OutT>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, idx, xo, g, b, yo, B, N_in, k, extra, out_rows, eps)); break;
+  case nv: TPAT_CUDA(launch_kernel(gather_layernorm_kernel<nv, OutT>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, idx, xo, g, b, yo, B, N_in, k, extra, out_rows, eps, g_walk_desc)); break;
   switch (D / 128) {
     TPAT_GLN_CASE(1) TPAT_GLN_CASE(2) TPAT_GLN_CASE(3) TPAT_GLN_CASE(4) TPAT_GLN_CASE(5) TPAT_GLN_CASE(6)
     TPAT_GLN_CASE(8) TPAT_GLN_CASE(10) TPAT_GLN_CASE(12) TPAT_GLN_CASE(16)
