@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 2
+#define TPAT_VERSION 3
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -77,6 +77,23 @@ int tpat_device_ok(void);
 int tpat_patchify(const float* spec, void* patches, int out_dtype, float* tokens,
                   const float* extra_tok, const float* pos, int B, int T, int F, int D,
                   int num_extra, int order, tpat_stream_t stream);
+
+/*
+ * Per-patch statistics of the spectrogram, in token order: the ablation ranking vectors.
+ * Replaces `rearrange(x, 'b c (h p) (w q) -> b (c p q) (h w)', p=16, q=16).mean(dim=1)` / `.std(dim=1)`
+ * (unbiased, n-1) of models_vit.py:345-349,354-355 and ast_models.py:447-451,456-457.
+ *   spec [B, T, F] fp32;  mean / std [B, P] fp32, either may be NULL;  order as for tpat_patchify.
+ */
+int tpat_patch_stats(const float* spec, float* mean, float* std, int B, int T, int F, int order,
+                     tpat_stream_t stream);
+
+/*
+ * out[b, i] = rank[b, idx[b, i]]: carries a custom ranking vector through a pruning block
+ * (`custom_rank = torch.gather(custom_rank, dim=1, index=topk_idx)`, models_vit.py:373-374, ast_models.py:482-483).
+ *   rank [B, n] fp32, idx [B, k] int64 with values in [0, n), out [B, k] fp32.
+ */
+int tpat_gather_rank(const float* rank, const int64_t* idx, float* out, int B, int n, int k,
+                     tpat_stream_t stream);
 
 /*
  * LayerNorm over the last dim.  Replaces nn.LayerNorm (models_vit.py:197,205; ast_models.py:209,217,500).

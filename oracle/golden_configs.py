@@ -32,3 +32,37 @@ GOLDEN_CONFIGS = {
     "ast_spc2_b4_unpruned": dict(variant="ast", T=128, B=4, num_classes=35, drop_loc=(),
                                  base_keep_rate=1.0, keep_rate_list=None, flavour="perturbed", wseed=5, xseed=3),
 }
+
+# Ablation paths of the reference forward: custom patch-statistic ranking and the batch-of-one
+# intensity filter.  Golden files tests/golden/abl_<name>.pt hold the reference's logits (or None).
+ABLATION_CONFIGS = {
+    "audiomae_256_b2_rank_mean": dict(variant="audiomae", T=256, B=2, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                      keep_rate_list=None, flavour="perturbed", wseed=3, xseed=5, use_custom_rank="mean"),
+    "audiomae_1024_b2_rank_std": dict(variant="audiomae", T=1024, B=2, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                      keep_rate_list=None, flavour="perturbed", wseed=3, xseed=6, use_custom_rank="std"),
+    "ast_128_b3_rank_std": dict(variant="ast", T=128, B=3, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                keep_rate_list=None, flavour="perturbed", wseed=3, xseed=7, use_custom_rank="std"),
+    "ast_256_b2_rank_mean_list": dict(variant="ast", T=256, B=2, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                      keep_rate_list=(1.0, 0.8, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0, 1.0, 1.0, 0.9, 1.0),
+                                      flavour="perturbed", wseed=3, xseed=8, use_custom_rank="mean"),
+    "audiomae_256_b1_filter_blk2": dict(variant="audiomae", T=256, B=1, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                        keep_rate_list=None, flavour="perturbed", wseed=3, xseed=9,
+                                        drop_token_blk_idx=2, retain_min=-0.05, retain_max=0.05),
+    "ast_128_b1_filter_blk0": dict(variant="ast", T=128, B=1, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                             keep_rate_list=(1.0,) * 12, flavour="perturbed", wseed=3, xseed=10,
+                                             drop_token_blk_idx=0, retain_min=-0.03, retain_max=0.2),
+    "audiomae_256_b1_filter_none_left": dict(variant="audiomae", T=256, B=1, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                             keep_rate_list=None, flavour="perturbed", wseed=3, xseed=9,
+                                             drop_token_blk_idx=1, retain_min=5.0, retain_max=6.0),
+}
+
+# Fine-tune 2-D token masking, forward half: the reference in eval mode with the global RNG seeded
+# with `mseed` right before the call; the golden file stores the two noise draws so that the mask can be rebuilt.
+MASKED_CONFIGS = {
+    "audiomae_256_b2_mask_t03_f025": dict(variant="audiomae", T=256, B=2, num_classes=35, drop_loc=(3, 6, 9),
+                                          base_keep_rate=0.7, keep_rate_list=None, flavour="perturbed", wseed=3, xseed=5,
+                                          mask_t_prob=0.3, mask_f_prob=0.25, mseed=11),
+    "audiomae_1024_b2_mask_t02_unpruned": dict(variant="audiomae", T=1024, B=2, num_classes=35, drop_loc=(), base_keep_rate=1.0,
+                                               keep_rate_list=None, flavour="perturbed", wseed=3, xseed=6,
+                                               mask_t_prob=0.2, mask_f_prob=0.0, mseed=12),
+}

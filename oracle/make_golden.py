@@ -23,7 +23,7 @@ import sys
 import torch
 
 from . import ref_loader, weights, vit_oracle as vo
-from .golden_configs import GOLDEN_CONFIGS
+from .golden_configs import ABLATION_CONFIGS, GOLDEN_CONFIGS, MASKED_CONFIGS
 
 OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -81,5 +81,78 @@ def main(names=None):
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), logits {tuple(logits.shape)}")
 
 
+def main_ablation(names=None):
+    """tests/golden/abl_<name>.pt: the reference's output on its ablation paths."""
+    assert ref_loader.reference_available(), "run in the build container (needs /root/reference)"
+    for name, cfg in ABLATION_CONFIGS.items():
+        if names and name not in names:
+            continue
+        sd, x = make_inputs(cfg)
+        model = build_reference(cfg)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+        model.use_custom_rank = cfg.get("use_custom_rank")                 # main_finetune.py:448-455 / run.py:204-211
+        if cfg.get("drop_token_blk_idx") is not None:
+            model.retain_min, model.retain_max = cfg["retain_min"], cfg["retain_max"]
+            model.drop_token_blk_idx = cfg["drop_token_blk_idx"]
+        kw = dict(use_custom_rank=cfg.get("use_custom_rank"), drop_token_blk_idx=cfg.get("drop_token_blk_idx"),
+                  retain_min=cfg.get("retain_min"), retain_max=cfg.get("retain_max"))
+        with torch.no_grad():
+            logits = model(x, keep_rate_list=cfg["keep_rate_list"])
+            o_logits, info = vo.forward_ablation(cfg["variant"], sd, x, cfg["keep_rate_list"], cfg["drop_loc"],
+                                                 cfg["base_keep_rate"], **kw)
+            d_logits, d_info = vo.forward_ablation(cfg["variant"], sd, x, cfg["keep_rate_list"], cfg["drop_loc"],
+                                                   cfg["base_keep_rate"], dtype=torch.float64, **kw)
+        assert (logits is None) == (o_logits is None), name
+        if logits is not None:
+            assert torch.equal(logits, o_logits), name            # restatement bit-identical to the reference
+        blob = {
+            "meta": dict(cfg, name=name, torch=torch.__version__, sd_digest=weights.state_dict_digest(sd),
+                         x_digest=hashlib.sha256(x.numpy().tobytes()).hexdigest()),
+            "ref": {"logits": logits},
+            "oracle_info": info,       # decisions of the fp32 restatement (the reference does not return them)
+            "f64": {"logits": d_logits, "info": d_info},
+        }
+        path = os.path.join(OUT_DIR, "abl_" + name + ".pt")
+        torch.save(blob, path)
+        print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), logits "
+              f"{None if logits is None else tuple(logits.shape)}")
+
+
+def main_masked(names=None):
+    """tests/golden/mask_<name>.pt: reference logits of forward(x, mask_t_prob, mask_f_prob) in eval mode."""
+    assert ref_loader.reference_available(), "run in the build container (needs /root/reference)"
+    for name, cfg in MASKED_CONFIGS.items():
+        if names and name not in names:
+            continue
+        sd, x = make_inputs(cfg)
+        model = build_reference(cfg)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+        B, Tp = cfg["B"], cfg["T"] // 16
+        torch.manual_seed(cfg["mseed"])
+        noise_t, noise_f = torch.rand(B, Tp), torch.rand(B, 8)               # the draws random_masking_2d will make
+        torch.manual_seed(cfg["mseed"])
+        with torch.no_grad():
+            logits = model(x, keep_rate_list=cfg["keep_rate_list"], mask_t_prob=cfg["mask_t_prob"], mask_f_prob=cfg["mask_f_prob"])
+            keep_idx = vo.masking_2d_keep_indices(noise_t, noise_f, cfg["mask_t_prob"], cfg["mask_f_prob"])
+            o_logits = vo.forward_masked(cfg["variant"], sd, x, keep_idx, cfg["keep_rate_list"], cfg["drop_loc"],
+                                         cfg["base_keep_rate"])
+        assert torch.equal(logits, o_logits), name                            # restatement bit-identical to the reference
+        blob = {"meta": dict(cfg, name=name, torch=torch.__version__, sd_digest=weights.state_dict_digest(sd),
+                             x_digest=hashlib.sha256(x.numpy().tobytes()).hexdigest()),
+                "noise_t": noise_t, "noise_f": noise_f, "keep_idx": keep_idx, "ref": {"logits": logits}}
+        path = os.path.join(OUT_DIR, "mask_" + name + ".pt")
+        torch.save(blob, path)
+        print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), kept {keep_idx.shape[1]} of {Tp * 8} patches")
+
+
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    args = sys.argv[1:]
+    if args and args[0] == "masked":
+        main_masked(args[1:])
+        sys.exit(0)
+    if args and args[0] == "ablation":
+        main_ablation(args[1:])
+    else:
+        main(args)

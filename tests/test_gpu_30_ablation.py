@@ -1,0 +1,106 @@
+"""GPU parity of the ablation paths and of the forward half of the fine-tune 2-D token masking
+(row a11) through the reference-facing model API, against golden logits produced by the REAL reference
+(tests/golden/abl_*.pt, oracle/make_golden.py ablation) and against the oracle on the same inputs.
+
+custom_rank ranks tokens by the mean / std of their 16x16 spectrogram patch: the ranking does not depend on the
+network, so the kept sets must be identical in BOTH precisions unless two patches tie to within fp32 rounding of
+the statistic (reported, not hidden); logits: fp32 2e-5, bf16 3e-2 of max|logit|.
+"""
+import pytest
+import torch
+
+import conftest  # noqa: F401
+from conftest import load_golden, make_case
+from gpu_util import dev, rel_err
+from oracle import vit_oracle as vo
+from oracle.golden_configs import ABLATION_CONFIGS, MASKED_CONFIGS
+from test_gpu_20_forward import build_model
+
+pytestmark = pytest.mark.gpu
+
+
+def configure(model, meta):
+    model.use_custom_rank = meta.get("use_custom_rank")                       # main_finetune.py:448-455 / run.py:204-211
+    if meta.get("drop_token_blk_idx") is not None:
+        model.retain_min, model.retain_max = meta["retain_min"], meta["retain_max"]
+        model.drop_token_blk_idx = meta["drop_token_blk_idx"]
+    return model
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(ABLATION_CONFIGS))
+def test_ablation_paths_match_reference_golden(name, precision):
+    g = load_golden("abl_" + name)
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    model = configure(build_model(meta, sd, precision), meta)
+    with torch.no_grad():
+        logits = model(x.to(dev()), keep_rate_list=meta["keep_rate_list"])
+    ref = g["ref"]["logits"]
+    if ref is None:
+        assert logits is None                                                 # nothing retained
+        return
+    assert logits is not None and tuple(logits.shape) == tuple(ref.shape)
+    # kept sets of every pruning block against the oracle's decisions (same inputs)
+    exp = g["oracle_info"]["topk_idx"]
+    got = model.last_topk_idx
+    assert sorted(got) == sorted(exp)
+    rank_mode = meta.get("use_custom_rank") is not None
+    for blk in sorted(exp):
+        a, b = got[blk].cpu(), exp[blk]
+        assert tuple(a.shape) == tuple(b.shape)
+        if rank_mode or precision == "fp32":
+            for c in range(b.shape[0]):
+                assert set(a[c].tolist()) == set(b[c].tolist()), f"{name} block {blk} clip {c}"
+    err = rel_err(logits.cpu(), ref)
+    print(f"[ablation {precision}] {name}: logits err {err:.2e}")
+    assert err < (2e-5 if precision == "fp32" else 3e-2)
+
+
+def test_patch_stats_and_rank_gather_kernels():
+    from tpat import ops, _lib
+    torch.manual_seed(0)
+    B, T, F = 3, 256, 128
+    spec = (torch.randn(B, T, F) * 0.5)
+    for order, view in ((_lib.TOKENS_TIME_MAJOR, spec.unsqueeze(1)), (_lib.TOKENS_FREQ_MAJOR, spec.unsqueeze(1).transpose(2, 3))):
+        mean, std = ops.patch_stats(spec.to(dev()), order, want_mean=True, want_std=True)
+        assert torch.allclose(mean.cpu(), vo.patch_statistic(view, "mean"), rtol=0, atol=1e-7)
+        assert torch.allclose(std.cpu(), vo.patch_statistic(view, "std"), rtol=1e-6, atol=1e-7)
+    rank = torch.randn(B, 128)
+    idx = torch.stack([torch.randperm(128)[:40] for _ in range(B)])
+    out = ops.gather_rank(rank.to(dev()), idx.to(dev()))
+    assert torch.equal(out.cpu(), torch.gather(rank, 1, idx))
+
+
+def test_intensity_filter_after_pruning_raises_like_the_reference():
+    """The filter indexes the ORIGINAL patch grid (models_vit.py:380-382): applied after a pruning block it runs
+    out of bounds in the reference (IndexError); same error here instead of a silent wrong gather."""
+    meta = dict(ABLATION_CONFIGS["audiomae_256_b1_filter_blk2"], drop_token_blk_idx=4, retain_min=-10.0, retain_max=10.0)
+    from oracle import weights
+    sd = weights.make_audiomae_state_dict(meta["num_classes"], meta["T"], meta["wseed"], meta["flavour"])
+    x = weights.make_spectrogram("audiomae", 1, meta["T"], meta["xseed"])
+    model = configure(build_model(meta, sd, "fp32"), meta)
+    with pytest.raises(IndexError):
+        model(x.to(dev()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(MASKED_CONFIGS))
+def test_masked_forward_matches_reference_golden(name, precision):
+    """mask_t_prob / mask_f_prob > 0 (models_vit.py:425-497,509-512), forward half: with the noise the reference drew
+    the surviving tokens must be the same list and the logits must match the reference's."""
+    g = load_golden("mask_" + name)
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    model = build_model(meta, sd, precision)
+    B = meta["B"]
+    keep_idx = model.random_masking_2d_indices(B, dev(), meta["mask_t_prob"], meta["mask_f_prob"],
+                                               noise=(g["noise_t"], g["noise_f"]))
+    assert torch.equal(keep_idx.cpu(), g["keep_idx"])
+    model.random_masking_2d_indices = lambda B, d, pt, pf, noise=None: keep_idx
+    with torch.no_grad():
+        got = model(x.to(dev()), keep_rate_list=meta["keep_rate_list"], mask_t_prob=meta["mask_t_prob"],
+                    mask_f_prob=meta["mask_f_prob"])
+    err = rel_err(got.cpu(), g["ref"]["logits"])
+    print(f"[masked {precision}] {name}: logits err {err:.2e}")
+    assert err < (2e-5 if precision == "fp32" else 3e-2)

@@ -54,11 +54,32 @@ def test_errors_match_reference_behaviour():
         m(torch.zeros(1, 1, 128, 128))
     with pytest.raises(AssertionError):                  # models_vit.py:336: T >= F and F == 128
         m(torch.zeros(1, 1, 64, 128))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):                    # masked / ablation paths have no CPU path either
         m(torch.zeros(1, 1, 128, 128), mask_t_prob=0.3)
+    m.use_custom_rank = "median"
+    with pytest.raises((ValueError, RuntimeError)):      # unknown statistic (ast_models.py:453) / no CPU path
+        m(torch.zeros(1, 1, 128, 128))
+    m.use_custom_rank = None
     from tpat import models_vit
     with pytest.raises(AssertionError):                  # models_vit.py:66
         models_vit.Attention(768, 12, default_keep_rate=0.0)
+
+
+def test_masking_indices_follow_reference_construction():
+    """random_masking_2d (models_vit.py:425-463) restated as an index list: compare with the reference's gathers on
+    a token-id grid, same noise."""
+    m = build_audiomae(T=256, C=10)
+    gen = torch.Generator().manual_seed(11)
+    noise = (torch.rand(2, 16, generator=gen), torch.rand(2, 8, generator=gen))
+    keep_idx = m.random_masking_2d_indices(2, torch.device("cpu"), 0.3, 0.25, noise=noise)
+    assert tuple(keep_idx.shape) == (2, int(16 * 0.7) * int(8 * 0.75))
+    tok = torch.arange(128).reshape(1, 16, 8).expand(2, -1, -1)
+    ids_t = torch.argsort(noise[0], dim=1)[:, :11]
+    ids_f = torch.argsort(noise[1], dim=1)[:, :6]
+    t1 = torch.gather(tok, 1, ids_t[:, :, None].expand(-1, -1, 8)).permute(0, 2, 1)           # N F T'
+    t2 = torch.gather(t1, 1, ids_f[:, :, None].expand(-1, -1, 11)).permute(0, 2, 1).reshape(2, -1)
+    assert torch.equal(keep_idx, t2)
+    assert torch.equal(keep_idx, vo.masking_2d_keep_indices(noise[0], noise[1], 0.3, 0.25))
 
 
 def test_precision_selection():

@@ -5,7 +5,7 @@ import torch
 
 from conftest import load_golden, make_case
 from oracle import vit_oracle as vo
-from oracle.golden_configs import GOLDEN_CONFIGS
+from oracle.golden_configs import ABLATION_CONFIGS, GOLDEN_CONFIGS, MASKED_CONFIGS
 
 
 @pytest.mark.parametrize("name", list(GOLDEN_CONFIGS))
@@ -35,6 +35,54 @@ def test_oracle_matches_reference_golden(name):
     # non-extract mode reports only the pruning blocks
     assert sorted(feats_plain) == sorted(k for k in keys if k.split(".")[0] in
                                          {kk.split(".")[0] for kk in keys if kk.endswith("topk_idx")})
+
+
+def ablation_kwargs(meta):
+    return dict(use_custom_rank=meta.get("use_custom_rank"), drop_token_blk_idx=meta.get("drop_token_blk_idx"),
+                retain_min=meta.get("retain_min"), retain_max=meta.get("retain_max"))
+
+
+@pytest.mark.parametrize("name", list(ABLATION_CONFIGS))
+def test_oracle_ablation_paths_match_reference_golden(name):
+    """custom_rank mean/std and the drop_token_blk_idx intensity filter against the logits the
+    real reference produced (models_vit.py:343-385, ast_models.py:445-497)."""
+    g = load_golden("abl_" + name)
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    with torch.no_grad():
+        logits, info = vo.forward_ablation(meta["variant"], sd, x, meta["keep_rate_list"], meta["drop_loc"],
+                                           meta["base_keep_rate"], **ablation_kwargs(meta))
+    ref = g["ref"]["logits"]
+    if ref is None:
+        assert logits is None                       # nothing retained -> the reference returns None
+        return
+    assert torch.allclose(logits, ref, rtol=0, atol=2e-6)
+    for blk, idx in g["oracle_info"]["topk_idx"].items():
+        for a, b in zip(info["topk_idx"][blk].tolist(), idx.tolist()):
+            assert set(a) == set(b), blk
+    if g["oracle_info"]["retain_idx"] is not None:
+        assert torch.equal(info["retain_idx"], g["oracle_info"]["retain_idx"])
+
+
+@pytest.mark.parametrize("name", list(MASKED_CONFIGS))
+def test_oracle_masked_forward_matches_reference_golden(name):
+    """Forward half of the fine-tune 2-D masking (models_vit.py:425-497) against the reference."""
+    g = load_golden("mask_" + name)
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    keep_idx = vo.masking_2d_keep_indices(g["noise_t"], g["noise_f"], meta["mask_t_prob"], meta["mask_f_prob"])
+    assert torch.equal(keep_idx, g["keep_idx"])
+    with torch.no_grad():
+        logits = vo.forward_masked(meta["variant"], sd, x, keep_idx, meta["keep_rate_list"], meta["drop_loc"],
+                                   meta["base_keep_rate"])
+    assert torch.allclose(logits, g["ref"]["logits"], rtol=0, atol=2e-6)
+
+
+def test_oracle_custom_rank_keeps_exactly_k_tokens():
+    """The reference's custom-rank gather indexes the full token list, so a pruning block hands on k tokens (no
+    separately kept cls row): 1 + 128 -> 90 -> 63 -> 44 at 256 frames, keep 0.7."""
+    g = load_golden("abl_audiomae_256_b2_rank_mean")
+    assert [g["oracle_info"]["topk_idx"][b].shape[1] for b in (3, 6, 9)] == [90, 63, 44]
 
 
 def test_fp64_oracle_agrees_with_fp32_reference_sets():

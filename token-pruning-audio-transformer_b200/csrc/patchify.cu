@@ -53,7 +53,86 @@ patchify_kernel(const float* __restrict__ spec, OutT* __restrict__ patches, floa
   }
 }
 
+// ---- ablation ranking vectors ----
+// One CTA per (16-frame block, clip): the 16 x F tile goes through shared memory, each warp then reduces whole
+// patches (lane = 8 of the 256 samples).  Sums in double: the result is the correctly rounded fp32 statistic up to
+// the final rounding (torch reduces in fp32 / Welford; both sit within 1-2 ulp of the exact value).
+__global__ void __launch_bounds__(256)
+patch_stats_kernel(const float* __restrict__ spec, float* __restrict__ mean_out, float* __restrict__ std_out,
+                   int T, int F, int order) {
+  extern __shared__ float tile[];  // [16][F+1]
+  const int tb = blockIdx.x, b = blockIdx.y;
+  const int TB = T / 16, FB = F / 16, P = TB * FB;
+  const int ld = F + 1;
+  const float* src = spec + ((size_t)b * T + (size_t)tb * 16) * F;
+  for (int v = threadIdx.x; v < 16 * F / 4; v += blockDim.x) {
+    const int r = (v * 4) / F, c = (v * 4) % F;
+    const float4 val = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * F + c));
+    float* d = tile + r * ld + c;
+    d[0] = val.x; d[1] = val.y; d[2] = val.z; d[3] = val.w;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int fb = warp; fb < FB; fb += blockDim.x >> 5) {
+    float v[8];
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = lane * 8 + i;                       // sample e of the patch: frame e / 16, bin e % 16
+      v[i] = tile[(e >> 4) * ld + fb * 16 + (e & 15)];
+      s += (double)v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double mu = s / 256.0;
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const double d = (double)v[i] - mu; q += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) {
+      const size_t tok = (size_t)b * P + (order == TPAT_TOKENS_TIME_MAJOR ? (size_t)tb * FB + fb : (size_t)fb * TB + tb);
+      if (mean_out) mean_out[tok] = (float)mu;
+      if (std_out) std_out[tok] = (float)sqrt(q / 255.0);
+    }
+  }
+}
+
+__global__ void gather_rank_kernel(const float* __restrict__ rank, const int64_t* __restrict__ idx, float* __restrict__ out,
+                                   int n, int k, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / k;
+  out[i] = __ldg(rank + (size_t)b * n + (int)__ldg(idx + i));
+}
+
 }  // namespace tpat
+
+extern "C" int tpat_patch_stats(const float* spec, float* mean, float* std, int B, int T, int F, int order,
+                                tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(spec && (mean || std), "tpat_patch_stats: null pointer");
+  TPAT_CHECK(B > 0 && T > 0 && F > 0 && T % 16 == 0 && F % 16 == 0 && F <= 512,
+             "tpat_patch_stats: need T %% 16 == 0, F %% 16 == 0, F <= 512 (got B=%d T=%d F=%d)", B, T, F);
+  TPAT_CHECK(order == TPAT_TOKENS_TIME_MAJOR || order == TPAT_TOKENS_FREQ_MAJOR, "tpat_patch_stats: bad order %d", order);
+  TPAT_CHECK(aligned16(spec), "tpat_patch_stats: spec must be 16-byte aligned");
+  const size_t smem = (size_t)16 * (F + 1) * sizeof(float);
+  TPAT_CUDA(launch_kernel(patch_stats_kernel, dim3(T / 16, B), dim3(256), smem, as_stream(stream), spec, mean, std, T, F, order));
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tpat_gather_rank(const float* rank, const int64_t* idx, float* out, int B, int n, int k,
+                                tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(rank && idx && out, "tpat_gather_rank: null pointer");
+  TPAT_CHECK(B >= 0 && n > 0 && k > 0 && k <= n, "tpat_gather_rank: bad sizes n=%d k=%d", n, k);
+  if (B == 0) return 0;
+  const int total = B * k;
+  TPAT_CUDA(launch_kernel(gather_rank_kernel, dim3((total + 255) / 256), dim3(256), 0, as_stream(stream), rank, idx, out, n, k, total));
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int tpat_patchify(const float* spec, void* patches, int out_dtype, float* tokens,
                              const float* extra_tok, const float* pos, int B, int T, int F, int D,

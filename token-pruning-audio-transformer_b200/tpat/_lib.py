@@ -64,6 +64,8 @@ SIGNATURES = {
     "tpat_pool_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int,
                                c_int, c_int, c_int, c_void_p]),
     "tpat_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tpat_patch_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_gather_rank": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tpat_sizeof_forward_args": (c_size_t, []),
     "tpat_forward_workspace_bytes": (c_size_t, [POINTER(ForwardArgs)]),
     "tpat_forward": (c_int, [POINTER(ForwardArgs), c_void_p]),

@@ -16,7 +16,7 @@ Stated differences: the reference needs ``timm==0.4.5`` for the DeiT skeleton an
 skeleton is built locally and ``imagenet_pretrain=True`` raises -- load a checkpoint with
 ``load_state_dict`` instead.  ``@autocast`` (ast_models.py:424) is replaced by the explicit
 ``precision`` attribute ("bf16" tensor-core kernels / "fp32" parity kernels).  Inference only in
-this round; custom_rank / drop_token_blk_idx raise NotImplementedError.
+this round; the custom_rank / drop_token_blk_idx ablation paths run kernel by kernel (ForwardEngine.run_stepwise).
 """
 import os
 from functools import partial
@@ -191,14 +191,24 @@ class ASTModel(nn.Module):
         """x [B, time_frame_num, frequency_bins], e.g. (12, 1024, 128) (ast_models.py:431)."""
         if (keep_rate_list is not None) and (len(keep_rate_list) != len(self.v.blocks)):
             raise ValueError(f"keep_rate should be a list/tuple of length {len(self.v.blocks)}, got {keep_rate_list}")
-        if self.use_custom_rank is not None or self.drop_token_blk_idx is not None:
-            raise NotImplementedError("custom_rank / drop_token_blk_idx ablation paths are not built yet (SURVEY a12)")
         B, T, F = x.shape
         n_patches = (T // 16) * (F // 16)
         if self.v.pos_embed.shape[1] != n_patches + 2:
             raise RuntimeError(f"pos_embed has {self.v.pos_embed.shape[1]} rows but the input has {n_patches} patches + 2")
         rates = resolve_keep_rates(keep_rate_list, self.v.blocks)
         self._engine.pack(self._engine_tensors, self._pack_key())
+        if self.use_custom_rank is not None or self.drop_token_blk_idx is not None:
+            # ablation paths (ast_models.py:445-457,480-497): kernel-by-kernel forward
+            if self.use_custom_rank is not None:
+                assert flag_extract_features == False                         # ast_models.py:446
+            if flag_extract_features:
+                raise NotImplementedError("extract mode together with drop_token_blk_idx is not supported")
+            logits, info = self._engine.run_stepwise(x, rates, self.label_dim, precision=self.precision,
+                                                     use_custom_rank=self.use_custom_rank,
+                                                     drop_token_blk_idx=self.drop_token_blk_idx,
+                                                     retain_min=self.retain_min, retain_max=self.retain_max)
+            self.last_scores, self.last_topk_idx = None, info["topk_idx"]
+            return logits                                                     # None when no token is retained (:495-497)
         logits, scores, idxs = self._engine.run(x, rates, self.label_dim, want_all_scores=flag_extract_features,
                                                 precision=self.precision, use_graph=self.use_cuda_graph, fuse_token=self.fuse_token)
         self.last_scores, self.last_topk_idx = scores, idxs

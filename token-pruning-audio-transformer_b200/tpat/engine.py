@@ -215,3 +215,98 @@ class ForwardEngine:
         g.replay()
         return (logits.clone(), [None if s is None else s.clone() for s in scores],
                 [None if t is None else t.clone() for t in idxs])
+
+    # ---- kernel-by-kernel forward: ablation and masking paths -------------------------------
+    def run_stepwise(self, spec: torch.Tensor, keep_rates: Sequence[float], num_classes: int, precision: str = "bf16",
+                     use_custom_rank: Optional[str] = None, drop_token_blk_idx: Optional[int] = None,
+                     retain_min: Optional[float] = None, retain_max: Optional[float] = None,
+                     mask_keep_idx: Optional[torch.Tensor] = None):
+        """The forward assembled from the per-kernel entry points, for the paths whose token flow the fused
+        ``tpat_forward`` does not cover:
+
+        * ``use_custom_rank`` 'mean' | 'std': rank tokens by a statistic of their spectrogram patch; the gather takes
+          its indices over the FULL token list and keeps exactly k tokens, as the reference's
+          ``forward_with_custom_rank`` does (models_vit.py:209-224,343-351,371-374; ast_models.py:221-236,445-453).
+        * ``drop_token_blk_idx``: batch of one; after that block keep the patches whose mean intensity lies in
+          (retain_min, retain_max); returns ``None`` when none is left (models_vit.py:353-355,378-385).
+        * ``mask_keep_idx`` [B, n_keep] int64: patch tokens that survive the fine-tune 2-D masking, applied right
+          after the patch embedding (models_vit.py:425-497).
+
+        Same kernels as ``run`` (every op in libtpat.so); only the sequencing lives here.  Returns
+        (logits or None, {'topk_idx': {block: idx}, 'retain_idx': idx or None})."""
+        from . import ops
+        if not spec.is_cuda:
+            raise RuntimeError("tpat: input must be a CUDA tensor; there is no CPU path")
+        if not lib.tpat_device_ok():
+            raise RuntimeError("tpat: the current device is not compute capability 10.x (B200, sm_100a)")
+        if use_custom_rank not in (None, "mean", "std"):
+            raise ValueError(f"custom_rank should be in ['mean', 'std'], got {use_custom_rank}")
+        if spec.dtype != torch.float32 or not spec.is_contiguous():
+            spec = spec.float().contiguous()
+        impl = _lib.IMPL_TC if precision == "bf16" else _lib.IMPL_SIMT
+        act = torch.bfloat16 if impl == _lib.IMPL_TC else torch.float32
+        pk, extra, D, H = self._packed, self.num_extra, self.D, self.H
+        ast = self.variant == _lib.VARIANT_AST
+        order = _lib.TOKENS_FREQ_MAJOR if ast else _lib.TOKENS_TIME_MAJOR
+        B, T, F = spec.shape
+        P = (T // 16) * (F // 16)
+        info = {"topk_idx": {}, "retain_idx": None}
+
+        rank = None
+        if use_custom_rank is not None:
+            mean, std = ops.patch_stats(spec, order, want_mean=use_custom_rank == "mean", want_std=use_custom_rank == "std")
+            rank = mean if use_custom_rank == "mean" else std
+        intensity = ops.patch_stats(spec, order)[0] if drop_token_blk_idx is not None else None
+
+        x = torch.empty(B, extra + P, D, device=spec.device, dtype=torch.float32)
+        patches = ops.patchify(spec, act, order, tokens=x, extra_tok=pk["extra_tok"], pos=pk["pos"])
+        ops.gemm(patches, self._mat(pk["patch_w"], impl), pk["patch_b"], torch.float32, _lib.EPI_BIAS_POS, impl,
+                 out=x.view(-1, D), pos=pk["pos"], P=P, num_extra=extra)
+        if mask_keep_idx is not None:
+            x, _ = ops.gather_layernorm(x, mask_keep_idx.contiguous(), extra, None, None, 1e-6, act)
+
+        for i, blk in enumerate(pk["blocks"]):
+            N = x.shape[1]
+            kr = keep_rates[i]
+            k = math.ceil(kr * (N - extra))
+            assert k > 0                                                         # models_vit.py:106
+            prune = kr < 1.0
+            y = ops.layernorm(x, blk["ln1_g"], blk["ln1_b"], 1e-6, act)
+            qkv = ops.gemm(y.view(-1, D), self._mat(blk["qkv_w"], impl), blk["qkv_b"], act, _lib.EPI_BIAS, impl)
+            smode = _lib.SCORE_NONE
+            if prune and rank is None:
+                smode = _lib.SCORE_CLS_ROW if ast else _lib.SCORE_COLMEAN
+            ao, partial = ops.attention(qkv, B, N, H, extra, smode, impl)
+            x2 = x.view(-1, D)
+            ops.gemm(ao, self._mat(blk["proj_w"], impl), blk["proj_b"], torch.float32, _lib.EPI_BIAS_RESIDUAL, impl,
+                     residual=x2, out=x2)
+            if prune and rank is not None:
+                _, idx = ops.score_topk(rank.view(B, 1, -1), 1.0, 0, k)          # torch.topk(custom_rank, k)
+                x, y2 = ops.gather_layernorm(x, idx, 0, blk["ln2_g"], blk["ln2_b"], 1e-6, act)   # full token list
+                rank = ops.gather_rank(rank, idx)
+                info["topk_idx"][i] = idx
+            elif prune:
+                divisor = float(H) if ast else float(H) * float(N - extra)
+                _, idx = ops.score_topk(partial, divisor, extra, k)
+                x, y2 = ops.gather_layernorm(x, idx, extra, blk["ln2_g"], blk["ln2_b"], 1e-6, act)
+                info["topk_idx"][i] = idx
+            else:
+                y2 = ops.layernorm(x, blk["ln2_g"], blk["ln2_b"], 1e-6, act)
+            hdn = ops.gemm(y2.view(-1, D), self._mat(blk["fc1_w"], impl), blk["fc1_b"], act, _lib.EPI_BIAS_GELU, impl)
+            x2 = x.view(-1, D)
+            ops.gemm(hdn, self._mat(blk["fc2_w"], impl), blk["fc2_b"], torch.float32, _lib.EPI_BIAS_RESIDUAL, impl,
+                     residual=x2, out=x2)
+            if drop_token_blk_idx == i:
+                assert B == 1                                                    # models_vit.py:379
+                m = intensity[0].cpu()                                           # host decision: data-dependent token count
+                retain = torch.nonzero((m > retain_min) & (m < retain_max))[:, 0]
+                if retain.numel() == 0:
+                    return None, info
+                if int(retain.max()) + extra >= x.shape[1]:
+                    raise IndexError(f"index {int(retain.max()) + extra} is out of bounds for dimension 1 with size "
+                                     f"{x.shape[1]} (the intensity filter indexes the original patch grid)")
+                info["retain_idx"] = retain
+                x, _ = ops.gather_layernorm(x, retain.to(x.device).view(1, -1).contiguous(), extra, None, None, 1e-6, act)
+
+        pooled = ops.pool_norm(x, self.variant, pk["norm_g"], pk["norm_b"], 1e-6, pk["head_ln_g"], pk["head_ln_b"], 1e-5)
+        return ops.head(pooled, pk["head_w"], pk["head_b"]), info

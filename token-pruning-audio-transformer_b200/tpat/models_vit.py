@@ -18,8 +18,9 @@ parameters to ``engine.ForwardEngine`` which makes one ``tpat_forward`` call int
 
 Differences from the reference, stated (not hidden):
   * forward is inference-only in this round (no autograd graph); DropPath is therefore identity,
-    as in the reference's eval mode.  Token masking (mask_t_prob / mask_f_prob > 0), custom_rank
-    and drop_token_blk_idx raise NotImplementedError.
+    as in the reference's eval mode.  The ablation paths (custom_rank, drop_token_blk_idx) and
+    the forward half of the fine-tune 2-D token masking (mask_t_prob / mask_f_prob > 0; row a11) run kernel by
+    kernel through ``ForwardEngine.run_stepwise``; there is no backward pass.
   * torch.topk leaves the order of exactly tied scores unspecified; here ties go to the lower index.
   * extra constructor keyword ``fuse_token`` (default False): EViT's fused inattentive token, which BASELINE.json
     configs[2] names but the reference forward never implemented -- semantics from upstream EViT.
@@ -218,10 +219,22 @@ class VisionTransformer(nn.Module):
         if tuple(self.patch_embed.proj.weight.shape[1:]) != (1, 16, 16):
             raise NotImplementedError("libtpat expects the 1-channel 16x16 patch projection "
                                       "(replace model.patch_embed as main_finetune.py:378 does)")
-        if self.use_custom_rank is not None or self.drop_token_blk_idx is not None:
-            raise NotImplementedError("custom_rank / drop_token_blk_idx ablation paths are not built yet (SURVEY a12)")
         if not isinstance(self.head, nn.Linear):
             raise NotImplementedError("num_classes == 0 (Identity head) is not supported")
+
+    def random_masking_2d_indices(self, B, device, mask_t_prob, mask_f_prob, noise=None):
+        """Patch-token indices [B, T'*F'] kept by ``random_masking_2d`` (models_vit.py:425-463): per clip, the
+        ``int(T*(1-mask_t_prob))`` time columns and ``int(F*(1-mask_f_prob))`` frequency rows with the smallest
+        noise, in argsort order; kept token (t', f') is original token ids_t[t'] * F + ids_f[f'].  The two
+        ``torch.rand`` calls are made in the reference's order on the input's device, so a seeded generator gives
+        the reference's masks.  ``noise`` = (noise_t [B,T], noise_f [B,F]) overrides the draw (tests)."""
+        T, F = self.target_length // 16, 8                                    # models_vit.py:436-437
+        len_keep_T, len_keep_F = int(T * (1 - mask_t_prob)), int(F * (1 - mask_f_prob))
+        noise_t = torch.rand(B, T, device=device) if noise is None else noise[0].to(device)
+        ids_t = torch.argsort(noise_t, dim=1)[:, :len_keep_T]
+        noise_f = torch.rand(B, F, device=device) if noise is None else noise[1].to(device)
+        ids_f = torch.argsort(noise_f, dim=1)[:, :len_keep_F]
+        return (ids_t[:, :, None] * F + ids_f[:, None, :]).reshape(B, len_keep_T * len_keep_F).contiguous()
 
     def forward_features(self, x, keep_rate_list=None, flag_extract_features: bool = False):
         """Kept for API parity; returns what forward returns before the head is NOT available
@@ -232,18 +245,38 @@ class VisionTransformer(nn.Module):
                 flag_extract_features: bool = False):
         if (keep_rate_list is not None) and (len(keep_rate_list) != len(self.blocks)):
             raise ValueError(f"keep_rate should be a list/tuple of length {len(self.blocks)}, got {keep_rate_list}")
-        if mask_t_prob > 0.0 or mask_f_prob > 0.0:
-            assert flag_extract_features == False
-            raise NotImplementedError("2-D token masking (fine-tune only, SURVEY a11) is not built yet")
         self._check_supported(x)
         B, _, T, F = x.shape
-        assert T >= F and F == 128                                            # models_vit.py:336
+        masking = mask_t_prob > 0.0 or mask_f_prob > 0.0
+        if masking:
+            assert flag_extract_features == False                             # models_vit.py:510
+        else:
+            assert T >= F and F == 128                                        # models_vit.py:336
         n_patches = (T // 16) * (F // 16)
         if self.pos_embed.shape[1] != n_patches + 1:
             raise RuntimeError(f"pos_embed has {self.pos_embed.shape[1]} rows but the input has {n_patches} patches + cls")
         rates = resolve_keep_rates(keep_rate_list, self.blocks)
         self._engine.pack(self._engine_tensors, self._pack_key())
         spec = x.reshape(B, T, F)
+        if masking:
+            # fine-tune 2-D token masking (forward only; no autograd through libtpat yet): models_vit.py:425-497,509-512
+            keep_idx = self.random_masking_2d_indices(B, x.device, mask_t_prob, mask_f_prob)
+            logits, info = self._engine.run_stepwise(spec, rates, self.num_classes, precision=self.precision,
+                                                     mask_keep_idx=keep_idx)
+            self.last_scores, self.last_topk_idx = None, info["topk_idx"]
+            return logits
+        if self.use_custom_rank is not None or self.drop_token_blk_idx is not None:
+            # ablation paths (models_vit.py:343-355,371-385): kernel-by-kernel forward
+            if self.use_custom_rank is not None:
+                assert flag_extract_features == False                         # models_vit.py:344
+            if flag_extract_features:
+                raise NotImplementedError("extract mode together with drop_token_blk_idx is not supported")
+            logits, info = self._engine.run_stepwise(spec, rates, self.num_classes, precision=self.precision,
+                                                     use_custom_rank=self.use_custom_rank,
+                                                     drop_token_blk_idx=self.drop_token_blk_idx,
+                                                     retain_min=self.retain_min, retain_max=self.retain_max)
+            self.last_scores, self.last_topk_idx = None, info["topk_idx"]
+            return logits                                                     # None when no token is retained (:384-385)
         logits, scores, idxs = self._engine.run(spec, rates, self.num_classes, want_all_scores=flag_extract_features,
                                                 precision=self.precision, use_graph=self.use_cuda_graph, fuse_token=self.fuse_token)
         self.last_scores, self.last_topk_idx = scores, idxs

@@ -47,6 +47,27 @@ def patchify(spec: torch.Tensor, out_dtype: torch.dtype, order: int, tokens: Opt
     return patches
 
 
+def patch_stats(spec: torch.Tensor, order: int, want_mean: bool = True, want_std: bool = False):
+    """spec [B,T,F] fp32 -> (mean [B,P] or None, std [B,P] or None): per-patch statistics in token order."""
+    _req(spec, torch.float32, "spec")
+    B, T, F = spec.shape
+    P = (T // 16) * (F // 16)
+    mean = torch.empty(B, P, device=spec.device, dtype=torch.float32) if want_mean else None
+    std = torch.empty(B, P, device=spec.device, dtype=torch.float32) if want_std else None
+    check(lib.tpat_patch_stats(spec.data_ptr(), _ptr(mean), _ptr(std), B, T, F, order, _stream()), "tpat_patch_stats")
+    return mean, std
+
+
+def gather_rank(rank: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """rank [B,n] fp32, idx [B,k] int64 -> rank gathered along dim 1."""
+    _req(rank, torch.float32, "rank"); _req(idx, torch.int64, "idx")
+    B, n = rank.shape
+    k = idx.shape[1]
+    out = torch.empty(B, k, device=rank.device, dtype=torch.float32)
+    check(lib.tpat_gather_rank(rank.data_ptr(), idx.data_ptr(), out.data_ptr(), B, n, k, _stream()), "tpat_gather_rank")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype) -> torch.Tensor:
     _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
     D = x.shape[-1]
