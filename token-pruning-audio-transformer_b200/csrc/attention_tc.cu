@@ -36,16 +36,14 @@ int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld,
 constexpr int AT_BM = 128;          // queries per CTA
 constexpr int AT_BK = 64;           // keys per block
 constexpr int AT_HD = 64;
-#ifndef AT_CTAS_PER_SM
-#define AT_CTAS_PER_SM 2            // resident CTAs per SM (2: two S buffers, 6 ring slots; 3: one S buffer, 3 ring slots)
-#endif
-constexpr int AT_SBUF = AT_CTAS_PER_SM >= 3 ? 1 : 2;      // S accumulators in TMEM
-constexpr int AT_SLOTS = AT_CTAS_PER_SM >= 3 ? 3 : 6;     // K/V ring slots
-constexpr int AT_Q_BYTES = AT_BM * AT_HD * 2;    // 16 KB (also one P buffer / the O staging tile)
+#define AT_CTAS_PER_SM 2            // resident CTAs per SM (256 of the 512 TMEM columns each)
+constexpr int AT_SBUF = 2;          // S accumulators in TMEM
+constexpr int AT_SLOTS = 6;         // K/V ring slots
+constexpr int AT_Q_BYTES = AT_BM * AT_HD * 2;    // 16 KB (also the O staging tile of the epilogue)
 constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;   // 8 KB
-constexpr int AT_P_BYTES = AT_BM * AT_BK * 2;    // 16 KB
+constexpr int AT_P_COLS = AT_BK / 2;             // one P buffer in TMEM: 64 bf16 keys = 32 columns of 32 bits
 constexpr int AT_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps
-constexpr int AT_TMEM_COLS = AT_SBUF == 1 ? 128 : 256;   // S buffers [0, 64*SBUF), then O (64 columns)
+constexpr int AT_TMEM_COLS = 256;   // S0, S1 [0, 128), O [128, 192), P0, P1 (bf16 pairs) [192, 256)
 constexpr int AT_SMEM_LIMIT = 227 * 1024;   // hard cap; <= 113 KB keeps two CTAs per SM (N <= 960 with the column-sum buffer)
 constexpr float AT_RESCALE_LOG2 = 64.0f;  // online softmax: the reference max is only raised past 2^64 (then the tile is redone)
 #ifndef AT_POLY_EVERY
@@ -100,8 +98,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   // address space (a round trip through uintptr_t turns every staging access into a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* q_s = smem;                                   // 16 KB
-  uint8_t* p_s = q_s + AT_Q_BYTES;                       // 2 x 16 KB
-  uint8_t* kv_s = p_s + 2 * AT_P_BYTES;                  // AT_SLOTS x 8 KB
+  uint8_t* kv_s = q_s + AT_Q_BYTES;                      // AT_SLOTS x 8 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(kv_s + AT_SLOTS * AT_KV_BYTES);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* kv_full = bars + 1;            // [SLOTS]
@@ -147,6 +144,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + AT_SBUF * AT_BK;
+  const uint32_t tmem_p = tmem_o + AT_HD;
   pdl_wait();   // everything above touched only on-chip state; global memory from here on
 
   const int col_q = h * AT_HD, col_k = (p.H + h) * AT_HD, col_v = (2 * p.H + h) * AT_HD;
@@ -204,15 +202,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::mbar_wait(&kv_full[slot], phase);           // V_j
         ptx::mbar_wait(&p_full[pb], (j >> 1) & 1);       // P_j written by the softmax warps
         ptx::tc_fence_after();
-        const uint32_t p_addr = ptx::smem_u32(p_s + pb * AT_P_BYTES);
         const uint32_t v_addr = ptx::smem_u32(kv_s + slot * AT_KV_BYTES);
         const int valid = min(AT_BK, p.N - j * AT_BK);   // keys of this block that exist
         const int ksteps = (valid + 15) >> 4;            // P is zero beyond `valid`, V rows beyond N are zero-filled
         for (int k = 0; k < ksteps; ++k) {
-          // A: 16 keys = 32 B inside the 64-key swizzle atom;  B (MN-major): 16 keys = two 8-row groups of 1024 B
-          const uint64_t a_desc = ptx::smem_desc_sw128(p_addr + k * 32, 16, 1024);
+          // A: P from TMEM, 16 keys = 8 columns;  B (MN-major): 16 keys = two 8-row groups of 1024 B
           const uint64_t b_desc = ptx::smem_desc_sw128(v_addr + k * 2048, 16, 1024);
-          ptx::mma_f16_ss(tmem_o, a_desc, b_desc, idesc_o, (j | k) != 0);
+          ptx::mma_f16_ts(tmem_o, tmem_p + pb * AT_P_COLS + k * 8, b_desc, idesc_o, (j | k) != 0);
         }
         ptx::tc_commit(&kv_empty[slot]);
         ptx::tc_commit(&p_empty[pb]);
@@ -326,9 +322,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (!warp_live) {
         if (TWO_PASS && p.score_mode == TPAT_SCORE_COLMEAN)     // this warp's rows contribute nothing to the column sums
           colsum_w[j * AT_BK + half * 32 + lane] = 0.f;
-        release_s(sb);
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
+        release_s(sb);                                   // (fence::before_thread_sync + __syncwarp inside)
         if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
         continue;
       }
@@ -353,15 +347,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       ATTN_TRACE(5);
       // P buffer pb was last read by PV(j-2), which the MMA thread issued BEFORE S(j); tcgen05 operations retire
       // in issue order and s_full(j) is a commit of everything issued before it, so the buffer is already free.
-      uint8_t* p_row = p_s + pb * AT_P_BYTES + r_local * 128;
+      const uint32_t p_tm = tmem_p + lane_off + pb * AT_P_COLS + half * 16;   // this thread's 32 keys = 16 columns
       const float l2a_in = l2a, l2b_in = l2b, l2c_in = l2c, l2d_in = l2d;
       auto emit_half = [&]() {
         const int col0 = j * AT_BK + half * 32;
         if (vh <= 0) {
           if (half * 32 < ((valid + 15) & ~15)) {        // still inside the MMA's K range: zero it
+            uint32_t z[16];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4*>(p_row + (((half * 4 + g) ^ (r_local & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < 16; ++i) z[i] = 0u;
+            ptx::tmem_st_32x32b_x16(p_tm, z);
           }
           return;
         }
@@ -375,7 +370,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
         }
-        store_p_half(p_row, half, r_local, v);
+        {
+          uint32_t pk[16];                               // bf16 pairs: the K-major A operand of P.V, straight into TMEM
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          ptx::tmem_st_32x32b_x16(p_tm, pk);
+        }
         if (TWO_PASS) {
           if (p.score_mode == TPAT_SCORE_COLMEAN) {
             // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
@@ -435,7 +435,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
       }
       ATTN_TRACE(7);
-      ptx::fence_proxy_async_smem();   // make this thread's generic-proxy P writes visible to the tensor core
+      ptx::tmem_st_wait();             // P is in tensor memory before the MMA thread is told so
+      ATTN_TRACE(6);
+      ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
       ATTN_TRACE(8);
@@ -460,12 +462,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]) * o_scale;
-      store_p_half(p_s + r_local * 128, half, r_local, v);
+      store_p_half(q_s + r_local * 128, half, r_local, v);     // Q is dead: its tile stages O
     }
     ptx::fence_proxy_async_smem();
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
     if (warp == 2 && lane == 0) {
-      ptx::tma_store_3d(&tmap_o, p_s, h * AT_HD, q0, b);   // rows >= N are clipped by the tensor map
+      ptx::tma_store_3d(&tmap_o, q_s, h * AT_HD, q0, b);   // rows >= N are clipped by the tensor map
       ptx::tma_store_commit();
     }
     if (TWO_PASS && p.score_mode == TPAT_SCORE_COLMEAN) {
@@ -503,9 +505,9 @@ int attention_tc_qtiles(int N) { return (N + AT_BM - 1) / AT_BM; }
 template <bool TWO_PASS>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to, const AttnTcParams& p,
                        dim3 grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
+  static DeviceOnce once;
   auto kern = attention_tc_kernel<TWO_PASS>;
-  if (!attr_set) {
+  if (once.first()) {
     TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_LIMIT));
     TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (getenv("TPAT_DEBUG")) {
@@ -513,7 +515,6 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUte
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, AT_THREADS, smem);
       fprintf(stderr, "[tpat] attention_tc_kernel<%d>: %d CTAs/SM at %zu B smem\n", (int)TWO_PASS, nblk, smem);
     }
-    attr_set = true;
   }
   TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(AT_THREADS), smem, st, tq, tkv, to, p));
   TPAT_LAUNCH_CHECK();
@@ -541,7 +542,7 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
   p.qt_offset = 0;
   p.desc = g_walk_desc;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const size_t base_smem = 1024 + AT_Q_BYTES + 2 * AT_P_BYTES + AT_SLOTS * AT_KV_BYTES + 256 + 2 * AT_BM * sizeof(float2) + 64;
+  const size_t base_smem = 1024 + AT_Q_BYTES + AT_SLOTS * AT_KV_BYTES + 256 + 2 * AT_BM * sizeof(float2) + 64;
   const size_t colsum_bytes = (size_t)4 * p.nb * AT_BK * sizeof(float);
   TPAT_CHECK(base_smem + (score_mode == TPAT_SCORE_COLMEAN ? colsum_bytes : 0) <= (size_t)AT_SMEM_LIMIT,
              "tpat_attention(tc): N=%d needs %zu bytes of shared memory", N, base_smem + colsum_bytes);

@@ -35,6 +35,20 @@ static inline size_t dtype_size(int dt) { return dt == TPAT_BF16 ? 2 : 4; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();  // cached multiprocessor count of the current device
+
+// Per-device once-flags for cudaFuncSetAttribute (function attributes belong to the device's context: a process that
+// drives several GPUs, e.g. the reference's nn.DataParallel replicas, must set them on each).  Benign race: idempotent.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 bool pdl_enabled();  // programmatic dependent launch when TPAT_PDL=1 (measured r01: 11.18k vs 11.46k clips/s -> off by default)
 
 // Walk direction of the next launches made by this thread (library-internal, set by tpat_forward only; the per-kernel

@@ -243,12 +243,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 template <int EPI, typename OutT>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const TcGemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;  // benign race: idempotent attribute
+  static DeviceOnce once;
   auto kern = gemm_tc_kernel<EPI, OutT>;
-  if (!attr_set) {
-    TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
-    attr_set = true;
-  }
+  if (once.first()) TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(TG_THREADS), TG_SMEM_BYTES, st, ta, tw, p));

@@ -241,13 +241,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 template <int EPI, typename OutT, bool RES_TMA = false>
 static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr, const CUtensorMap& tc,
                       const TcGemmParams& p, cudaStream_t st) {
-  static bool attr_set = false;
+  static DeviceOnce once;
   auto kern = gemm_tc2_kernel<EPI, OutT, RES_TMA>;
   constexpr int smem_bytes = (RES_TMA && EPI == TPAT_EPI_BIAS_RESIDUAL) ? T2R_SMEM_BYTES : T2_SMEM_BYTES;
-  if (!attr_set) {
-    TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  if (once.first()) TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles = p.tiles_m * p.tiles_n;
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;

@@ -135,7 +135,9 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem]
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M rows = TMEM lanes, K-major, two bf16 per 32-bit column, 8 columns
+// per K=16 step) is read straight from tensor memory -- how the softmax probabilities reach the P.V product without
+// a round trip through shared memory.
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
