@@ -400,13 +400,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
       };
       emit_half();
+      ATTN_TRACE(12);
       if (!TWO_PASS && j > 0) {
         // does any row of this quarter need a higher reference?  Each partner knows its own columns only: the
         // warp-level verdicts are swapped through shared memory (slot = tile parity) around a 64-thread barrier
         const float mx_own = vh > 0 ? max32(r) : -INFINITY;
         const bool need_w = __any_sync(0xffffffffu, (mx_own - m_run) * c > AT_RESCALE_LOG2);
         if (lane == 0) flag_s[(j & 1) * 8 + quarter * 2 + half] = need_w ? 1 : 0;
+        ATTN_TRACE(13);
         pair_sync();
+        ATTN_TRACE(14);
         if (need_w || flag_s[(j & 1) * 8 + quarter * 2 + (half ^ 1)] != 0) {
           my_x->x = mx_own;
           pair_sync();

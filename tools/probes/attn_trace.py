@@ -26,7 +26,7 @@ buf = (ctypes.c_longlong * 128)()
 assert lib.tpat_debug_attn_trace(buf) == 0
 n = buf[127]
 prev = 0
-names = {1: "start", 2: "wait S", 3: "S ready", 4: "S in regs", 5: "max done", 6: "P free", 7: "exp+store done", 8: "arrived", 9: "loop done", 10: "O ready", 11: "end"}
+names = {1: "start", 2: "wait S", 3: "S ready", 4: "S in regs", 5: "max done", 6: "P free", 7: "exp+store done", 8: "arrived", 9: "loop done", 10: "O ready", 11: "end", 12: "exps+st issued", 13: "max/vote/flag", 14: "pair barrier"}
 for i in range(n):
     slot, t = buf[i] >> 48, buf[i] & ((1 << 48) - 1)
     print(f"{t:8d} (+{t - prev:6d})  {names.get(slot, slot)}")
