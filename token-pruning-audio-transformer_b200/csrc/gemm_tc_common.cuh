@@ -32,18 +32,21 @@ __device__ __forceinline__ int tc_tile_m(const TcGemmParams& p, int tile) {
   return p.desc ? p.tiles_m - 1 - mt : mt;
 }
 
-// GELU for the bf16 tensor-core epilogue: x * sigmoid(x * (c1 + c3 x^2 + c5 x^4)), coefficients fitted
-// (minimax, tools/probes/fit_gelu.py) to the erf form nn.GELU() uses: |error| <= 8.2e-5 absolute over
-// all x, i.e. about one bf16 ulp at worst (x ~ -3) and far below it elsewhere -- invisible once the
-// result is rounded to bf16.  9 instructions (2 MUFU) instead of ~30 for libdevice erff: the fc1
-// epilogue was instruction-issue bound (ncu: 97 M warp instructions, 660 -> 940 TF/s with an
-// Abramowitz-Stegun erf, -> see profiles/ with this form).  The fp32 parity path keeps erff.
+// GELU for the bf16 tensor-core epilogue: x * sigmoid(z), z = x (c1 + c3 x^2 + c5 x^4) with the coefficients fitted
+// (minimax, tools/probes/fit_gelu.py) to the erf form nn.GELU() uses: |error| <= 8.2e-5 absolute over all x, i.e.
+// about one bf16 ulp at worst (x ~ -3) and far below it elsewhere -- invisible once the result is rounded to bf16.
+// Evaluated as 0.5 x (1 + tanh(z / 2)): 8 instructions with ONE MUFU (tanh.approx.f32) -- libdevice erff is ~30
+// instructions and made the fc1 epilogue instruction-issue bound (660 TF/s); the x * rcp(1 + ex2(.)) form (two MUFU)
+// left it MUFU-bound (1215 TF/s, XU pipe 48 %); this form measures 1285 TF/s with the same error in every x range
+// (tools/probes/gelu_probe.py, profiles/r01f_gelu_probe.txt).  The fp32 parity path keeps erff.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float x2 = fminf(x * x, 81.0f);              // the fit is valid for |x| <= 9; beyond it the sigmoid is saturated
-  float p = fmaf(x2, 8.2617402e-4f, -0.10563205f);   // -log2(e) * (c5 x^2 + c3)
-  p = fmaf(p, x2, -2.3019710f);                      // -log2(e) * c1
-  const float e = ptx::ex2_ftz(p * x);               // exp(-x (c1 + c3 x^2 + c5 x^4))
-  return x * ptx::rcp_ftz(1.0f + e);
+  float h = fmaf(x2, -2.8633e-4f, 0.036609f);        // (c5 x^2 + c3) / 2
+  h = fmaf(h, x2, 0.797786f);                        // ... + c1 / 2
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 // Per-tile epilogue state that does not depend on the accumulator: loaded BEFORE waiting for the MMA
