@@ -54,9 +54,11 @@ def test_gemm_tc_residual_in_place(M, N, K):
     assert rel_err(x, ref) < 2e-5
 
 
-def test_gemm_tc_patch_pos_epilogue():
+@pytest.mark.parametrize("B,P,extra", [(5, 512, 1), (3, 64, 2), (3, 104, 1), (2, 8, 2)])
+def test_gemm_tc_patch_pos_epilogue(B, P, extra):
+    """P % 32 == 0: TMA read-modify-write epilogue (position block in, shifted C block out); otherwise the register path."""
     from tpat import ops, _lib
-    B, P, extra, D = 5, 512, 1, 768
+    D = 768
     a, w, bias = _mk(B * P, D, 256, 14)
     pos = torch.randn(extra + P, D, generator=torch.Generator().manual_seed(15)).to(dev())
     out = torch.full((B * (extra + P), D), 7.0, device=dev())

@@ -35,7 +35,9 @@ template <int EPI, typename OutT, bool RES_TMA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_c, const TcGemmParams p) {
-  constexpr bool kResTma = RES_TMA && EPI == TPAT_EPI_BIAS_RESIDUAL;   // TMA-fed residual epilogue (short-K GEMMs)
+  // TMA-fed read-modify-write epilogue: short-K residual GEMMs, and the patch-embed GEMM whose "residual" is the
+  // position table (row extra + m % P) and whose output rows are shifted by the clip's extra-token rows
+  constexpr bool kResTma = RES_TMA && (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS);
   constexpr int NSTAGES = kResTma ? T2R_STAGES : T2_STAGES;
   constexpr int STAGING = kResTma ? T2R_STAGING_BYTES : T2_STAGING_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -154,7 +156,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint64_t* rb = res_bar + (warp - 2) * 2;
       int buf = 0; uint32_t rph0 = 0, rph1 = 0;
       auto item_cols = [&](int tile, int ci) { return (tile % p.tiles_n) * TG_BN + (cg + CS * ci) * 32; };
-      auto item_live = [&](int tile, int ci) { return ci < NCH && cg + CS * ci < 8 && item_cols(tile, ci) < p.N; };
+      auto item_row0 = [&](int tile) { return tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32; };
+      auto item_live = [&](int tile, int ci) {
+        if (EPI == TPAT_EPI_BIAS_POS && item_row0(tile) >= p.M) return false;   // (M is a multiple of 32 here)
+        return ci < NCH && cg + CS * ci < 8 && item_cols(tile, ci) < p.N;
+      };
+      // row of the block in the tensor that is read (residual: m0; pos table: extra + m0 % P) / written (shifted by the
+      // extra-token rows of the clips before it)
+      auto load_row = [&](int m0) { return EPI == TPAT_EPI_BIAS_POS ? p.num_extra + m0 % p.P : m0; };
+      auto store_row = [&](int m0) { return EPI == TPAT_EPI_BIAS_POS ? m0 + (m0 / p.P + 1) * p.num_extra : m0; };
       // first live item at or after (tile, ci) in this warp's walk order; tile >= num_tiles when there is none
       auto next_live = [&](int& tile, int& ci) {
         while (tile < num_tiles) {
@@ -167,7 +177,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32;
         ptx::tma_store_wait_read<0>();                   // the store that last read this buffer has drained its smem reads
         ptx::mbar_arrive_expect_tx(&rb[b], 4096);
-        ptx::tma_load_2d(stg + b * 4096, &tmap_r, &rb[b], item_cols(tile, ci), m0);
+        ptx::tma_load_2d(stg + b * 4096, &tmap_r, &rb[b], item_cols(tile, ci), load_row(m0));
       };
       {
         int t0 = cluster_id, c0 = 0;
@@ -219,7 +229,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_2d(&tmap_c, stg + buf * 4096, n, m0);   // rows >= M are clipped by the tensor map
+            ptx::tma_store_2d(&tmap_c, stg + buf * 4096, n, store_row(m0));   // rows >= M are clipped by the tensor map
             ptx::tma_store_commit();
           }
           buf ^= 1;
@@ -243,7 +253,7 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
                       const TcGemmParams& p, cudaStream_t st) {
   static DeviceOnce once;
   auto kern = gemm_tc2_kernel<EPI, OutT, RES_TMA>;
-  constexpr int smem_bytes = (RES_TMA && EPI == TPAT_EPI_BIAS_RESIDUAL) ? T2R_SMEM_BYTES : T2_SMEM_BYTES;
+  constexpr int smem_bytes = (RES_TMA && (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS)) ? T2R_SMEM_BYTES : T2_SMEM_BYTES;
   if (once.first()) TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles = p.tiles_m * p.tiles_n;
   int clusters = sm_count() / 2;
@@ -280,8 +290,16 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
       if (int rc = encode_tmap_2d(&tc, C, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ldc * 4, 32, 32, true)) return rc;
       return launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, true>(ta, tw, tr, tc, p, st);
     }
-    case TPAT_EPI_BIAS_POS:
-      return launch_tc2<TPAT_EPI_BIAS_POS, float>(ta, tw, ta, ta, p, st);
+    case TPAT_EPI_BIAS_POS: {
+      // K = 256: the epilogue (fp32 rows out, position rows in) is the whole cost.  When a 32-row block never straddles
+      // a clip (P % 32 == 0) it runs as a TMA read-modify-write like the residual epilogue: pos block in, C block out.
+      const int rows_out = (M / ep.P) * (ep.P + ep.num_extra);
+      if (ep.P % 32 != 0 || M % ep.P != 0) return launch_tc2<TPAT_EPI_BIAS_POS, float>(ta, tw, ta, ta, p, st);
+      CUtensorMap tr, tc;
+      if (int rc = encode_tmap_2d(&tr, ep.pos, 4, (uint64_t)(ep.P + ep.num_extra), (uint64_t)N, (uint64_t)ldc * 4, 32, 32, true)) return rc;
+      if (int rc = encode_tmap_2d(&tc, C, 4, (uint64_t)rows_out, (uint64_t)N, (uint64_t)ldc * 4, 32, 32, true)) return rc;
+      return launch_tc2<TPAT_EPI_BIAS_POS, float, true>(ta, tw, tr, tc, p, st);
+    }
   }
   set_error("tpat_gemm(tc2): bad epilogue %d", ep.epilogue);
   return 1;

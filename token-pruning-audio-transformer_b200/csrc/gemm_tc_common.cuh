@@ -98,6 +98,15 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
           extra[it] = m < p.M ? *reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + ncol) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+    } else if constexpr (EPI == TPAT_EPI_BIAS_POS) {
+      if (live) {   // the position rows are requested before the TMEM read as well (8 independent loads in flight)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = m0 + it * 4 + rl;
+          const int pp = m % p.P;
+          extra[it] = m < p.M ? __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(p.num_extra + pp) * p.ldc + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
     }
     uint32_t r[32];
     if (live) {
@@ -131,7 +140,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
         v[it].x = gelu_erf_fast(v[it].x); v[it].y = gelu_erf_fast(v[it].y);
         v[it].z = gelu_erf_fast(v[it].z); v[it].w = gelu_erf_fast(v[it].w);
       }
-    } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
+    } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) { v[it].x += extra[it].x; v[it].y += extra[it].y; v[it].z += extra[it].z; v[it].w += extra[it].w; }
     }
@@ -143,8 +152,6 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
       if constexpr (EPI == TPAT_EPI_BIAS_POS) {
         const int b = m / p.P, pp = m - b * p.P;
         orow = (size_t)b * (p.num_extra + p.P) + p.num_extra + pp;
-        const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (size_t)(p.num_extra + pp) * p.ldc + ncol));
-        v[it].x += pe.x; v[it].y += pe.y; v[it].z += pe.z; v[it].w += pe.w;
       }
       if constexpr (sizeof(OutT) == 4) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + ncol) = v[it];

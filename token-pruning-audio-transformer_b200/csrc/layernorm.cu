@@ -211,8 +211,11 @@ head_kernel(const float* __restrict__ pooled, const float* __restrict__ W, const
 #pragma unroll
   for (int i = 0; i < NV; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)c * D) + lane + 32 * i);
   const float bc = bias ? __ldg(bias + c) : 0.f;
+  // the clips are split over blockIdx.y (more, shorter dependency chains: this kernel is pure latency);
   // four clips per step: four independent load / FMA / shuffle chains in flight
-  for (int b0 = 0; b0 < B; b0 += 4) {
+  const int per = ((B + (int)gridDim.y - 1) / (int)gridDim.y + 3) & ~3;
+  const int b_end = min(B, ((int)blockIdx.y + 1) * per);
+  for (int b0 = (int)blockIdx.y * per; b0 < b_end; b0 += 4) {
     float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -402,7 +405,7 @@ extern "C" int tpat_head(const float* pooled, const float* W, const float* bias,
   TPAT_CHECK(B >= 0 && C > 0 && D > 0 && D % 128 == 0 && D <= 1024, "tpat_head: need D %% 128 == 0, D <= 1024 (D=%d)", D);
   TPAT_CHECK(aligned16(pooled) && aligned16(W), "tpat_head: pooled and W must be 16-byte aligned");
   if (B == 0) return 0;
-  const int grid = (C + 7) / 8;
+  const dim3 grid((C + 7) / 8, B >= 32 ? 8 : (B >= 8 ? 2 : 1));
   cudaStream_t st = as_stream(stream);
   switch (D / 128) {
     case 1: TPAT_CUDA(launch_kernel(head_kernel<1>, dim3(grid), dim3(256), 0, st, pooled, W, bias, logits, B, C)); break;

@@ -34,3 +34,19 @@ with open(os.path.join(out, f"{tag}_ncu_full_summary.txt"), "w") as f:
         for k in keys:
             if k in idx: f.write(f"    {k:72s} {d[idx[k]]:>18s} {units[idx[k]]}\n")
 print(open(os.path.join(out, f"{tag}_launch_shares.txt")).read())
+# dram traffic per launch of the kernels bench.py reports a roofline for -> profiles/ncu_traffic.json (read by bench.py)
+import json
+names = {"gemm_tc2_kernel<1": "gemm_fc1_tcgen05", "layernorm_kernel": "layernorm", "attention_tc_kernel<0>": "attention_tcgen05"}
+def to_bytes(v, u):
+    v = float(v.replace(",", ""))
+    return int(v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1))
+traffic = {}
+for d in data:
+    kn = d[idx["Kernel Name"]]
+    for pat, key in names.items():
+        if pat in kn and key not in traffic:
+            rd = to_bytes(d[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+            wr = to_bytes(d[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+            traffic[key] = {"dram_bytes": rd + wr, "read": rd, "write": wr, "kernel": kn[:100], "source": f"profiles/{tag}_ncu_full_summary.txt"}
+json.dump(traffic, open(os.path.join(out, "ncu_traffic.json"), "w"), indent=1)
+print(json.dumps(traffic, indent=1))
