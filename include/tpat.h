@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 3
+#define TPAT_VERSION 4
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -64,6 +64,28 @@ int tpat_version(void);
 const char* tpat_last_error(void);
 /* 1 when the current device is compute capability 10.x, 0 otherwise (no error is set) */
 int tpat_device_ok(void);
+
+/*
+ * Kaldi-compatible log-mel front end: waveforms -> the normalised spectrogram tpat_forward / tpat_patchify consume.
+ * Replaces (eval path) `waveform - waveform.mean()`, torchaudio.compliance.kaldi.fbank(htk_compat=True, use_energy=False,
+ * window_type='hanning', num_mel_bins=n_mel, dither=0.0, frame_shift=10), pad-with-minimum / crop to T frames and
+ * `(fbank - norm_mean) / (norm_std * 2)` (audiomae/dataset.py:175-230,298; ast/src/dataloader.py:98-149,204).
+ * torchaudio is the reference's pinned third-party dependency (torchaudio==2.4.1, amae_pruning_miniconda.yml:90).
+ *   wave     [B, L] fp32 mono; lengths [B] int32 valid samples per clip or NULL (all L)
+ *   subtract_clip_mean  != 0: subtract each clip's mean first;  clip_mean_ws: 32 * B floats of scratch, 8-byte aligned
+ *            (always required: partial sums and the clip's minimum log-mel value live there)
+ *   window   [win] fp32 (torch.hann_window(win, periodic=False)); frames of `win` samples every `shift`, snip_edges:
+ *            n_frames(b) = 1 + (len_b - win) / shift; per frame: DC removal, pre-emphasis `preemph` with replicate
+ *            padding, window, zero-pad to nfft (256 | 512 | 1024), power spectrum
+ *   mel      [n_mel, nfft/2 + 1] fp32 triangular filters (kaldi get_mel_banks + one zero column), mel_start / mel_len
+ *            [n_mel] int32: first non-zero FFT bin and number of bins of each filter
+ *   spec     [B, T, n_mel] fp32 out (n_mel % 4 == 0): log(max(energy, FLT_EPSILON)); rows >= n_frames(b) = the clip's minimum; then
+ *            (v - norm_mean) / (2 norm_std)
+ */
+int tpat_fbank(const float* wave, const int* lengths, int B, int L, int subtract_clip_mean, float* clip_mean_ws,
+               const float* window, int win, int shift, int nfft, float preemph, const float* mel,
+               const int* mel_start, const int* mel_len, int n_mel, float* spec, int T, float norm_mean,
+               float norm_std, tpat_stream_t stream);
 
 /*
  * Patch extraction (im2col of the 16x16 / stride-16 conv) + extra-token rows.

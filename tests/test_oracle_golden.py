@@ -106,3 +106,26 @@ def test_melspec_indices_composition():
     b = torch.tensor([[2, 0]])
     out = vo.melspec_indices([a, b])
     assert out[1].tolist() == [[2, 3]]
+
+
+def test_fbank_oracle_matches_golden_and_mel_table_matches_torchaudio():
+    """The front-end oracle (torchaudio kaldi fbank + the loaders' pad / crop / normalise) against the committed
+    outputs, and the host-built mel filter table against torchaudio's (bit-identical)."""
+    pytest.importorskip("torchaudio")
+    import torchaudio.compliance.kaldi as kaldi
+    from oracle import fbank_oracle as fo
+    from tpat.frontend import FbankFrontend, mel_banks
+    g = load_golden("fbank_cases")
+    for name in g["meta"]["cases"]:
+        c = g[name]
+        spec = fo.wav2fbank(fo.make_waveform(c["n"], c["seed"]), target_length=c["T"])
+        assert torch.allclose(spec, c["spec"], rtol=0, atol=2e-5), name
+    ref, _ = kaldi.get_mel_banks(128, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
+    mine, start, length = mel_banks(128, 512, 16000.0)
+    assert torch.equal(mine[:, :256], ref) and torch.all(mine[:, 256] == 0)
+    for m in range(128):
+        nz = torch.nonzero(mine[m] > 0).flatten()
+        if nz.numel():
+            assert int(start[m]) == int(nz[0]) and int(start[m] + length[m] - 1) == int(nz[-1])
+    fe = FbankFrontend()
+    assert (fe.win, fe.shift, fe.nfft, fe.num_frames(163840)) == (400, 160, 512, 1022)

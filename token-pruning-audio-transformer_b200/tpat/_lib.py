@@ -64,6 +64,8 @@ SIGNATURES = {
     "tpat_pool_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float, c_int,
                                c_int, c_int, c_int, c_void_p]),
     "tpat_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tpat_fbank": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
+                           c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_void_p]),
     "tpat_patch_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tpat_gather_rank": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tpat_sizeof_forward_args": (c_size_t, []),
