@@ -109,14 +109,17 @@ class ClockSampler:
 
 
 def build_model(device):
+    """The product arm: random-init weights with the reference's init statistics (the model class' own constructor
+    init under a fixed seed; nothing from oracle/ is used on this arm)."""
     import torch.nn as nn
-    from oracle import weights
     from tpat import models_vit
+    torch.manual_seed(0)
     m = models_vit.vit_base_patch16(num_classes=NUM_CLASSES, drop_path_rate=0.1, mean_pooling=True, mask_2d=True,
                                     target_length=T_FRAMES, drop_loc=DROP_LOC, base_keep_rate=KEEP_RATE, precision="bf16")
     m.patch_embed = models_vit.PatchEmbed((T_FRAMES, F_BINS), 16, 1, 768)           # main_finetune.py:378-382
-    m.pos_embed = nn.Parameter(torch.zeros(1, m.patch_embed.num_patches + 1, 768), requires_grad=False)
-    m.load_state_dict(weights.make_audiomae_state_dict(NUM_CLASSES, T_FRAMES, 0, "refinit"), strict=True)
+    pos = torch.zeros(1, m.patch_embed.num_patches + 1, 768)
+    nn.init.trunc_normal_(pos, std=.02)
+    m.pos_embed = nn.Parameter(pos, requires_grad=False)
     return m.to(device).eval()
 
 
