@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 4
+#define TPAT_VERSION 5
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -138,6 +138,31 @@ int tpat_layernorm(const float* x, const float* gamma, const float* beta, void* 
 int tpat_gemm(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
               void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
               int P, int num_extra, int M, int N, int K, int epilogue, int impl, tpat_stream_t stream);
+
+/*
+ * tpat_gemm with the LayerNorm that FOLLOWS a residual GEMM folded into its neighbours (tcgen05 path only), so that
+ * `x = x + f(...)` followed by `norm(x)` and the next nn.Linear (models_vit.py:198,205 then :197/:205 of the next
+ * sub-block) need no separate pass over x:
+ *   producer  (TPAT_EPI_BIAS_RESIDUAL): besides C it writes xb = bf16(C) and, for every row and 32-column chunk, the
+ *             partial moments part_out[m][n/32] = (sum, sum of squared deviations from the chunk mean);
+ *   consumer  (TPAT_EPI_BIAS, TPAT_EPI_BIAS_GELU): A = xb, W = bf16(W * gamma) (gamma along K), bias = W beta + b,
+ *             ln_colsum[n] = sum_k W'[n, k]; the epilogue computes
+ *             rstd[m] * (acc[m, n] - mean[m] * ln_colsum[n]) + bias[n]   with mean / rstd of row m combined from
+ *             ln_part[m][0 .. K/32) (Chan's update in a fixed order: deterministic), variance biased, eps = ln_eps.
+ * fold == NULL or all pointers NULL: identical to tpat_gemm.
+ */
+typedef struct tpat_ln_fold {
+  void* xb;                /* producer: bf16 [M, ldxb] or NULL */
+  int ldxb;
+  float* part_out;         /* producer: fp32 [M, N/32, 2] */
+  const float* ln_part;    /* consumer: fp32 [M, K/32, 2] or NULL */
+  const float* ln_colsum;  /* consumer: fp32 [N] */
+  float ln_eps;
+} tpat_ln_fold;
+int tpat_gemm_ln(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
+                 void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
+                 int P, int num_extra, int M, int N, int K, int epilogue, int impl, const tpat_ln_fold* fold,
+                 tpat_stream_t stream);
 
 /*
  * Fused multi-head attention that also emits the importance-score partials.

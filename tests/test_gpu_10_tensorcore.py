@@ -69,6 +69,47 @@ def test_gemm_tc_patch_pos_epilogue(B, P, extra):
     assert torch.all(o[:, :extra] == 7.0)
 
 
+@pytest.mark.parametrize("M,K", [(1000, 768), (513 * 3, 3072), (64, 768)])
+def test_gemm_ln_fold_producer_and_consumer(M, K):
+    """LayerNorm fold (tpat_gemm_ln): the residual GEMM emits bf16(x) + per-chunk partial moments (TMA epilogue for
+    K = 768, register epilogue for K = 3072); a following GEMM with gamma-scaled weights normalises in its epilogue.
+    Compared with LayerNorm(x) @ W^T + b in float64 and with the unfused tpat path (LayerNorm kernel -> bf16 -> GEMM)."""
+    from tpat import ops, _lib
+    D, N2 = 768, 2304
+    g = torch.Generator().manual_seed(M + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).to(dev()).to(torch.bfloat16)
+    w = (torch.randn(D, K, generator=g) * 0.03).to(dev()).to(torch.bfloat16)
+    bias = (torch.randn(D, generator=g) * 0.1).to(dev())
+    x0 = (torch.randn(M, D, generator=g) * 2.0 + 0.3).to(dev())
+    x_ref = x0.clone()
+    ops.gemm(a, w, bias, torch.float32, _lib.EPI_BIAS_RESIDUAL, _lib.IMPL_TC, residual=x_ref, out=x_ref)
+    x = x0.clone()
+    _, xb, part = ops.gemm_ln(a, w, bias, torch.float32, _lib.EPI_BIAS_RESIDUAL, residual=x, out=x, emit=True)
+    assert torch.equal(x, x_ref)                                   # C itself is unchanged by the extra outputs
+    assert torch.equal(xb, x.to(torch.bfloat16))                   # bf16 copy = round-to-nearest of the fp32 value
+    xc = x.double().reshape(M, D // 32, 32)
+    assert torch.allclose(part[..., 0].double(), xc.sum(-1), rtol=1e-5, atol=1e-4)
+    m2 = ((xc - xc.mean(-1, keepdim=True)) ** 2).sum(-1)
+    assert torch.allclose(part[..., 1].double(), m2, rtol=1e-4, atol=1e-4)
+    # consumer: y = LN(x) @ W2^T + b2, with gamma folded into W2 and beta into the bias
+    gamma = (1.0 + 0.2 * torch.randn(D, generator=g)).to(dev())
+    beta = (0.1 * torch.randn(D, generator=g)).to(dev())
+    w2 = (torch.randn(N2, D, generator=g) * 0.03).to(dev())
+    b2 = (torch.randn(N2, generator=g) * 0.1).to(dev())
+    w2f = (w2 * gamma[None, :]).to(torch.bfloat16)
+    colsum = w2f.float().sum(1).contiguous()
+    b2f = (w2 @ beta + b2).contiguous()
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-6) @ w2.double().T + b2.double()
+    for epi in (_lib.EPI_BIAS, _lib.EPI_BIAS_GELU):
+        want = ref if epi == _lib.EPI_BIAS else torch.nn.functional.gelu(ref)
+        got = ops.gemm_ln(xb, w2f, b2f, torch.bfloat16, epi, ln_part=part, ln_colsum=colsum, ln_eps=1e-6)
+        y = ops.layernorm(x, gamma, beta, 1e-6, torch.bfloat16)
+        unfused = ops.gemm(y, w2.to(torch.bfloat16), b2, torch.bfloat16, epi, _lib.IMPL_TC)
+        e_fold, e_unf = rel_err(got.float(), want), rel_err(unfused.float(), want)
+        print(f"[ln fold] M={M} K={K} epi={epi}: fold err {e_fold:.2e}, unfused err {e_unf:.2e}")
+        assert e_fold < 1e-2 and e_fold < 1.5 * e_unf + 1e-3
+
+
 def test_gemm_tc_rejects_bad_arguments():
     from tpat import ops, _lib
     a, w, bias = _mk(64, 64, 96, 16)

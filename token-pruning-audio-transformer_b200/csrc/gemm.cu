@@ -4,6 +4,14 @@
 extern "C" int tpat_gemm(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
                          void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
                          int P, int num_extra, int M, int N, int K, int epilogue, int impl, tpat_stream_t stream) {
+  return tpat_gemm_ln(A, a_dtype, lda, W, w_dtype, bias, C, c_dtype, ldc, residual, ldr, pos, P, num_extra, M, N, K, epilogue,
+                      impl, nullptr, stream);
+}
+
+extern "C" int tpat_gemm_ln(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
+                            void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
+                            int P, int num_extra, int M, int N, int K, int epilogue, int impl, const tpat_ln_fold* fold,
+                            tpat_stream_t stream) {
   using namespace tpat;
   TPAT_CHECK(A && W && C, "tpat_gemm: null pointer");
   TPAT_CHECK(M >= 0 && N > 0 && K > 0, "tpat_gemm: bad sizes M=%d N=%d K=%d", M, N, K);
@@ -15,6 +23,19 @@ extern "C" int tpat_gemm(const void* A, int a_dtype, int lda, const void* W, int
   if (epilogue == TPAT_EPI_BIAS_POS) TPAT_CHECK(pos && P > 0 && num_extra >= 0 && M % P == 0 && ldc == N && c_dtype == TPAT_F32, "tpat_gemm: pos epilogue needs pos, P | M, ldc == N and fp32 C");
   if (M == 0) return 0;
   EpiParams ep{bias, residual, ldr, pos, P, num_extra, epilogue};
+  if (fold != nullptr && (fold->xb != nullptr || fold->ln_part != nullptr)) {
+    TPAT_CHECK(impl == TPAT_IMPL_TC, "tpat_gemm_ln: the LayerNorm fold exists on the tcgen05 path only");
+    if (fold->xb != nullptr) {
+      TPAT_CHECK(epilogue == TPAT_EPI_BIAS_RESIDUAL && fold->part_out != nullptr && fold->ldxb >= N && fold->ldxb % 8 == 0 && aligned16(fold->xb),
+                 "tpat_gemm_ln: xb needs the residual epilogue, part_out and a 16-byte aligned bf16 buffer with ldxb %% 8 == 0");
+      ep.xb = fold->xb; ep.ldxb = fold->ldxb; ep.part_out = fold->part_out; ep.part_ld = N / 32;
+    }
+    if (fold->ln_part != nullptr) {
+      TPAT_CHECK((epilogue == TPAT_EPI_BIAS || epilogue == TPAT_EPI_BIAS_GELU) && fold->ln_colsum != nullptr && aligned16(fold->ln_colsum) && K % 32 == 0,
+                 "tpat_gemm_ln: ln_part needs the bias / bias+GELU epilogue, ln_colsum and K %% 32 == 0");
+      ep.ln_part = fold->ln_part; ep.ln_chunks = K / 32; ep.ln_colsum = fold->ln_colsum; ep.ln_eps = fold->ln_eps;
+    }
+  }
   if (impl == TPAT_IMPL_SIMT) return gemm_simt(A, a_dtype, lda, W, C, c_dtype, ldc, M, N, K, ep, as_stream(stream));
   if (impl == TPAT_IMPL_TC) {
     TPAT_CHECK(a_dtype == TPAT_BF16, "tpat_gemm: the tcgen05 path takes bf16 operands");

@@ -9,6 +9,12 @@ struct EpiParams {
   const float* residual; int ldr;
   const float* pos; int P; int num_extra;
   int epilogue;
+  // LayerNorm fold (tpat_gemm_ln): producer outputs / consumer inputs, all optional
+  void* xb = nullptr; int ldxb = 0;
+  float* part_out = nullptr; int part_ld = 0;
+  const float* ln_part = nullptr; int ln_chunks = 0;
+  const float* ln_colsum = nullptr;
+  float ln_eps = 0.f;
 };
 
 // CUDA-core fp32-FMA path (gemm_simt.cu)

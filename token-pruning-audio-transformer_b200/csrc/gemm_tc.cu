@@ -272,7 +272,8 @@ int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc
   CUtensorMap ta, tw;
   if (int rc = encode_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, TG_BM, TG_BK, true)) return rc;
   if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, TG_BN, TG_BK, true)) return rc;
-  TcGemmParams p;
+  TPAT_CHECK(ep.xb == nullptr && ep.ln_part == nullptr, "tpat_gemm_ln: the LayerNorm fold needs the CTA-pair kernel (TPAT_GEMM_2CTA=0 is set)");
+  TcGemmParams p{};
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + TG_BN - 1) / TG_BN;

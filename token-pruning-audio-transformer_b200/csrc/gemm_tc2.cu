@@ -25,7 +25,8 @@ constexpr int T2_A_BYTES = 128 * TG_BK * 2;    // 16 KB: this CTA's 128 rows of 
 constexpr int T2_B_BYTES = 128 * TG_BK * 2;    // 16 KB: this CTA's 128 rows of W
 constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 constexpr int T2_STAGING_BYTES = tg_staging_bytes(T2_EPI_WARPS);
-constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + T2_STAGING_BYTES + 1024 + 256;
+constexpr int T2_ROWSTAT_BYTES = T2_EPI_WARPS * 32 * 8;   // LayerNorm fold, consumer side: (mean, rstd) of each warp's 32 rows
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + T2_STAGING_BYTES + 1024 + 512 + T2_ROWSTAT_BYTES;
 // residual epilogue (proj, fc2): the fp32 residual chunk is TMA-prefetched into a second 4 KB buffer per warp
 constexpr int T2R_STAGES = 4;
 constexpr int T2R_STAGING_BYTES = 2 * T2_STAGING_BYTES;
@@ -135,15 +136,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int acc = 0; uint32_t acc_phase = 0;
     if constexpr (!kResTma) {
       uint8_t* stg = staging + (warp - 2) * 4096;
+      float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512) + (warp - 2) * 32;
+      const bool fold = p.ln_part != nullptr;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
         TcEpiPrefetch<T2_EPI_WARPS> pf;
         tc_epilogue_prefetch<T2_EPI_WARPS>(p, n0, cg, lane, pf);
+        if (fold) {     // LayerNorm fold: (mean, rstd) of this warp's 32 rows, computed while the MMA is still running
+          __syncwarp();
+          rowstat[lane] = m0 + lane < p.M ? ln_row_moments(p.ln_part + (size_t)(m0 + lane) * p.ln_chunks, p.ln_chunks, p.ln_eps)
+                                          : make_float2(0.f, 1.f);
+          __syncwarp();
+        }
         ptx::mbar_wait(&acc_full[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
         const uint32_t rel_leader = ptx::mapa_shared(ptx::smem_u32(&acc_empty[acc]), 0);
-        tc_epilogue_tile<EPI, OutT, T2_EPI_WARPS>(p, taddr_row, m0, n0, cg, stg, lane, pf, [&]() { if (lane == 0) ptx::mbar_arrive_cluster(rel_leader); });
+        tc_epilogue_tile<EPI, OutT, T2_EPI_WARPS>(p, taddr_row, m0, n0, cg, stg, lane, pf, [&]() { if (lane == 0) ptx::mbar_arrive_cluster(rel_leader); },
+                                                  fold ? rowstat : nullptr);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else {
@@ -225,6 +235,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             x.x += __uint_as_float(r[4 * j]) + bb.x; x.y += __uint_as_float(r[4 * j + 1]) + bb.y;
             x.z += __uint_as_float(r[4 * j + 2]) + bb.z; x.w += __uint_as_float(r[4 * j + 3]) + bb.w;
             *cell = x;
+            r[4 * j] = __float_as_uint(x.x); r[4 * j + 1] = __float_as_uint(x.y);      // keep the row for the fold below
+            r[4 * j + 2] = __float_as_uint(x.z); r[4 * j + 3] = __float_as_uint(x.w);
+          }
+          if (EPI == TPAT_EPI_BIAS_RESIDUAL && p.xb != nullptr) {
+            // LayerNorm fold, producer side: this thread's 32 new values of row m0 + lane -> bf16 copy + partial moments
+            float sm = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sm += __uint_as_float(r[i]);
+            const float mc = sm * (1.0f / 32.0f);
+            float q2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(r[i]) - mc; q2 = fmaf(d, d, q2); }
+            const int m = m0 + lane;
+            if (m < p.M) {
+              uint4* dst = reinterpret_cast<uint4*>(p.xb + (size_t)m * p.ldxb + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
+                                    pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                                    pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                                    pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+              p.part_out[(size_t)m * p.part_ld + (n >> 5)] = make_float2(sm, q2);
+            }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -268,9 +301,11 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   CUtensorMap ta, tw;
   if (int rc = encode_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 128, TG_BK, true)) return rc;
   if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, 128, TG_BK, true)) return rc;
-  TcGemmParams p;
+  TcGemmParams p{};
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
+  p.xb = (__nv_bfloat16*)ep.xb; p.ldxb = ep.ldxb; p.part_out = reinterpret_cast<float2*>(ep.part_out); p.part_ld = ep.part_ld;
+  p.ln_part = reinterpret_cast<const float2*>(ep.ln_part); p.ln_chunks = ep.ln_chunks; p.ln_colsum = ep.ln_colsum; p.ln_eps = ep.ln_eps;
   p.tiles_m = (M + 255) / 256; p.tiles_n = (N + TG_BN - 1) / TG_BN;
   p.desc = g_walk_desc;
   { const char* e = getenv("TPAT_GEMM_DEBUG_SKIP"); p.debug_skip = e ? atoi(e) : 0; }

@@ -23,6 +23,16 @@ struct TcGemmParams {
   const float* pos; int P, num_extra;
   int tiles_m, tiles_n;
   int desc;         // 1 = walk the row tiles from the last one down (see g_walk_desc)
+  // LayerNorm fold.  Producer side (residual GEMMs): besides C, write bf16(C) and, for every row and
+  // 32-column chunk, the partial moments (sum, sum of squared deviations from the chunk mean).  Consumer side (the GEMM
+  // that follows the LayerNorm): A is that bf16 copy, W carries gamma, and the epilogue applies
+  //   out[m, n] = rstd[m] * (acc[m, n] - mean[m] * ln_colsum[n]) + bias[n]       (bias already holds W beta + b)
+  // with mean / rstd combined from the partial moments of row m.  All pointers NULL = plain GEMM.
+  __nv_bfloat16* xb; int ldxb;
+  float2* part_out; int part_ld;
+  const float2* ln_part; int ln_chunks;
+  const float* ln_colsum;
+  float ln_eps;
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
 };
 
@@ -49,12 +59,27 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// (mean, rstd) of one row from the partial moments of its 32-element chunks (Chan's pairwise update, fixed order)
+__device__ __forceinline__ float2 ln_row_moments(const float2* __restrict__ part, int chunks, float eps) {
+  float mean = 0.f, m2 = 0.f, n = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const float2 pc = __ldg(part + c);
+    const float mc = pc.x * (1.0f / 32.0f);
+    const float delta = mc - mean, nn = n + 32.0f;
+    mean = fmaf(delta, 32.0f / nn, mean);
+    m2 += pc.y + delta * delta * (n * 32.0f / nn);
+    n = nn;
+  }
+  return make_float2(mean, rsqrtf(m2 / n + eps));
+}
+
 // Per-tile epilogue state that does not depend on the accumulator: loaded BEFORE waiting for the MMA
 // so that the global-load latency (bias) is off the critical path.
 template <int EW> struct TcEpiPrefetch {
   static constexpr int CSTRIDE = EW / 4;                       // warps per lane quarter
   static constexpr int NCH = (8 + CSTRIDE - 1) / CSTRIDE;      // chunks per warp (the last may be dead)
   float4 bias[NCH];
+  float4 colsum[NCH];   // consumer side of the LayerNorm fold
 };
 
 template <int EW>
@@ -65,6 +90,7 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmParams& p, int 
     const int c = cg + TcEpiPrefetch<EW>::CSTRIDE * ci;
     const int ncol = n0 + c * 32 + jl * 4;
     pf.bias[ci] = (p.bias != nullptr && c < 8 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pf.colsum[ci] = (p.ln_colsum != nullptr && c < 8 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -79,7 +105,8 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmParams& p, int 
 // Residual rows are requested before the TMEM read of the chunk so their latency overlaps it.
 template <int EPI, typename OutT, int EW, typename ReleaseFn>
 __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t taddr_row, int m0, int n0, int cg,
-                                                 uint8_t* stg, int lane, const TcEpiPrefetch<EW>& pf, ReleaseFn release) {
+                                                 uint8_t* stg, int lane, const TcEpiPrefetch<EW>& pf, ReleaseFn release,
+                                                 const float2* rowstat = nullptr) {
   constexpr int NCH = TcEpiPrefetch<EW>::NCH, CSTRIDE = TcEpiPrefetch<EW>::CSTRIDE;
   const int jl = lane & 7, rl = lane >> 3;   // coalesced phase: lane -> (16 B piece, row within a group of 4)
   bool released = false;
@@ -131,7 +158,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
     for (int it = 0; it < 8; ++it) {
       const int row = it * 4 + rl;
       const float4 a = *reinterpret_cast<const float4*>(stg + row * 128 + ((jl ^ (row & 7)) << 4));
-      v[it] = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+      if (rowstat != nullptr) {          // LayerNorm fold: rstd * (acc - mean * colsum) + bias'
+        const float2 rs = rowstat[row];
+        const float4 cs = pf.colsum[ci];
+        v[it] = make_float4(fmaf(rs.y, fmaf(-rs.x, cs.x, a.x), bb.x), fmaf(rs.y, fmaf(-rs.x, cs.y, a.y), bb.y),
+                            fmaf(rs.y, fmaf(-rs.x, cs.z, a.z), bb.z), fmaf(rs.y, fmaf(-rs.x, cs.w, a.w), bb.w));
+      } else {
+        v[it] = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+      }
     }
     __syncwarp();   // all lanes have read the transpose buffer: the next chunk may overwrite it
     if constexpr (EPI == TPAT_EPI_BIAS_GELU) {
@@ -143,6 +177,24 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
     } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) { v[it].x += extra[it].x; v[it].y += extra[it].y; v[it].z += extra[it].z; v[it].w += extra[it].w; }
+    }
+    if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
+      if (p.xb != nullptr) {             // LayerNorm fold, producer side: bf16 copy + partial moments of this chunk
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = m0 + it * 4 + rl;
+          float sm = (v[it].x + v[it].y) + (v[it].z + v[it].w);
+          sm += __shfl_xor_sync(0xffffffffu, sm, 1); sm += __shfl_xor_sync(0xffffffffu, sm, 2); sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+          const float mc = sm * (1.0f / 32.0f);
+          const float dx = v[it].x - mc, dy = v[it].y - mc, dz = v[it].z - mc, dw = v[it].w - mc;
+          float q = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+          if (m < p.M) {
+            *reinterpret_cast<uint2*>(p.xb + (size_t)m * p.ldxb + ncol) = make_uint2(pack_bf16x2(v[it].x, v[it].y), pack_bf16x2(v[it].z, v[it].w));
+            if (jl == 0) p.part_out[(size_t)m * p.part_ld + (n >> 5)] = make_float2(sm, q);
+          }
+        }
+      }
     }
 #pragma unroll
     for (int it = 0; it < 8; ++it) {

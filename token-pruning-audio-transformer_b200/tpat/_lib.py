@@ -26,6 +26,12 @@ class BlockWeights(Structure):
         "ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
 
+class LnFold(Structure):
+    """tpat_ln_fold (include/tpat.h): producer outputs / consumer inputs of the folded LayerNorm."""
+    _fields_ = [("xb", c_void_p), ("ldxb", c_int), ("part_out", c_void_p), ("ln_part", c_void_p), ("ln_colsum", c_void_p),
+                ("ln_eps", c_float)]
+
+
 class ForwardArgs(Structure):
     _fields_ = [
         ("variant", c_int), ("impl", c_int), ("B", c_int), ("T", c_int), ("F", c_int),
@@ -53,6 +59,8 @@ SIGNATURES = {
     "tpat_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "tpat_gemm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_gemm_ln": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                             c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(LnFold), c_void_p]),
     "tpat_attention_qtiles": (c_int, [c_int, c_int]),
     "tpat_attention": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                c_int, c_void_p]),

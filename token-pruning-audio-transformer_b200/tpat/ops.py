@@ -97,6 +97,32 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dty
     return out
 
 
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dtype: torch.dtype, epilogue: int,
+            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, emit: bool = False,
+            ln_part: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-6):
+    """tpat_gemm_ln on the tcgen05 path.  ``emit`` (residual epilogue): also return (xb bf16 [M,N], part [M,N/32,2]).
+    ``ln_part`` / ``ln_colsum`` (bias, bias+GELU epilogues): fold the LayerNorm of the rows of ``a`` into the epilogue."""
+    import ctypes
+    _req(a, torch.bfloat16, "a"); _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    fold = _lib.LnFold()
+    xb = part = None
+    if emit:
+        xb = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+        part = torch.empty(M, N // 32, 2, device=a.device, dtype=torch.float32)
+        fold.xb, fold.ldxb, fold.part_out = xb.data_ptr(), N, part.data_ptr()
+    if ln_part is not None:
+        _req(ln_part, torch.float32, "ln_part"); _req(ln_colsum, torch.float32, "ln_colsum")
+        fold.ln_part, fold.ln_colsum, fold.ln_eps = ln_part.data_ptr(), ln_colsum.data_ptr(), float(ln_eps)
+    check(lib.tpat_gemm_ln(a.data_ptr(), _lib.BF16, K, w.data_ptr(), _lib.BF16, _ptr(bias), out.data_ptr(), _DT[out_dtype], N,
+                           _ptr(residual), N if residual is not None else 0, None, 0, 0, M, N, K, epilogue, _lib.IMPL_TC,
+                           ctypes.byref(fold), _stream()), "tpat_gemm_ln")
+    return (out, xb, part) if emit else out
+
+
 def attention_qtiles(N: int, impl: int) -> int:
     return lib.tpat_attention_qtiles(N, impl)
 
