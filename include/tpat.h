@@ -246,6 +246,12 @@ typedef struct {
   const float* ln2_g; const float* ln2_b;
   const void* fc1_w;  const float* fc1_b;   /* [Dh, D] */
   const void* fc2_w;  const float* fc2_b;   /* [D, Dh] */
+  /* Optional (TPAT_IMPL_TC only; NULL = keep the separate LayerNorm kernels): the LayerNorm fold of tpat_gemm_ln.
+   *   qkv_w_ln = bf16(qkv_w * ln1_g[k]), qkv_colsum[n] = sum_k qkv_w_ln[n, k], qkv_b_ln = qkv_w ln1_b + qkv_b;
+   *   fc1_* likewise with ln2_g / ln2_b.  With them, norm1 of block i > 0 and norm2 of non-pruning blocks cost no
+   *   pass over x: fc2 / proj emit bf16(x) + partial moments, qkv / fc1 normalise in their epilogue. */
+  const void* qkv_w_ln;  const float* qkv_colsum;  const float* qkv_b_ln;
+  const void* fc1_w_ln;  const float* fc1_colsum;  const float* fc1_b_ln;
 } tpat_block_weights;
 
 typedef struct {

@@ -22,7 +22,8 @@ struct Workspace {
   float* partial;     // score partials          [B*R*Nmax]
   float* score_tmp;   // block score when the caller does not ask for it but the fused token needs it [B*Nmax]
   int32_t* rest;      // not-kept token indices (fused token) [B*Nmax]
-  float* pooled;      // [B*D]
+  float* pooled;
+  float* part;      // [B*D]
   size_t bytes;
 };
 
@@ -46,6 +47,15 @@ static int validate(const tpat_forward_args* a) {
   return 0;
 }
 
+// LayerNorm fold (tpat_gemm_ln): norm1 of block i > 0 is folded when the block carries the gamma-scaled qkv weights (the
+// fc2 of block i - 1 then emits bf16(x) + moments); norm2 is folded in blocks that do not prune (the gather comes first).
+static bool fold_ln1(const tpat_forward_args* a, int i) {
+  return a->impl == TPAT_IMPL_TC && i > 0 && i < a->depth && a->blocks[i].qkv_w_ln && a->blocks[i].qkv_colsum && a->blocks[i].qkv_b_ln;
+}
+static bool fold_ln2(const tpat_forward_args* a, int i) {
+  return a->impl == TPAT_IMPL_TC && !a->prune[i] && a->blocks[i].fc1_w_ln && a->blocks[i].fc1_colsum && a->blocks[i].fc1_b_ln;
+}
+
 static Workspace carve(const tpat_forward_args* a, uint8_t* base) {
   const int extra = a->variant == TPAT_VARIANT_AST ? 2 : 1;
   const size_t P = (size_t)(a->T / 16) * (a->F / 16), Nmax = extra + P, B = a->B, D = a->D;
@@ -66,6 +76,7 @@ static Workspace carve(const tpat_forward_args* a, uint8_t* base) {
   w.score_tmp = (float*)take(B * Nmax * 4);
   w.rest = (int32_t*)take(B * Nmax * 4);
   w.pooled = (float*)take(B * D * 4);
+  w.part = (float*)take(B * Nmax * (D / 32) * 2 * 4);   // LayerNorm fold: partial moments of every row of x
   w.bytes = off;
   return w;
 }
@@ -79,17 +90,18 @@ extern "C" size_t tpat_forward_workspace_bytes(const tpat_forward_args* a) {
 
 extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
   if (tpat::validate(a) != 0) return -1;
+  using tpat::fold_ln1; using tpat::fold_ln2;
   int n = 2;  // patchify + patch GEMM
   const int extra = a->variant == TPAT_VARIANT_AST ? 2 : 1;
   int cur = (a->T / 16) * (a->F / 16);
   for (int i = 0; i < a->depth; ++i) {
     const bool prune = a->prune[i] != 0;
     const bool score = prune || a->want_all_scores;
-    n += 4;                                   // LN1, QKV, attention, proj
+    n += fold_ln1(a, i) ? 3 : 4;              // (LN1,) QKV, attention, proj
     // AST score blocks on the tensor-core path: the cls tile (two-pass) and the other tiles are separate launches
     if (score && a->variant == TPAT_VARIANT_AST && a->impl == TPAT_IMPL_TC && tpat_attention_qtiles(extra + cur, a->impl) > 1) n += 1;
     if (score) n += 1;                        // score / top-k
-    n += 3;                                   // (gather+)LN2, fc1, fc2
+    n += fold_ln2(a, i) ? 2 : 3;              // ((gather+)LN2,) fc1, fc2
     if (prune && a->fuse_token && a->keep[i] < cur) { n += 1; cur = a->keep[i] + 1; }   // fused token
     else cur = a->keep[i];
   }
@@ -133,17 +145,29 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
     const bool prune = a->prune[i] != 0;
     const bool want_score = prune || a->want_all_scores;
     float* x = w.x[xi];
-    flip();
-    if (int rc = tpat_layernorm(x, bw.ln1_g, bw.ln1_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
-    flip();
-    if (int rc = tpat_gemm(w.y, act, D, bw.qkv_w, act, bw.qkv_b, w.qkv, act, 3 * D, nullptr, 0, nullptr, 0, 0,
-                           M, 3 * D, D, TPAT_EPI_BIAS, impl, stream)) return rc;
+    if (fold_ln1(a, i)) {
+      // norm1 folded: w.y holds bf16(x) and w.part its row moments (written by the previous block's fc2)
+      const tpat_ln_fold f{nullptr, 0, nullptr, w.part, bw.qkv_colsum, a->ln_eps};
+      flip();
+      if (int rc = tpat_gemm_ln(w.y, act, D, bw.qkv_w_ln, act, bw.qkv_b_ln, w.qkv, act, 3 * D, nullptr, 0, nullptr, 0, 0,
+                                M, 3 * D, D, TPAT_EPI_BIAS, impl, &f, stream)) return rc;
+    } else {
+      flip();
+      if (int rc = tpat_layernorm(x, bw.ln1_g, bw.ln1_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
+      flip();
+      if (int rc = tpat_gemm(w.y, act, D, bw.qkv_w, act, bw.qkv_b, w.qkv, act, 3 * D, nullptr, 0, nullptr, 0, 0,
+                             M, 3 * D, D, TPAT_EPI_BIAS, impl, stream)) return rc;
+    }
     const int smode = !want_score ? TPAT_SCORE_NONE : (ast ? TPAT_SCORE_CLS_ROW : TPAT_SCORE_COLMEAN);
     flip();
     if (int rc = tpat_attention(w.qkv, w.ao, act, w.partial, smode, B, N, H, 64, extra, scale, impl, stream)) return rc;
     flip();
-    if (int rc = tpat_gemm(w.ao, act, D, bw.proj_w, act, bw.proj_b, x, TPAT_F32, D, x, D, nullptr, 0, 0,
-                           M, D, D, TPAT_EPI_BIAS_RESIDUAL, impl, stream)) return rc;
+    {
+      // proj + residual; when norm2 is folded it also emits bf16(x) (into w.y) and the row moments
+      const tpat_ln_fold f{fold_ln2(a, i) ? w.y : nullptr, D, w.part, nullptr, nullptr, 0.f};
+      if (int rc = tpat_gemm_ln(w.ao, act, D, bw.proj_w, act, bw.proj_b, x, TPAT_F32, D, x, D, nullptr, 0, 0,
+                                M, D, D, TPAT_EPI_BIAS_RESIDUAL, impl, &f, stream)) return rc;
+    }
     if (want_score) {
       const int R = ast ? H : H * tpat_attention_qtiles(N, impl);
       const float divisor = ast ? (float)H : (float)H * (float)(N - extra);
@@ -153,7 +177,7 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
                                    fuse_here ? w.rest : nullptr, B, N, extra, prune ? a->keep[i] : 0, stream)) return rc;
     }
     int M2 = M;
-    flip();
+    if (prune || !fold_ln2(a, i)) flip();
     if (prune) {
       float* xn = w.x[xi ^ 1];
       const bool fuse_here = a->fuse_token && a->keep[i] < cur;
@@ -169,15 +193,25 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
       x = xn;
       cur = out_rows - extra;
       M2 = B * out_rows;
-    } else {
+    } else if (!fold_ln2(a, i)) {
       if (int rc = tpat_layernorm(x, bw.ln2_g, bw.ln2_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
     }
     flip();
-    if (int rc = tpat_gemm(w.y, act, D, bw.fc1_w, act, bw.fc1_b, w.hid, act, Dh, nullptr, 0, nullptr, 0, 0,
-                           M2, Dh, D, TPAT_EPI_BIAS_GELU, impl, stream)) return rc;
+    if (fold_ln2(a, i)) {
+      const tpat_ln_fold f{nullptr, 0, nullptr, w.part, bw.fc1_colsum, a->ln_eps};
+      if (int rc = tpat_gemm_ln(w.y, act, D, bw.fc1_w_ln, act, bw.fc1_b_ln, w.hid, act, Dh, nullptr, 0, nullptr, 0, 0,
+                                M2, Dh, D, TPAT_EPI_BIAS_GELU, impl, &f, stream)) return rc;
+    } else {
+      if (int rc = tpat_gemm(w.y, act, D, bw.fc1_w, act, bw.fc1_b, w.hid, act, Dh, nullptr, 0, nullptr, 0, 0,
+                             M2, Dh, D, TPAT_EPI_BIAS_GELU, impl, stream)) return rc;
+    }
     flip();
-    if (int rc = tpat_gemm(w.hid, act, Dh, bw.fc2_w, act, bw.fc2_b, x, TPAT_F32, D, x, D, nullptr, 0, 0,
-                           M2, D, Dh, TPAT_EPI_BIAS_RESIDUAL, impl, stream)) return rc;
+    {
+      // fc2 + residual; emits bf16(x) + moments when the next block's norm1 is folded
+      const tpat_ln_fold f{fold_ln1(a, i + 1) ? w.y : nullptr, D, w.part, nullptr, nullptr, 0.f};
+      if (int rc = tpat_gemm_ln(w.hid, act, Dh, bw.fc2_w, act, bw.fc2_b, x, TPAT_F32, D, x, D, nullptr, 0, 0,
+                                M2, D, Dh, TPAT_EPI_BIAS_RESIDUAL, impl, &f, stream)) return rc;
+    }
   }
 
   // pooled head (models_vit.py:387-389,522 / ast_models.py:500-503); always fp32 CUDA cores (tiny)

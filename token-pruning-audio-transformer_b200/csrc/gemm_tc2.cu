@@ -32,7 +32,7 @@ constexpr int T2R_STAGES = 4;
 constexpr int T2R_STAGING_BYTES = 2 * T2_STAGING_BYTES;
 constexpr int T2R_SMEM_BYTES = T2R_STAGES * T2_STAGE_BYTES + T2R_STAGING_BYTES + 1024 + 512;
 
-template <int EPI, typename OutT, bool RES_TMA>
+template <int EPI, typename OutT, bool RES_TMA, bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_c, const TcGemmParams p) {
@@ -62,6 +62,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_tiles = p.tiles_m * p.tiles_n;   // 256 x 256 tiles
+  // Tile walk: round robin over the clusters (neighbouring clusters share A through L2), or -- for the consumer of a
+  // LayerNorm fold -- one contiguous range per cluster so that consecutive tiles share their row block and the row
+  // moments are combined once per row block instead of once per tile.
+  const bool contig = FOLD && EPI != TPAT_EPI_BIAS_RESIDUAL;
+  const int per_cluster = (num_tiles + num_clusters - 1) / num_clusters;
+  const int tile_first = contig ? cluster_id * per_cluster : cluster_id;
+  const int tile_step = contig ? 1 : num_clusters;
+  const int tile_end = contig ? min(num_tiles, tile_first + per_cluster) : num_tiles;
   const int nkb = p.K / TG_BK;
 
   if (warp == 0 && lane == 0) {
@@ -88,13 +96,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===== TMA producer (both CTAs): own A rows + own half of the W rows, credited to the leader's barrier =====
     if (ptx::elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128;
         const int n0 = (tile % p.tiles_n) * TG_BN + (int)rank * 128;
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full_leader = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
-          const bool first_fill = tile == cluster_id && kb < NSTAGES;
+          const bool first_fill = tile == tile_first && kb < NSTAGES;
           const bool load_a = p.debug_skip != 1 || first_fill;
           const bool load_b = p.debug_skip == 0 || first_fill;
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * ((load_a ? T2_A_BYTES : 0) + (load_b ? T2_B_BYTES : 0)));
@@ -110,7 +118,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(256, TG_BN, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TG_BN;
@@ -137,12 +145,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if constexpr (!kResTma) {
       uint8_t* stg = staging + (warp - 2) * 4096;
       float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512) + (warp - 2) * 32;
-      const bool fold = p.ln_part != nullptr;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int stat_mt = -1;                 // row block whose moments `rowstat` currently holds
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
         TcEpiPrefetch<T2_EPI_WARPS> pf;
         tc_epilogue_prefetch<T2_EPI_WARPS>(p, n0, cg, lane, pf);
-        if (fold) {     // LayerNorm fold: (mean, rstd) of this warp's 32 rows, computed while the MMA is still running
+        if (FOLD && EPI != TPAT_EPI_BIAS_RESIDUAL && tc_tile_m(p, tile) != stat_mt) {
+          // LayerNorm fold: (mean, rstd) of this warp's 32 rows, combined while the MMA is still running
+          stat_mt = tc_tile_m(p, tile);
           __syncwarp();
           rowstat[lane] = m0 + lane < p.M ? ln_row_moments(p.ln_part + (size_t)(m0 + lane) * p.ln_chunks, p.ln_chunks, p.ln_eps)
                                           : make_float2(0.f, 1.f);
@@ -152,8 +162,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         ptx::tc_fence_after();
         const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
         const uint32_t rel_leader = ptx::mapa_shared(ptx::smem_u32(&acc_empty[acc]), 0);
-        tc_epilogue_tile<EPI, OutT, T2_EPI_WARPS>(p, taddr_row, m0, n0, cg, stg, lane, pf, [&]() { if (lane == 0) ptx::mbar_arrive_cluster(rel_leader); },
-                                                  fold ? rowstat : nullptr);
+        tc_epilogue_tile<EPI, OutT, T2_EPI_WARPS, FOLD>(p, taddr_row, m0, n0, cg, stg, lane, pf, [&]() { if (lane == 0) ptx::mbar_arrive_cluster(rel_leader); },
+                                                        rowstat);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else {
@@ -177,8 +187,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       auto store_row = [&](int m0) { return EPI == TPAT_EPI_BIAS_POS ? m0 + (m0 / p.P + 1) * p.num_extra : m0; };
       // first live item at or after (tile, ci) in this warp's walk order; tile >= num_tiles when there is none
       auto next_live = [&](int& tile, int& ci) {
-        while (tile < num_tiles) {
-          if (ci >= NCH) { tile += num_clusters; ci = 0; continue; }
+        while (tile < tile_end) {
+          if (ci >= NCH) { tile += tile_step; ci = 0; continue; }
           if (item_live(tile, ci)) return;
           ++ci;
         }
@@ -190,11 +200,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         ptx::tma_load_2d(stg + b * 4096, &tmap_r, &rb[b], item_cols(tile, ci), load_row(m0));
       };
       {
-        int t0 = cluster_id, c0 = 0;
+        int t0 = tile_first, c0 = 0;
         next_live(t0, c0);
-        if (t0 < num_tiles && lane == 0) issue_load(t0, c0, 0);
+        if (t0 < tile_end && lane == 0) issue_load(t0, c0, 0);
       }
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32;
         const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
         const uint32_t rel_leader = ptx::mapa_shared(ptx::smem_u32(&acc_empty[acc]), 0);
@@ -221,7 +231,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (lane == 0) {                               // prefetch the residual block of this warp's next item
             int nt = tile, nc = ci + 1;
             next_live(nt, nc);
-            if (nt < num_tiles) issue_load(nt, nc, buf ^ 1);
+            if (nt < tile_end) issue_load(nt, nc, buf ^ 1);
           }
           const int n = item_cols(tile, ci);
           ptx::mbar_wait(&rb[buf], buf ? rph1 : rph0);
@@ -238,8 +248,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             r[4 * j] = __float_as_uint(x.x); r[4 * j + 1] = __float_as_uint(x.y);      // keep the row for the fold below
             r[4 * j + 2] = __float_as_uint(x.z); r[4 * j + 3] = __float_as_uint(x.w);
           }
-          if (EPI == TPAT_EPI_BIAS_RESIDUAL && p.xb != nullptr) {
-            // LayerNorm fold, producer side: this thread's 32 new values of row m0 + lane -> bf16 copy + partial moments
+          if constexpr (FOLD && EPI == TPAT_EPI_BIAS_RESIDUAL) {
+            // LayerNorm fold, producer side: partial moments of this thread's 32 new values of row m0 + lane
             float sm = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) sm += __uint_as_float(r[i]);
@@ -247,23 +257,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             float q2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float d = __uint_as_float(r[i]) - mc; q2 = fmaf(d, d, q2); }
-            const int m = m0 + lane;
-            if (m < p.M) {
-              uint4* dst = reinterpret_cast<uint4*>(p.xb + (size_t)m * p.ldxb + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
-                                    pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
-                                    pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
-                                    pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
-              p.part_out[(size_t)m * p.part_ld + (n >> 5)] = make_float2(sm, q2);
-            }
+            if (m0 + lane < p.M) p.part_out[(size_t)(m0 + lane) * p.part_ld + (n >> 5)] = make_float2(sm, q2);
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             ptx::tma_store_2d(&tmap_c, stg + buf * 4096, n, store_row(m0));   // rows >= M are clipped by the tensor map
             ptx::tma_store_commit();
+          }
+          if constexpr (FOLD && EPI == TPAT_EPI_BIAS_RESIDUAL) {
+            // bf16 copy of the block: re-read the swizzled fp32 tile with lanes ALONG the rows (8 lanes = one 64 B row
+            // segment, 4 rows per instruction) so that every global store fills whole 32 B sectors
+            const int jl = lane & 7, rl = lane >> 3;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = it * 4 + rl;
+              const float4 a = *reinterpret_cast<const float4*>(stg + buf * 4096 + row * 128 + ((jl ^ (row & 7)) << 4));
+              if (m0 + row < p.M)
+                *reinterpret_cast<uint2*>(p.xb + (size_t)(m0 + row) * p.ldxb + n + jl * 4) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+            }
           }
           buf ^= 1;
         }
@@ -281,11 +293,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int EPI, typename OutT, bool RES_TMA = false>
+template <int EPI, typename OutT, bool RES_TMA = false, bool FOLD = false>
 static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tr, const CUtensorMap& tc,
                       const TcGemmParams& p, cudaStream_t st) {
   static DeviceOnce once;
-  auto kern = gemm_tc2_kernel<EPI, OutT, RES_TMA>;
+  auto kern = gemm_tc2_kernel<EPI, OutT, RES_TMA, FOLD>;
   constexpr int smem_bytes = (RES_TMA && (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS)) ? T2R_SMEM_BYTES : T2_SMEM_BYTES;
   if (once.first()) TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles = p.tiles_m * p.tiles_n;
@@ -311,19 +323,25 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   { const char* e = getenv("TPAT_GEMM_DEBUG_SKIP"); p.debug_skip = e ? atoi(e) : 0; }
   switch (ep.epilogue) {
     case TPAT_EPI_BIAS:
+      if (p.ln_part != nullptr && c_dtype == TPAT_BF16) return launch_tc2<TPAT_EPI_BIAS, __nv_bfloat16, false, true>(ta, tw, ta, ta, p, st);
+      TPAT_CHECK(p.ln_part == nullptr, "tpat_gemm_ln: the folded GEMM writes bf16");
       return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS, __nv_bfloat16>(ta, tw, ta, ta, p, st) : launch_tc2<TPAT_EPI_BIAS, float>(ta, tw, ta, ta, p, st);
     case TPAT_EPI_BIAS_GELU:
+      if (p.ln_part != nullptr && c_dtype == TPAT_BF16) return launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16, false, true>(ta, tw, ta, ta, p, st);
+      TPAT_CHECK(p.ln_part == nullptr, "tpat_gemm_ln: the folded GEMM writes bf16");
       return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16>(ta, tw, ta, ta, p, st) : launch_tc2<TPAT_EPI_BIAS_GELU, float>(ta, tw, ta, ta, p, st);
     case TPAT_EPI_BIAS_RESIDUAL: {
       // Long-K GEMMs (fc2, K = 3072) hide the register-path epilogue behind the main loop and prefer the fifth
       // pipeline stage; short-K ones (proj, K = 768) are bound by the residual read-modify-write and use the
       // TMA-fed epilogue (measured r01: proj 0.081 -> 0.064 ms, fc2 0.129 -> 0.140 ms with it).
-      if (K > 1536) return launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, false>(ta, tw, ta, ta, p, st);
+      if (K > 1536) return p.xb ? launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, false, true>(ta, tw, ta, ta, p, st)
+                                : launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, false>(ta, tw, ta, ta, p, st);
       // fp32 residual in / C out as 32 x 32 blocks (128 B rows, 128B swizzle)
       CUtensorMap tr, tc;
       if (int rc = encode_tmap_2d(&tr, ep.residual, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldr * 4, 32, 32, true)) return rc;
       if (int rc = encode_tmap_2d(&tc, C, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ldc * 4, 32, 32, true)) return rc;
-      return launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, true>(ta, tw, tr, tc, p, st);
+      return p.xb ? launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, true, true>(ta, tw, tr, tc, p, st)
+                  : launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, true>(ta, tw, tr, tc, p, st);
     }
     case TPAT_EPI_BIAS_POS: {
       // K = 256: the epilogue (fp32 rows out, position rows in) is the whole cost.  When a 32-row block never straddles

@@ -62,13 +62,20 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 // (mean, rstd) of one row from the partial moments of its 32-element chunks (Chan's pairwise update, fixed order)
 __device__ __forceinline__ float2 ln_row_moments(const float2* __restrict__ part, int chunks, float eps) {
   float mean = 0.f, m2 = 0.f, n = 0.f;
-  for (int c = 0; c < chunks; ++c) {
-    const float2 pc = __ldg(part + c);
-    const float mc = pc.x * (1.0f / 32.0f);
-    const float delta = mc - mean, nn = n + 32.0f;
-    mean = fmaf(delta, 32.0f / nn, mean);
-    m2 += pc.y + delta * delta * (n * 32.0f / nn);
-    n = nn;
+  for (int c0 = 0; c0 < chunks; c0 += 8) {        // eight independent loads in flight, then the (sequential) updates
+    float2 pc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pc[u] = c0 + u < chunks ? __ldg(part + c0 + u) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c0 + u < chunks) {
+        const float mc = pc[u].x * (1.0f / 32.0f);
+        const float delta = mc - mean, nn = n + 32.0f;
+        mean = fmaf(delta, 32.0f / nn, mean);
+        m2 += pc[u].y + delta * delta * (n * 32.0f / nn);
+        n = nn;
+      }
+    }
   }
   return make_float2(mean, rsqrtf(m2 / n + eps));
 }
@@ -103,7 +110,7 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmParams& p, int 
 // Per chunk: tcgen05.ld (thread = row) -> XOR-swizzled transpose buffer -> re-read with lanes along
 // the row, so every global access is a full 128 B (fp32) / 64 B (bf16) row segment per 8 lanes.
 // Residual rows are requested before the TMEM read of the chunk so their latency overlaps it.
-template <int EPI, typename OutT, int EW, typename ReleaseFn>
+template <int EPI, typename OutT, int EW, bool FOLD = false, typename ReleaseFn>
 __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t taddr_row, int m0, int n0, int cg,
                                                  uint8_t* stg, int lane, const TcEpiPrefetch<EW>& pf, ReleaseFn release,
                                                  const float2* rowstat = nullptr) {
@@ -158,7 +165,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
     for (int it = 0; it < 8; ++it) {
       const int row = it * 4 + rl;
       const float4 a = *reinterpret_cast<const float4*>(stg + row * 128 + ((jl ^ (row & 7)) << 4));
-      if (rowstat != nullptr) {          // LayerNorm fold: rstd * (acc - mean * colsum) + bias'
+      if constexpr (FOLD && (EPI == TPAT_EPI_BIAS || EPI == TPAT_EPI_BIAS_GELU)) {   // LayerNorm fold: rstd * (acc - mean * colsum) + bias'
         const float2 rs = rowstat[row];
         const float4 cs = pf.colsum[ci];
         v[it] = make_float4(fmaf(rs.y, fmaf(-rs.x, cs.x, a.x), bb.x), fmaf(rs.y, fmaf(-rs.x, cs.y, a.y), bb.y),
@@ -178,8 +185,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
 #pragma unroll
       for (int it = 0; it < 8; ++it) { v[it].x += extra[it].x; v[it].y += extra[it].y; v[it].z += extra[it].z; v[it].w += extra[it].w; }
     }
-    if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
-      if (p.xb != nullptr) {             // LayerNorm fold, producer side: bf16 copy + partial moments of this chunk
+    if constexpr (FOLD && EPI == TPAT_EPI_BIAS_RESIDUAL) {
+      {                                  // LayerNorm fold, producer side: bf16 copy + partial moments of this chunk
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int m = m0 + it * 4 + rl;

@@ -23,7 +23,8 @@ VARIANT_AUDIOMAE, VARIANT_AST = 0, 1
 
 class BlockWeights(Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+        "ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+        "qkv_w_ln", "qkv_colsum", "qkv_b_ln", "fc1_w_ln", "fc1_colsum", "fc1_b_ln")]
 
 
 class LnFold(Structure):

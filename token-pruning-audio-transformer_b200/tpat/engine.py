@@ -66,6 +66,12 @@ class ForwardEngine:
         self.variant, self.depth, self.D, self.H, self.Dh = variant, depth, D, H, Dh
         self.num_extra = 2 if variant == _lib.VARIANT_AST else 1
         self._pack_key = None
+        self._fold: Dict[int, Dict[str, torch.Tensor]] = {}
+        # LayerNorm fold (tpat_gemm_ln, bf16 path): "0" off (default), "qkv" norm1 -> qkv only, "all" norm1 and norm2.
+        # Measured r01f (B = 64): the 20 LayerNorm launches it removes (0.39 ms) are paid back by the producer's extra
+        # bf16 write + moments (proj +16 us, fc2 +13 us) and the consumer epilogues (qkv +10 us, fc1 +20 us: the GELU
+        # epilogue has no slack) -- 5.01 vs 4.87 ms per step for "all", no measurable change for "qkv" -> off.
+        self.ln_fold = os.environ.get("TPAT_LN_FOLD", "0")
         self._packed: Dict[str, object] = {}
         self._bf16: Dict[int, torch.Tensor] = {}
         self._workspace: Optional[torch.Tensor] = None
@@ -96,6 +102,7 @@ class ForwardEngine:
         for k in ("norm_g", "norm_b", "head_ln_g", "head_ln_b", "head_w", "head_b"):
             pk[k] = f(tensors[k]) if tensors.get(k) is not None else None
         self._packed = pk
+        self._fold = {}
         self._bf16 = {}
         self._graphs = {}
         self._pack_key = key
@@ -108,6 +115,21 @@ class ForwardEngine:
             c = t.to(torch.bfloat16).contiguous()
             self._bf16[id(t)] = c
         return c
+
+    def _folded(self, i: int) -> Dict[str, torch.Tensor]:
+        """Weights of the LayerNorm fold for block i (tpat_gemm_ln): W' = bf16(W * gamma), colsum = sum_k W', b' = W beta + b."""
+        f = self._fold.get(i)
+        if f is None:
+            blk = self._packed["blocks"][i]
+            f = {}
+            for name, g, b in (("qkv", "ln1_g", "ln1_b"), ("fc1", "ln2_g", "ln2_b")):
+                w = blk[name + "_w"]
+                wl = (w * blk[g][None, :]).to(torch.bfloat16).contiguous()
+                f[name + "_w_ln"] = wl
+                f[name + "_colsum"] = wl.float().sum(dim=1).contiguous()
+                f[name + "_b_ln"] = (w @ blk[b] + blk[name + "_b"]).contiguous()
+            self._fold[i] = f
+        return f
 
     # ---- one forward ---------------------------------------------------------------------
     def _fill_args(self, spec, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, workspace,
@@ -132,6 +154,10 @@ class ForwardEngine:
                 setattr(bw, name, blk[name].data_ptr())
             for name in ("qkv_w", "proj_w", "fc1_w", "fc2_w"):
                 setattr(bw, name, self._mat(blk[name], impl).data_ptr())
+            if impl == _lib.IMPL_TC and self.ln_fold in ("qkv", "all"):
+                for name, t in self._folded(i).items():
+                    if self.ln_fold == "all" or name.startswith("qkv"):
+                        setattr(bw, name, t.data_ptr())
         a.norm_g, a.norm_b, a.norm_eps = pk["norm_g"].data_ptr(), pk["norm_b"].data_ptr(), 1e-6
         if pk["head_ln_g"] is not None:
             a.head_ln_g, a.head_ln_b, a.head_ln_eps = pk["head_ln_g"].data_ptr(), pk["head_ln_b"].data_ptr(), 1e-5
