@@ -135,6 +135,31 @@ def test_forward_bf16_against_reference_golden(name):
     assert err < (3e-2 if all(o == 1.0 for o in overlaps) else 1e-1)
 
 
+@pytest.mark.parametrize("name", ["ast_spc2_b4_unpruned", "audiomae_1024_b2_kr07_pert", "audiomae_256_b3_list"])
+def test_forward_bf16_with_layernorm_fold(name):
+    """The LayerNorm fold (tpat_gemm_ln through tpat_forward, off by default) gives the same forward within the bf16
+    tolerances: no separate LayerNorm launch for norm1 of blocks > 0 and norm2 of non-pruning blocks."""
+    g = load_golden(name)
+    meta, f64 = g["meta"], g["f64"]
+    sd, x = make_case(meta)
+    plain = build_model(meta, sd, "bf16")
+    folded = build_model(meta, sd, "bf16")
+    folded._engine.ln_fold = "all"
+    with torch.no_grad():
+        a = plain(x.to(dev()), keep_rate_list=meta["keep_rate_list"])
+        n_plain = plain._engine.last_launch_count
+        b = folded(x.to(dev()), keep_rate_list=meta["keep_rate_list"])
+        n_fold = folded._engine.last_launch_count
+    ia = [t for t in plain.last_topk_idx if t is not None]
+    ib = [t for t in folded.last_topk_idx if t is not None]
+    same_tokens = all(torch.equal(p.sort(1).values, q.sort(1).values) for p, q in zip(ia, ib))
+    ea, eb = rel_err(a.cpu(), f64["logits"]), rel_err(b.cpu(), f64["logits"])
+    print(f"[ln fold] {name}: launches {n_plain} -> {n_fold}, logits err vs fp64 {ea:.2e} (plain) {eb:.2e} (folded), same kept sets: {same_tokens}")
+    n_prune = len(ia)
+    assert n_fold == n_plain - (11 + 12 - n_prune)
+    assert eb < (3e-2 if same_tokens else 1e-1)
+
+
 def test_forward_is_deterministic_and_batch_invariant():
     """Full-size property (BASELINE configs[1] shape, B=64): the same clip gives bit-identical
     logits and indices run to run and regardless of which batch it sits in (no atomics, fixed
