@@ -28,6 +28,12 @@ GOLDEN_CONFIGS = {
                                  base_keep_rate=0.7,
                                  keep_rate_list=(0.9, 1.0, 0.61, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0, 1.0, 1.0, 0.8),
                                  flavour="perturbed", wseed=4, xseed=11),
+    # "trained" weight statistics (peaked attention, outlier channels): the regime in which the north-star bf16 bar
+    # (>= 99.9 % kept-set overlap, 1e-2 logits) is meaningful -- random-init weights give near-uniform scores
+    "audiomae_1024_b4_kr07_trained": dict(variant="audiomae", T=1024, B=4, num_classes=527, drop_loc=(3, 6, 9),
+                                          base_keep_rate=0.7, keep_rate_list=None, flavour="trained", wseed=6, xseed=21),
+    "ast_1024_b4_kr07_trained": dict(variant="ast", T=1024, B=4, num_classes=527, drop_loc=(3, 6, 9),
+                                     base_keep_rate=0.7, keep_rate_list=None, flavour="trained", wseed=7, xseed=22),
     # unpruned (keep 1.0 everywhere): the unpruned baseline arm of configs[2]/[4]
     "ast_spc2_b4_unpruned": dict(variant="ast", T=128, B=4, num_classes=35, drop_loc=(),
                                  base_keep_rate=1.0, keep_rate_list=None, flavour="perturbed", wseed=5, xseed=3),

@@ -12,6 +12,10 @@ Two flavours:
     The headline bench and the BASELINE parity configs use this.
   * ``perturbed`` -- same, but biases ~ N(0, .02), LayerNorm weight 1+N(0,.1) / bias N(0,.05) so
     that every bias / affine term is exercised by the parity tests.
+  * ``trained``   -- ``perturbed`` reshaped towards the statistics of a fine-tuned checkpoint: q / k weights x 3.2
+    (attention logits of std ~ 3 instead of 0.3: peaked attention, importance scores that are NOT near-uniform, so
+    the top-k cut is not a field of near-ties), larger proj / MLP weights, LayerNorm gains spread log-normally, and
+    three outlier channels in the position table (the "massive activations" of trained ViTs).
 
 Key names and shapes follow the reference state-dicts.
 """
@@ -55,11 +59,27 @@ def _conv(sd, prefix, gen, dim):
     sd[f"{prefix}.bias"] = (torch.rand((dim,), generator=gen) * 2 - 1) * bound
 
 
+def _trainedlike(sd, prefix, pos_key, seed, depth, dim):
+    gen = torch.Generator().manual_seed(seed + 100003)
+    for i in range(depth):
+        b = f"{prefix}blocks.{i}."
+        sd[b + "attn.qkv.weight"][: 2 * dim] *= 3.2            # q and k rows
+        sd[b + "attn.qkv.bias"][: 2 * dim] *= 3.2
+        sd[b + "attn.proj.weight"] *= 2.0
+        sd[b + "mlp.fc1.weight"] *= 2.0
+        sd[b + "mlp.fc2.weight"] *= 1.5
+        for n in ("norm1", "norm2"):
+            sd[b + n + ".weight"] = sd[b + n + ".weight"] * torch.exp(0.3 * torch.randn(dim, generator=gen))
+    for ch, v in ((7, 8.0), (300, -6.0), (511, 10.0)):
+        sd[pos_key][..., ch] += v
+    return sd
+
+
 def make_audiomae_state_dict(num_classes=527, target_length=1024, seed=0, flavour="refinit",
                              depth=12, dim=768, mlp_ratio=4):
     """Keys as audiomae/models_vit.py VisionTransformer after main_finetune.py:374-382."""
-    assert flavour in ("refinit", "perturbed")
-    p = flavour == "perturbed"
+    assert flavour in ("refinit", "perturbed", "trained")
+    p = flavour != "refinit"
     gen = torch.Generator().manual_seed(seed)
     n_patches = (target_length // 16) * (128 // 16)
     sd = {}
@@ -72,14 +92,16 @@ def make_audiomae_state_dict(num_classes=527, target_length=1024, seed=0, flavou
     sd["fc_norm.bias"] = _n(gen, (dim,), 0.05) if p else torch.zeros(dim)
     sd["head.weight"] = _tn(gen, (num_classes, dim))
     sd["head.bias"] = _n(gen, (num_classes,), 0.02) if p else torch.zeros(num_classes)
+    if flavour == "trained":
+        _trainedlike(sd, "", "pos_embed", seed, depth, dim)
     return sd
 
 
 def make_ast_state_dict(label_dim=527, input_tdim=1024, seed=0, flavour="refinit",
                         depth=12, dim=768, mlp_ratio=4):
     """Keys as ast/src/models/ast_models.py ASTModel (the subset its forward uses)."""
-    assert flavour in ("refinit", "perturbed")
-    p = flavour == "perturbed"
+    assert flavour in ("refinit", "perturbed", "trained")
+    p = flavour != "refinit"
     gen = torch.Generator().manual_seed(seed)
     n_patches = (input_tdim // 16) * (128 // 16)
     sd = {}
@@ -95,6 +117,8 @@ def make_ast_state_dict(label_dim=527, input_tdim=1024, seed=0, flavour="refinit
     sd["mlp_head.0.bias"] = _n(gen, (dim,), 0.05) if p else torch.zeros(dim)
     sd["mlp_head.1.weight"] = _tn(gen, (label_dim, dim))
     sd["mlp_head.1.bias"] = _n(gen, (label_dim,), 0.02) if p else torch.zeros(label_dim)
+    if flavour == "trained":
+        _trainedlike(sd, "v.", "v.pos_embed", seed, depth, dim)
     return sd
 
 

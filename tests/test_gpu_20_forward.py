@@ -119,17 +119,22 @@ def test_forward_bf16_against_reference_golden(name):
     s0 = rel_err(feats["block-0.attn_score"], f64["block-0.attn_score"])
     print(f"[bf16] {name}: kept-set overlap vs fp64 {['%.4f' % o for o in overlaps]}, logits err {err:.2e}, "
           f"block-0 score err {s0:.2e}")
-    assert s0 < 5e-3
+    # near-uniform scores (random-init weights): 5e-3; peaked attention ("trained" statistics, logits of std ~3): the bf16
+    # rounding of q / k moves individual probabilities by a few per cent and the score by < 1.5e-2 of its maximum
+    assert s0 < (1.5e-2 if meta["flavour"] == "trained" else 5e-3)
     if blocks:
         # first pruning block sees the same tokens on both sides: mismatches must be near-ties at the cut
         b0 = blocks[0]
         sc = f64[f"block-{b0}.attn_score"]
         kk = f64[f"block-{b0}.topk_idx"].shape[1]
+        # ... i.e. closer to the cut than 1 % of it or than twice the largest score error of this block (the flipped
+        # token and the token at the cut can each be off by that much)
+        max_abs = (feats[f"block-{b0}.attn_score"].double() - sc).abs().max().item()
         for c in range(sc.shape[0]):
             cut = torch.sort(sc[c], descending=True).values[kk - 1].item()
             diff = set(feats[f"block-{b0}.topk_idx"][c].tolist()) ^ set(f64[f"block-{b0}.topk_idx"][c].tolist())
             for tkn in diff:
-                assert abs(sc[c, tkn].item() - cut) <= 1e-2 * abs(cut), (b0, c, tkn)
+                assert abs(sc[c, tkn].item() - cut) <= max(1e-2 * abs(cut), 2.0 * max_abs), (b0, c, tkn)
         for o, e in zip(overlaps, exp):
             assert o >= 1.0 - max(0.03, 3.0 / e.shape[1]), (overlaps,)
     assert err < (3e-2 if all(o == 1.0 for o in overlaps) else 1e-1)
