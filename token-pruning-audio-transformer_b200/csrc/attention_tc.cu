@@ -2,12 +2,13 @@
 //
 // Replaces q k^T * scale, softmax, attn @ v and the score slice/mean over the materialised
 // [B,H,N,N] matrix (reference audiomae/models_vit.py:79-95,113; ast/src/models/ast_models.py:92-109,124).
-// One CTA per (clip, head, 128-query tile), two CTAs resident per SM (<= 113 KB smem, 256 TMEM
-// columns each) so one CTA's softmax hides the other's prologue / MMA round trips.  320 threads:
+// One CTA per (clip, head, 128-query tile), two CTAs resident per SM (~68 KB smem, 256 TMEM
+// columns each: S0 S1 | O | P0 P1) so one CTA's softmax hides the other's prologue / MMA round trips.  320 threads:
 //   warp 0   TMA producer: Q tile once, then K / V 64-key tiles into a 6-slot 8 KB ring
 //            (3-D tensor maps over qkv[B][N][3*H*64]: rows >= N are zero-filled, never the next clip)
 //   warp 1   MMA issuer (one elected thread): S = Q K^T (M=128,N=64,K=64) into one of two TMEM
-//            buffers; O += P V (M=128,N=64,K<=64) with P from 128B-swizzled smem, V as MN-major B
+//            buffers; O += P V (M=128,N=64,K<=64) with P read from TENSOR MEMORY (tcgen05.mma, A operand in TMEM:
+//            the softmax warps tcgen05.st their bf16 pairs there), V as MN-major B from the TMA tile
 //   warps 2-9 softmax: thread = (query row = TMEM lane, 32-key half); warps w and w+4 share a row quarter and
 //            split each 64-key block by columns (four softmax warps per SM sub-partition with two CTAs resident).
 //
@@ -23,7 +24,7 @@
 //            2^64 is m_ref raised, O (TMEM) and the running sum rescaled by the softmax warp itself and the
 //            tile redone.  P stays <= 2^64 (exact in bf16 / fp32 range).  O is divided by the row sum at the
 //            end.  One exp and one QK^T per element, K streamed once.
-// The N x N matrix never leaves the SM; O leaves through one TMA store.
+// The N x N matrix never leaves the SM; O leaves through one TMA store staged in the (dead) Q tile.
 #include "attention.cuh"
 #include "ptx_sm100.cuh"
 
@@ -46,10 +47,6 @@ constexpr int AT_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps
 constexpr int AT_TMEM_COLS = 256;   // S0, S1 [0, 128), O [128, 192), P0, P1 (bf16 pairs) [192, 256)
 constexpr int AT_SMEM_LIMIT = 227 * 1024;   // hard cap; <= 113 KB keeps two CTAs per SM (N <= 960 with the column-sum buffer)
 constexpr float AT_RESCALE_LOG2 = 64.0f;  // online softmax: the reference max is only raised past 2^64 (then the tile is redone)
-#ifndef AT_POLY_EVERY
-#define AT_POLY_EVERY 0                   // every AT_POLY_EVERY-th probability of a full single-pass tile uses exp2_poly (0 = none;
-                                          // measured r01: 2/4/8 are all SLOWER than 0 -- the kernel is latency-, not MUFU-bound)
-#endif
 
 #ifdef TPAT_ATTN_TRACE
 #define ATTN_TRACE(slot) do { if (tracing && trace_n < 120) p.trace[trace_n++] = clock64() - t_start + ((long long)(slot) << 48); } while (0)
@@ -73,20 +70,6 @@ __device__ __forceinline__ void store_p_half(uint8_t* p_row, int hf, int r_local
     *reinterpret_cast<uint4*>(p_row + (((hf * 4 + g) ^ (r_local & 7)) * 16)) =
         make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
                    pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
-}
-
-// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic minimax for 2^f
-// (relative error <= 2.4e-4, far below the bf16 rounding of P), exponent n added into the float's bits.
-// Used for every other probability of the single-pass tiles so that the 16-lane/clk MUFU.EX2 pipe and the
-// FMA pipes work in parallel (the exp count, not the tensor core, bounds this kernel).
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;          // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.0574900442f, 0.242630517f);
-  p = fmaf(p, f, 0.692895364f);
-  p = fmaf(p, f, 0.999916112f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
 template <bool TWO_PASS>
@@ -362,10 +345,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = fmaf(__uint_as_float(r[i]), c, -off);                                   // -inf -> 0
-          v[i] = (AT_POLY_EVERY > 0 && (i % (AT_POLY_EVERY > 0 ? AT_POLY_EVERY : 1)) == AT_POLY_EVERY - 1) ? exp2_poly(x) : ptx::ex2_ftz(x);
-        }
+        for (int i = 0; i < 32; ++i) v[i] = ptx::ex2_ftz(fmaf(__uint_as_float(r[i]), c, -off));   // -inf -> 0
         if (!TWO_PASS) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) { l2a += v[i]; l2b += v[i + 1]; l2c += v[i + 2]; l2d += v[i + 3]; }
