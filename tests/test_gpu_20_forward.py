@@ -206,6 +206,23 @@ def test_cuda_graph_path_matches_eager_launches():
     assert torch.equal(eager, graphed) and all(torch.equal(p, q) for p, q in zip(idx_e, idx_g))
 
 
+def test_model_on_a_second_device_runs_there():
+    """One process driving two GPUs (the reference's nn.DataParallel layout): the forward runs on the input's device,
+    not on the current one, and gives the same bits as on device 0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = load_golden("ast_spc2_b8_kr07")
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    m0 = build_model(meta, sd, "bf16")
+    m1 = build_model(meta, sd, "bf16").to("cuda:1")
+    with torch.no_grad():
+        a = m0(x.to("cuda:0"))
+        assert torch.cuda.current_device() == 0
+        b = m1(x.to("cuda:1"))
+    assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())
+
+
 def test_weights_are_repacked_after_an_update():
     g = load_golden("ast_spc2_b4_unpruned")
     meta = g["meta"]

@@ -193,11 +193,17 @@ class ForwardEngine:
             self._graphs = {}
         return self._workspace
 
-    def run(self, spec: torch.Tensor, keep_rates: Sequence[float], num_classes: int, want_all_scores: bool = False,
-            precision: str = "bf16", use_graph: bool = False, fuse_token: bool = False):
-        """spec [B,T,F] fp32 CUDA.  Returns (logits [B,C], scores list, topk_idx list) -- device tensors."""
+    def run(self, spec: torch.Tensor, *args, **kwargs):
+        """spec [B,T,F] fp32 CUDA.  Returns (logits [B,C], scores list, topk_idx list) -- device tensors.
+        Runs on the INPUT's device and that device's current stream (as a torch op would), so one process can drive
+        several GPUs (the reference's nn.DataParallel replicas)."""
         if not spec.is_cuda:
             raise RuntimeError("tpat: input must be a CUDA tensor; there is no CPU path")
+        with torch.cuda.device(spec.device):
+            return self._run(spec, *args, **kwargs)
+
+    def _run(self, spec: torch.Tensor, keep_rates: Sequence[float], num_classes: int, want_all_scores: bool = False,
+             precision: str = "bf16", use_graph: bool = False, fuse_token: bool = False):
         if not lib.tpat_device_ok():
             raise RuntimeError("tpat: the current device is not compute capability 10.x (B200, sm_100a)")
         if spec.dtype != torch.float32 or not spec.is_contiguous():
@@ -243,10 +249,17 @@ class ForwardEngine:
                 [None if t is None else t.clone() for t in idxs])
 
     # ---- kernel-by-kernel forward: ablation and masking paths -------------------------------
-    def run_stepwise(self, spec: torch.Tensor, keep_rates: Sequence[float], num_classes: int, precision: str = "bf16",
-                     use_custom_rank: Optional[str] = None, drop_token_blk_idx: Optional[int] = None,
-                     retain_min: Optional[float] = None, retain_max: Optional[float] = None,
-                     mask_keep_idx: Optional[torch.Tensor] = None):
+    def run_stepwise(self, spec: torch.Tensor, *args, **kwargs):
+        """Device-guarded entry of ``_run_stepwise`` (see there)."""
+        if not spec.is_cuda:
+            raise RuntimeError("tpat: input must be a CUDA tensor; there is no CPU path")
+        with torch.cuda.device(spec.device):
+            return self._run_stepwise(spec, *args, **kwargs)
+
+    def _run_stepwise(self, spec: torch.Tensor, keep_rates: Sequence[float], num_classes: int, precision: str = "bf16",
+                      use_custom_rank: Optional[str] = None, drop_token_blk_idx: Optional[int] = None,
+                      retain_min: Optional[float] = None, retain_max: Optional[float] = None,
+                      mask_keep_idx: Optional[torch.Tensor] = None):
         """The forward assembled from the per-kernel entry points, for the paths whose token flow the fused
         ``tpat_forward`` does not cover:
 

@@ -80,6 +80,10 @@ class FbankFrontend:
             raise RuntimeError("tpat: the front end takes CUDA tensors; there is no CPU path")
         if wave.dim() != 2 or wave.dtype != torch.float32 or not wave.is_contiguous():
             raise RuntimeError("wave must be a contiguous fp32 [B, L] tensor (mono)")
+        with torch.cuda.device(wave.device):
+            return self._call(wave, lengths)
+
+    def _call(self, wave: torch.Tensor, lengths: Optional[torch.Tensor]) -> torch.Tensor:
         B, L = wave.shape
         w, mel, ms, ml = self._tables(wave.device)
         if lengths is not None:
