@@ -241,6 +241,8 @@ class ForwardEngine:
             with torch.cuda.graph(g):
                 check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
             ent = (g, static_in, logits, scores, idxs, ws)
+            if len(self._graphs) >= 8:                       # bounded cache: drop the oldest captured schedule
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
         g, static_in, logits, scores, idxs, _ = ent
         static_in.copy_(spec)
