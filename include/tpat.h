@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 5
+#define TPAT_VERSION 6
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -279,6 +279,9 @@ typedef struct {
   float* scores[TPAT_MAX_DEPTH];     /* [B, n_i] fp32 or NULL (n_i = non-extra tokens entering block i) */
   int64_t* topk_idx[TPAT_MAX_DEPTH]; /* [B, keep[i]] int64; required where prune[i]                  */
   void* workspace; size_t workspace_bytes;
+  float* pooled;              /* optional [B, D] fp32: the classifier input (AudioMAE: fc_norm(mean of tokens 1:),
+                                 i.e. what forward_features returns, models_vit.py:387-389; AST: mlp_head.0 of the
+                                 (cls + dist) / 2 of v.norm) -- NULL: kept in the workspace only */
 } tpat_forward_args;
 
 /* sizeof(tpat_forward_args) as compiled into the library (lets a foreign-language binding verify its struct layout) */

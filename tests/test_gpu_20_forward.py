@@ -223,6 +223,22 @@ def test_model_on_a_second_device_runs_there():
     assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())
 
 
+def test_forward_features_returns_the_classifier_input():
+    """models_vit.py:334-396: forward_features = fc_norm(mean of the patch tokens) after the pruned blocks."""
+    g = load_golden("audiomae_256_b3_list")
+    meta = g["meta"]
+    sd, x = make_case(meta)
+    model = build_model(meta, sd, "fp32")
+    with torch.no_grad():
+        feats = model.forward_features(x.to(dev()), keep_rate_list=meta["keep_rate_list"])
+        logits = model(x.to(dev()), keep_rate_list=meta["keep_rate_list"])
+        _, _, pooled = vo.forward("audiomae", sd, x, meta["keep_rate_list"], meta["drop_loc"], meta["base_keep_rate"],
+                                  return_pooled=True)
+    assert tuple(feats.shape) == (3, 768)
+    assert rel_err(feats.cpu(), pooled) < 2e-5
+    assert rel_err((feats @ model.head.weight.T + model.head.bias).cpu(), logits.cpu()) < 1e-5
+
+
 def test_weights_are_repacked_after_an_update():
     g = load_golden("ast_spc2_b4_unpruned")
     meta = g["meta"]

@@ -215,7 +215,8 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
   }
 
   // pooled head (models_vit.py:387-389,522 / ast_models.py:500-503); always fp32 CUDA cores (tiny)
-  if (int rc = tpat_pool_norm(w.x[xi], w.pooled, a->norm_g, a->norm_b, a->norm_eps, a->head_ln_g, a->head_ln_b,
+  float* pooled = a->pooled ? a->pooled : w.pooled;
+  if (int rc = tpat_pool_norm(w.x[xi], pooled, a->norm_g, a->norm_b, a->norm_eps, a->head_ln_g, a->head_ln_b,
                               a->head_ln_eps, B, extra + cur, D, a->variant, stream)) return rc;
-  return tpat_head(w.pooled, a->head_w, a->head_b, a->logits, B, D, a->num_classes, stream);
+  return tpat_head(pooled, a->head_w, a->head_b, a->logits, B, D, a->num_classes, stream);
 }

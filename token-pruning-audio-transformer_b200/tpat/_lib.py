@@ -47,6 +47,7 @@ class ForwardArgs(Structure):
         ("spec", c_void_p), ("logits", c_void_p),
         ("scores", c_void_p * TPAT_MAX_DEPTH), ("topk_idx", c_void_p * TPAT_MAX_DEPTH),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("pooled", c_void_p),
     ]
 
 

@@ -77,6 +77,7 @@ class ForwardEngine:
         self._workspace: Optional[torch.Tensor] = None
         self._graphs: Dict[tuple, tuple] = {}
         self.last_launch_count = 0
+        self.last_pooled: Optional[torch.Tensor] = None
 
     # ---- weights -------------------------------------------------------------------------
     @staticmethod
@@ -217,8 +218,11 @@ class ForwardEngine:
         args = self._fill_args(spec, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, None, fuse_token)
         ws = self._ensure_workspace(args, spec.device)
         args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        pooled = torch.empty(B, self.D, device=spec.device, dtype=torch.float32)
+        args.pooled = pooled.data_ptr()
         self.last_launch_count = lib.tpat_forward_launch_count(ctypes.byref(args))
         check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
+        self.last_pooled = pooled                            # the classifier input (forward_features' return value)
         return logits, scores, idxs
 
     def _run_graph(self, spec, prune, keep, want_all_scores, impl, num_classes, fuse_token=False):
@@ -233,6 +237,8 @@ class ForwardEngine:
                                    fuse_token)
             ws = self._ensure_workspace(args, spec.device)
             args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+            pooled = torch.empty(spec.shape[0], self.D, device=spec.device, dtype=torch.float32)
+            args.pooled = pooled.data_ptr()
             self.last_launch_count = lib.tpat_forward_launch_count(ctypes.byref(args))
             # warm-up outside capture (function attributes, tensor-map cache), then capture
             check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
@@ -240,13 +246,14 @@ class ForwardEngine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
-            ent = (g, static_in, logits, scores, idxs, ws)
+            ent = (g, static_in, logits, scores, idxs, ws, pooled)
             if len(self._graphs) >= 8:                       # bounded cache: drop the oldest captured schedule
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
-        g, static_in, logits, scores, idxs, _ = ent
+        g, static_in, logits, scores, idxs, _, pooled = ent
         static_in.copy_(spec)
         g.replay()
+        self.last_pooled = pooled.clone()
         return (logits.clone(), [None if s is None else s.clone() for s in scores],
                 [None if t is None else t.clone() for t in idxs])
 

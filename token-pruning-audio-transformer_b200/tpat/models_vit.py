@@ -237,9 +237,16 @@ class VisionTransformer(nn.Module):
         return (ids_t[:, :, None] * F + ids_f[:, None, :]).reshape(B, len_keep_T * len_keep_F).contiguous()
 
     def forward_features(self, x, keep_rate_list=None, flag_extract_features: bool = False):
-        """Kept for API parity; returns what forward returns before the head is NOT available
-        separately (the head is fused into the native call) -- use forward."""
-        raise NotImplementedError("use forward(); the pooled features are not materialised separately")
+        """``fc_norm(x[:, 1:].mean(1))`` after the 12 blocks (models_vit.py:334-396): the classifier input, [B, D] fp32 --
+        or ``(outcome, feature_dict)`` in extract mode.  Computed by the same native call as ``forward`` (the head GEMM
+        also runs; its logits are discarded)."""
+        out = self.forward(x, keep_rate_list, flag_extract_features=flag_extract_features)
+        if out is None:
+            return None
+        if self.use_custom_rank is not None or self.drop_token_blk_idx is not None:
+            raise NotImplementedError("forward_features on the ablation paths: use forward()")
+        pooled = self._engine.last_pooled
+        return (pooled, out[1]) if flag_extract_features else pooled
 
     def forward(self, x, keep_rate_list: Union[list, tuple, type(None)] = None, mask_t_prob=0.0, mask_f_prob=0.0,
                 flag_extract_features: bool = False):
