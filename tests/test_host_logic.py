@@ -82,6 +82,16 @@ def test_masking_indices_follow_reference_construction():
     assert torch.equal(keep_idx, vo.masking_2d_keep_indices(noise[0], noise[1], 0.3, 0.25))
 
 
+def test_keep_rate_schedule_matches_reference_golden():
+    """engine_finetune.py:29-53: all-ones before the shrink phase, half-cosine descent during it, None afterwards;
+    golden values produced by the reference function itself (tests/golden/keep_rate_schedule.pt)."""
+    from conftest import load_golden
+    from tpat.schedule import get_scheduled_keep_rate_list
+    for kwargs, want in load_golden("keep_rate_schedule")["cases"]:
+        got = get_scheduled_keep_rate_list(**kwargs)
+        assert got == want, (kwargs, got, want)
+
+
 def test_precision_selection():
     assert build_audiomae(T=128, C=10).precision == "bf16"
     assert build_audiomae(T=128, C=10, precision="fp32").precision == "fp32"
