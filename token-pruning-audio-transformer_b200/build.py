@@ -39,6 +39,14 @@ def build(force: bool = False, verbose: bool = True) -> str:
     headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     headers.append(os.path.join(INCLUDE, "tpat.h"))
     hdr_digest = _digest(headers, " ".join(FLAGS))
+    # library-level stamp: the .so shipped to the GPU box (the object directory does not travel) is reused as is when
+    # no source, header or flag changed
+    lib_stamp = LIB_PATH + ".sha"
+    lib_want = _digest(sources, hdr_digest)
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(lib_stamp) and open(lib_stamp).read() == lib_want:
+        if verbose:
+            print(f"[tpat build] {LIB_PATH} (up to date; {len(sources)} sources)")
+        return LIB_PATH
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
@@ -63,6 +71,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(lib_stamp, "w") as f:
+        f.write(lib_want)
     if verbose:
         print(f"[tpat build] {LIB_PATH} ({'rebuilt' if rebuilt else 'up to date'}; {len(objs)} objects)")
     return LIB_PATH
