@@ -27,7 +27,7 @@ def _digest(paths, extra=""):
     h = hashlib.sha256(extra.encode())
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())     # not the full path: the repo lives elsewhere on the GPU box
             h.update(f.read())
     return h.hexdigest()
 
