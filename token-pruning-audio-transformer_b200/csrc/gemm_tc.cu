@@ -177,10 +177,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (ptx::elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = tc_tile_m(p, tile) * TG_BM, n0 = (tile % p.tiles_n) * TG_BN;
+        const int m0 = tc_tile_m(p, tile) * TG_BM, n0 = (tile % p.tiles_n) * p.bn;
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], TG_STAGE_BYTES);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], TG_A_BYTES + p.bn * TG_BK * 2);
           ptx::tma_load_2d(smem_a + stage * TG_A_BYTES, &tmap_a, &full_bar[stage], kb * TG_BK, m0);
           ptx::tma_load_2d(smem_b + stage * TG_B_BYTES, &tmap_w, &full_bar[stage], kb * TG_BK, n0);
           if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
@@ -190,7 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(TG_BM, TG_BN, 0, 0);
+      const uint32_t idesc = ptx::idesc_bf16_f32(TG_BM, p.bn, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -221,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* stg = staging + (warp - 2) * 4096;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = tc_tile_m(p, tile) * TG_BM + q * 32, n0 = (tile % p.tiles_n) * TG_BN;
+      const int m0 = tc_tile_m(p, tile) * TG_BM + q * 32, n0 = (tile % p.tiles_n) * p.bn;
       TcEpiPrefetch<TG_EPI_WARPS> pf;
       tc_epilogue_prefetch<TG_EPI_WARPS>(p, n0, cg, lane, pf);
       ptx::mbar_wait(&acc_full[acc], acc_phase);
@@ -267,16 +267,30 @@ int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc
     // CTA-pair kernel (cta_group::2) unless TPAT_GEMM_2CTA=0; read per call so tests can A/B both kernels
     const char* e = getenv("TPAT_GEMM_2CTA");
     const bool two_cta = e == nullptr || e[0] != '0';
-    if (two_cta && sm_count() >= 2) return gemm_tc2(A, lda, W, C, c_dtype, ldc, M, N, K, ep, st);
+    // Small batches (M <= 3072 rows, i.e. up to ~6 clips of 513 tokens): a 256 x 256 tile per CTA pair leaves most SMs
+    // idle and its K loop alone is 3 us; the 1-CTA kernel with 128 x 128 / 128 x 64 tiles spreads the work over the whole
+    // chip (measured r01g, CUDA-graph replay: B = 1 0.95 -> 0.72 ms, B = 4 1.01 -> 0.85 ms; TPAT_GEMM_SMALL_M moves the
+    // threshold, TPAT_GEMM_NO_SMALL=1 disables it).
+    static const bool small_off = getenv("TPAT_GEMM_NO_SMALL") != nullptr;
+    static const int small_m = [] { const char* t = getenv("TPAT_GEMM_SMALL_M"); return t ? atoi(t) : 3072; }();
+    const bool small = !small_off && M <= small_m && ep.xb == nullptr && ep.ln_part == nullptr;
+    if (two_cta && sm_count() >= 2 && !small) return gemm_tc2(A, lda, W, C, c_dtype, ldc, M, N, K, ep, st);
+  }
+  int bn = TG_BN;
+  if (M <= 8192) {
+    const int tm = (M + TG_BM - 1) / TG_BM;
+    if (tm * ((N + 255) / 256) < 100 && N % 128 == 0) bn = 128;
+    if (tm * ((N + 127) / 128) < 100 && N % 64 == 0) bn = 64;
   }
   CUtensorMap ta, tw;
   if (int rc = encode_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, TG_BM, TG_BK, true)) return rc;
-  if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, TG_BN, TG_BK, true)) return rc;
+  if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, bn, TG_BK, true)) return rc;
   TPAT_CHECK(ep.xb == nullptr && ep.ln_part == nullptr, "tpat_gemm_ln: the LayerNorm fold needs the CTA-pair kernel (TPAT_GEMM_2CTA=0 is set)");
   TcGemmParams p{};
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
-  p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + TG_BN - 1) / TG_BN;
+  p.bn = bn;
+  p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + bn - 1) / bn;
   p.desc = g_walk_desc;
   p.debug_skip = 0;
   switch (ep.epilogue) {

@@ -319,6 +319,7 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   p.xb = (__nv_bfloat16*)ep.xb; p.ldxb = ep.ldxb; p.part_out = reinterpret_cast<float2*>(ep.part_out); p.part_ld = ep.part_ld;
   p.ln_part = reinterpret_cast<const float2*>(ep.ln_part); p.ln_chunks = ep.ln_chunks; p.ln_colsum = ep.ln_colsum; p.ln_eps = ep.ln_eps;
   p.tiles_m = (M + 255) / 256; p.tiles_n = (N + TG_BN - 1) / TG_BN;
+  p.bn = TG_BN;
   p.desc = g_walk_desc;
   { const char* e = getenv("TPAT_GEMM_DEBUG_SKIP"); p.debug_skip = e ? atoi(e) : 0; }
   switch (ep.epilogue) {

@@ -22,6 +22,7 @@ struct TcGemmParams {
   const float* residual; int ldr;
   const float* pos; int P, num_extra;
   int tiles_m, tiles_n;
+  int bn;           // columns per tile: 256, or 128 / 64 for small-M launches of the 1-CTA kernel (more, shorter tiles)
   int desc;         // 1 = walk the row tiles from the last one down (see g_walk_desc)
   // LayerNorm fold.  Producer side (residual GEMMs): besides C, write bf16(C) and, for every row and
   // 32-column chunk, the partial moments (sum, sum of squared deviations from the chunk mean).  Consumer side (the GEMM
@@ -96,8 +97,8 @@ __device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmParams& p, int 
   for (int ci = 0; ci < TcEpiPrefetch<EW>::NCH; ++ci) {
     const int c = cg + TcEpiPrefetch<EW>::CSTRIDE * ci;
     const int ncol = n0 + c * 32 + jl * 4;
-    pf.bias[ci] = (p.bias != nullptr && c < 8 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    pf.colsum[ci] = (p.ln_colsum != nullptr && c < 8 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pf.bias[ci] = (p.bias != nullptr && c < p.bn / 32 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pf.colsum[ci] = (p.ln_colsum != nullptr && c < p.bn / 32 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -121,7 +122,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
   for (int ci = 0; ci < NCH; ++ci) {
     const int c = cg + CSTRIDE * ci;
     const int n = n0 + c * 32;
-    const bool live = c < 8 && n < p.N;      // warp-uniform
+    const bool live = c < p.bn / 32 && n < p.N;      // warp-uniform
     const int ncol = n + jl * 4;
     float4 extra[8];
     if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
@@ -147,7 +148,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
       ptx::tmem_ld_32x32b_x32(taddr_row + c * 32, r);
       ptx::tmem_ld_wait();
     }
-    if (!released && (ci == NCH - 1 || c + CSTRIDE >= 8 || n + CSTRIDE * 32 >= p.N)) {
+    if (!released && (ci == NCH - 1 || c + CSTRIDE >= p.bn / 32 || n + CSTRIDE * 32 >= p.N)) {
       // last TMEM read of this tile is complete: hand the accumulator back to the MMA warp
       released = true;
       ptx::tc_fence_before();
