@@ -223,6 +223,33 @@ def test_model_on_a_second_device_runs_there():
     assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())
 
 
+@pytest.mark.parametrize("variant", ["audiomae", "ast"])
+def test_long_clip_2048_frames(variant):
+    """Twice the reference's longest input (2048 frames = 1024 patches, N = 1025 / 1026: nine query tiles, a one- / two-row
+    tail tile, 17 key blocks, a 1024-key top-k): fp32 mode against the oracle, and the bf16 mode for finiteness / overlap."""
+    from oracle import weights
+    T = 2048
+    meta = dict(variant=variant, T=T, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7)
+    mk = weights.make_audiomae_state_dict if variant == "audiomae" else weights.make_ast_state_dict
+    sd = mk(35, T, 9, "trained")
+    x = weights.make_spectrogram(variant, 2, T, 33)
+    with torch.no_grad():
+        exp, feats = vo.forward(variant, sd, x, None, (3, 6, 9), 0.7)
+        m32 = build_model(meta, sd, "fp32")
+        got = m32(x.to(dev()))
+        i32 = [t.cpu() for t in m32.last_topk_idx if t is not None]
+        m16 = build_model(meta, sd, "bf16")
+        got16 = m16(x.to(dev()))
+        i16 = [t.cpu() for t in m16.last_topk_idx if t is not None]
+    assert rel_err(got.cpu(), exp) < 2e-5
+    for blk, t in zip((3, 6, 9), i32):
+        for a, b in zip(t.tolist(), feats[f"block-{blk}.topk_idx"].tolist()):
+            assert set(a) == set(b), blk
+    assert [t.shape[1] for t in i16] == [717, 502, 352]
+    assert torch.isfinite(got16).all() and rel_err(got16.cpu(), exp) < 5e-2
+    assert set_overlap(i16[0], i32[0]) > 0.98
+
+
 def test_forward_features_returns_the_classifier_input():
     """models_vit.py:334-396: forward_features = fc_norm(mean of the patch tokens) after the pruned blocks."""
     g = load_golden("audiomae_256_b3_list")
