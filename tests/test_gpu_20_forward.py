@@ -250,6 +250,33 @@ def test_long_clip_2048_frames(variant):
     assert set_overlap(i16[0], i32[0]) > 0.98
 
 
+@pytest.mark.parametrize("variant", ["audiomae", "ast"])
+def test_extreme_pruning_down_to_one_token(variant):
+    """keep rates that leave 3, then 1, then 1 patch token (128 -> 3 -> 1 -> 1): tiny attention (N = 2 .. 4), top-k with
+    k = 1, GEMMs with a handful of rows -- both precisions against the oracle."""
+    from oracle import weights
+    T = 256
+    krl = (1.0, 1.0, 0.02, 1.0, 1.0, 0.3, 1.0, 1.0, 0.5, 1.0, 1.0, 1.0)
+    meta = dict(variant=variant, T=T, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7)
+    mk = weights.make_audiomae_state_dict if variant == "audiomae" else weights.make_ast_state_dict
+    sd = mk(35, T, 12, "trained")
+    x = weights.make_spectrogram(variant, 5, T, 44)
+    with torch.no_grad():
+        exp, feats = vo.forward(variant, sd, x, krl, (3, 6, 9), 0.7)
+        for precision, tol in (("fp32", 2e-5), ("bf16", 5e-2)):
+            m = build_model(meta, sd, precision)
+            got = m(x.to(dev()), keep_rate_list=krl)
+            idx = [t.cpu() for t in m.last_topk_idx if t is not None]
+            assert [t.shape[1] for t in idx] == [3, 1, 1]
+            if precision == "fp32":
+                for blk, t in zip((2, 5, 8), idx):
+                    assert torch.equal(t.sort(1).values, feats[f"block-{blk}.topk_idx"].sort(1).values), blk
+            assert torch.isfinite(got).all()
+            same = all(torch.equal(t.sort(1).values, feats[f"block-{b}.topk_idx"].sort(1).values) for b, t in zip((2, 5, 8), idx))
+            if same:
+                assert rel_err(got.cpu(), exp) < tol, precision
+
+
 def test_forward_features_returns_the_classifier_input():
     """models_vit.py:334-396: forward_features = fc_norm(mean of the patch tokens) after the pruned blocks."""
     g = load_golden("audiomae_256_b3_list")
