@@ -416,9 +416,9 @@ def main():
             "roofline": roofline_entry(kernels, achieved_tf, fl, peaks),
         }
         if not args.no_cpu_baseline and world == 1:
-            cps, sec, cores = cpu_reference_clips_per_s(steps=5, warmup=1)
+            cps, sec, cores = cpu_reference_clips_per_s(steps=30, warmup=1)       # ~ 11 s of CPU work on the box's 16 cores
             line["cpu_baseline"] = {"value": round(cps, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{CPU_SAMPLE_CLIPS} clips x 5 forwards of the same workload, oracle port of "
+                                    "sample": f"{CPU_SAMPLE_CLIPS} clips x 30 forwards of the same workload, oracle port of "
                                               f"the reference forward, fp32 torch CPU ({sec:.2f} s/forward)"}
         print(json.dumps(line), flush=True)
     if world > 1:
