@@ -147,8 +147,56 @@ def main_masked(names=None):
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), kept {keep_idx.shape[1]} of {Tp * 8} patches")
 
 
+def main_schedule():
+    """tests/golden/keep_rate_schedule.pt: outputs of the reference's OWN ``get_scheduled_keep_rate_list``
+    (audiomae/engine_finetune.py:29-53).  The module cannot be imported as a whole here (it needs timm.data.Mixup),
+    so the one function is cut out of the unmodified source with ``ast`` and compiled on its own."""
+    import ast
+    import math
+    src_path = os.path.join(ref_loader.REFERENCE_ROOT, "audiomae", "engine_finetune.py")
+    tree = ast.parse(open(src_path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_scheduled_keep_rate_list")
+    ns = {"math": math}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), src_path, "exec"), ns)
+    ref_fn = ns["get_scheduled_keep_rate_list"]
+    cases = []
+    for epoch in (0, 4, 5, 7, 12, 14, 15, 20):
+        for off in (0, 11, 36):
+            kw = dict(iters=epoch * 37 + off, epoch=epoch, shrink_start_epoch=5, total_epochs=15, ITERS_PER_EPOCH=37,
+                      base_keep_rate=0.7, num_blocks=12, drop_loc=(3, 6, 9))
+            cases.append((kw, ref_fn(**kw)))
+    path = os.path.join(OUT_DIR, "keep_rate_schedule.pt")
+    torch.save({"cases": cases}, path)
+    print(f"keep_rate_schedule: wrote {path} ({len(cases)} cases)")
+
+
+def main_fbank():
+    """tests/golden/fbank_cases.pt: the eval-time input pipeline (audiomae/dataset.py:175-178,209-229,298) run through
+    the reference's pinned third-party dependency, torchaudio.compliance.kaldi.fbank, on three deterministic waveforms
+    (shorter than / exactly / longer than the target length).  The dataset class itself reads audio files and json
+    manifests and cannot be driven without them; oracle/fbank_oracle.py restates the three statements around the
+    torchaudio call."""
+    import torchaudio
+    from . import fbank_oracle as fo
+    cases = {"short_1s": (16000, 1, 128), "exact_2p06s": (32960, 2, 204), "long_1p5s_crop": (24000, 3, 100)}
+    blob = {"meta": {"torchaudio": torchaudio.__version__, "torch": torch.__version__, "cases": list(cases)}}
+    for name, (n, seed, T) in cases.items():
+        x = fo.make_waveform(n, seed)
+        blob[name] = {"n": n, "seed": seed, "T": T, "x_digest": hashlib.sha256(x.numpy().tobytes()).hexdigest(),
+                      "spec": fo.wav2fbank(x, target_length=T)}
+    path = os.path.join(OUT_DIR, "fbank_cases.pt")
+    torch.save(blob, path)
+    print(f"fbank_cases: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
+    if args and args[0] == "schedule":
+        main_schedule()
+        sys.exit(0)
+    if args and args[0] == "fbank":
+        main_fbank()
+        sys.exit(0)
     if args and args[0] == "masked":
         main_masked(args[1:])
         sys.exit(0)

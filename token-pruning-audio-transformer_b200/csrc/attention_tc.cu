@@ -498,6 +498,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUte
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kern, AT_THREADS, smem);
       fprintf(stderr, "[tpat] attention_tc_kernel<%d>: %d CTAs/SM at %zu B smem\n", (int)TWO_PASS, nblk, smem);
     }
+    once.mark();
   }
   TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(AT_THREADS), smem, st, tq, tkv, to, p));
   TPAT_LAUNCH_CHECK();

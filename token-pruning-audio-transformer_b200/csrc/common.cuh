@@ -37,17 +37,14 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 int sm_count();  // cached multiprocessor count of the current device
 
 // Per-device once-flags for cudaFuncSetAttribute (function attributes belong to the device's context: a process that
-// drives several GPUs, e.g. the reference's nn.DataParallel replicas, must set them on each).  Benign race: idempotent.
+// drives several GPUs, e.g. the reference's nn.DataParallel replicas, must set them on each).  `first()` only READS the
+// flag; the caller sets the attribute and then calls `mark()`, so a second host thread racing on the same device sets
+// the (idempotent) attribute again instead of launching before it is in place.
 struct DeviceOnce {
-  bool done[64] = {};
-  bool first() {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
-    if (done[dev]) return false;
-    done[dev] = true;
-    return true;
-  }
+  volatile bool done[64] = {};
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool first() const { return !done[dev()]; }
+  void mark() { done[dev()] = true; }
 };
 bool pdl_enabled();  // programmatic dependent launch when TPAT_PDL=1 (measured r01: 11.18k vs 11.46k clips/s -> off by default)
 

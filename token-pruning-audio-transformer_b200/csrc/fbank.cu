@@ -41,6 +41,8 @@ fbank_kernel(const float* __restrict__ wave, int L, const int* __restrict__ leng
              const float* __restrict__ window, int win, int shift, float preemph,
              const float* __restrict__ mel, const int* __restrict__ mel_start, const int* __restrict__ mel_len, int n_mel,
              float* __restrict__ out, int out_frames) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int HALF = NFFT / 2;                               // complex FFT length
   constexpr bool ODD = (HALF == 128 || HALF == 512);           // odd power of two: one radix-2 stage first
   extern __shared__ float2 fb_smem[];
@@ -174,6 +176,8 @@ fbank_kernel(const float* __restrict__ wave, int L, const int* __restrict__ leng
 __global__ void __launch_bounds__(1024)
 wave_sum_kernel(const float* __restrict__ wave, int L, const int* __restrict__ lengths, float* __restrict__ ws, int do_sum) {
   __shared__ double red[32];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   if (blockIdx.x == 0 && threadIdx.x == 0)
     *reinterpret_cast<unsigned*>(ws + (size_t)b * FB_WS_FLOATS + 2 * FB_MEAN_CHUNKS) = 0xffffffffu;   // +max key
@@ -206,6 +210,8 @@ wave_sum_kernel(const float* __restrict__ wave, int L, const int* __restrict__ l
 __global__ void __launch_bounds__(256)
 fbank_finalize_kernel(float* __restrict__ spec, int L, const int* __restrict__ lengths, const float* __restrict__ ws, int win,
                       int shift, int T, int n_mel, float norm_mean, float inv_2std) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int len = lengths ? min(lengths[b], L) : L;
   const int n_frames = len >= win ? min(1 + (len - win) / shift, T) : 0;
@@ -246,7 +252,7 @@ extern "C" int tpat_fbank(const float* wave, const int* lengths, int B, int L, i
 #define TPAT_FBANK_CASE(N)                                                                                         \
   case N: {                                                                                                            \
     static DeviceOnce once;                                                                                            \
-    if (once.first()) TPAT_CUDA(cudaFuncSetAttribute(fbank_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    if (once.first()) { TPAT_CUDA(cudaFuncSetAttribute(fbank_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once.mark(); } \
     TPAT_CUDA(launch_kernel(fbank_kernel<N>, dim3(grid), dim3(32 * FB_WARPS), smem, st, wave, L, lengths, ws, use_mean, window, win, shift, \
                             preemph, mel, mel_start, mel_len, n_mel, spec, T));                                        \
   } break;

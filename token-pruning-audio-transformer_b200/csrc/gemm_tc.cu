@@ -245,7 +245,7 @@ template <int EPI, typename OutT>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const TcGemmParams& p, cudaStream_t st) {
   static DeviceOnce once;
   auto kern = gemm_tc_kernel<EPI, OutT>;
-  if (once.first()) TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES));
+  if (once.first()) { TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES)); once.mark(); }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(TG_THREADS), TG_SMEM_BYTES, st, ta, tw, p));

@@ -299,7 +299,7 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
   static DeviceOnce once;
   auto kern = gemm_tc2_kernel<EPI, OutT, RES_TMA, FOLD>;
   constexpr int smem_bytes = (RES_TMA && (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS)) ? T2R_SMEM_BYTES : T2_SMEM_BYTES;
-  if (once.first()) TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (once.first()) { TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); once.mark(); }
   const int tiles = p.tiles_m * p.tiles_n;
   int clusters = sm_count() / 2;
   if (tiles < clusters) clusters = tiles;
@@ -321,7 +321,9 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   p.tiles_m = (M + 255) / 256; p.tiles_n = (N + TG_BN - 1) / TG_BN;
   p.bn = TG_BN;
   p.desc = g_walk_desc;
-  { const char* e = getenv("TPAT_GEMM_DEBUG_SKIP"); p.debug_skip = e ? atoi(e) : 0; }
+#ifdef TPAT_DEBUG_BUILD
+  { const char* e = getenv("TPAT_GEMM_DEBUG_SKIP"); p.debug_skip = e ? atoi(e) : 0; }   // timing experiments (wrong results!)
+#endif
   switch (ep.epilogue) {
     case TPAT_EPI_BIAS:
       if (p.ln_part != nullptr && c_dtype == TPAT_BF16) return launch_tc2<TPAT_EPI_BIAS, __nv_bfloat16, false, true>(ta, tw, ta, ta, p, st);

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(256)
 patch_stats_kernel(const float* __restrict__ spec, float* __restrict__ mean_out, float* __restrict__ std_out,
                    int T, int F, int order) {
   extern __shared__ float tile[];  // [16][F+1]
+  pdl_trigger();
+  pdl_wait();
   const int tb = blockIdx.x, b = blockIdx.y;
   const int TB = T / 16, FB = F / 16, P = TB * FB;
   const int ld = F + 1;
@@ -100,6 +102,8 @@ patch_stats_kernel(const float* __restrict__ spec, float* __restrict__ mean_out,
 
 __global__ void gather_rank_kernel(const float* __restrict__ rank, const int64_t* __restrict__ idx, float* __restrict__ out,
                                    int n, int k, int total) {
+  pdl_trigger();
+  pdl_wait();   // idx comes from the score / top-k kernel launched just before
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = i / k;

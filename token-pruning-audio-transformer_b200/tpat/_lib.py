@@ -86,7 +86,12 @@ SIGNATURES = {
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
+    # Rebuild-if-stale on every import (stamp-checked: a no-op when no source / header / flag changed), so that an
+    # edited csrc/ or a pulled tree never runs against an old binary.  TPAT_LIB_PATH (kernel experiments) and a
+    # machine without nvcc (the prebuilt .so travelled with the tree) skip it.
+    have_src = os.path.isdir(os.path.join(_PKG_ROOT, "csrc"))
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.environ.get("TPAT_LIB_PATH") and have_src and (os.path.exists(nvcc) or not os.path.exists(LIB_PATH)):
         sys.path.insert(0, _PKG_ROOT)
         try:
             import build as _build  # token-pruning-audio-transformer_b200/build.py

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .engine import ForwardEngine, resolve_precision
+from .engine import EnginePool, param_key, resolve_precision
 from .models_vit import Block, PatchEmbed, block_tensors, resolve_keep_rates, trunc_normal_
 
 
@@ -162,7 +162,8 @@ class ASTModel(nn.Module):
         self.fuse_token = bool(fuse_token)
         self.precision = resolve_precision(precision)
         self.use_cuda_graph = False
-        self._engine = ForwardEngine(_lib.VARIANT_AST, depth, 768, 12, 3072)
+        self.graph_static_io = False     # with use_cuda_graph: replay on the caller's input buffer, outputs as views (engine._run_graph)
+        self._engines = EnginePool(_lib.VARIANT_AST, depth, 768, 12, 3072)
         self.last_scores = None
         self.last_topk_idx = None
 
@@ -185,7 +186,19 @@ class ASTModel(nn.Module):
         }
 
     def _pack_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return param_key(self)
+
+    def _device_of_params(self):
+        return self.v.cls_token.device
+
+    @property
+    def _engine(self):
+        """The ForwardEngine of the device this (replica of the) model lives on."""
+        return self._engines.get(self._device_of_params())
+
+    def invalidate_packed(self):
+        """Call after changing weights through ``p.data`` (no version bump): drops bf16 copies and captured graphs."""
+        self._engines.invalidate()
 
     def forward(self, x, keep_rate_list: Union[list, tuple, type(None)] = None, flag_extract_features: bool = False):
         """x [B, time_frame_num, frequency_bins], e.g. (12, 1024, 128) (ast_models.py:431)."""
@@ -209,6 +222,7 @@ class ASTModel(nn.Module):
                                                      retain_min=self.retain_min, retain_max=self.retain_max)
             self.last_scores, self.last_topk_idx = None, info["topk_idx"]
             return logits                                                     # None when no token is retained (:495-497)
+        self._engine.graph_static_io = self.graph_static_io
         logits, scores, idxs = self._engine.run(x, rates, self.label_dim, want_all_scores=flag_extract_features,
                                                 precision=self.precision, use_graph=self.use_cuda_graph, fuse_token=self.fuse_token)
         self.last_scores, self.last_topk_idx = scores, idxs

@@ -27,32 +27,67 @@ def shard_batch(x: torch.Tensor, world_size: Optional[int] = None, rank: Optiona
     return x[s:e]
 
 
-def _gather_ragged(t: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
-    """all_gather along dim 0 of per-rank tensors whose dim-0 sizes are ``counts`` (known on every rank)."""
-    world = dist.get_world_size()
-    mx = max(counts)
-    if t.shape[0] < mx:  # pad the short shards so every rank contributes the same shape
-        pad = torch.zeros((mx - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        t = torch.cat([t, pad], dim=0)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t.contiguous())
-    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+class PackedGather:
+    """ONE collective for the eval-time gather: logits (fp32) and the kept-index blocks (int32 on the wire, <= 4096
+    tokens) of this rank are packed into one pre-allocated int32 row buffer [rows_max, width] and exchanged with a single
+    ``all_gather_into_tensor`` -- the payload is <= 1 MB, i.e. latency-bound, so one launch instead of 1 + n_prune
+    list-based ``all_gather`` calls (+ pad / cat kernels) is what matters.  Buffers are cached per (shape, device), so a
+    steady-state step issues two small pack copies per tensor, the collective, and views for the unpack.
+
+    Mirrors ``concat_all_gather`` (audiomae/util/stat.py:12-22 at engine_finetune.py:246-248)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def _buffers(self, rows_max, width, world, device):
+        key = (rows_max, width, world, device)
+        ent = self._buf.get(key)
+        if ent is None:
+            send = torch.zeros(rows_max, width, dtype=torch.int32, device=device)
+            recv = torch.empty(world * rows_max, width, dtype=torch.int32, device=device)
+            ent = self._buf[key] = (send, recv)
+        return ent
+
+    def __call__(self, logits: torch.Tensor, topk_idx: Sequence[Optional[torch.Tensor]], global_batch: int
+                 ) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+        world = dist.get_world_size()
+        counts = [shard_bounds(global_batch, world, r)[1] - shard_bounds(global_batch, world, r)[0] for r in range(world)]
+        rows_max = max(counts)
+        n_local, C = logits.shape
+        widths = [C] + [0 if t is None else t.shape[1] for t in topk_idx]
+        send, recv = self._buffers(rows_max, sum(widths), world, logits.device)
+        send[:n_local, :C].copy_(logits.detach().float().view(torch.int32) if logits.dtype == torch.float32
+                                 else logits.detach().float().contiguous().view(torch.int32))
+        off = C
+        for t, w in zip(topk_idx, widths[1:]):
+            if t is not None:
+                send[:n_local, off:off + w].copy_(t)            # int64 -> int32 in the copy kernel
+            off += w
+        dist.all_gather_into_tensor(recv, send)
+        rv = recv.view(world, rows_max, -1)
+        if all(c == rows_max for c in counts):
+            flat = rv.reshape(world * rows_max, -1)
+        else:
+            flat = torch.cat([rv[r, :c] for r, c in enumerate(counts)], dim=0)
+        all_logits = flat[:, :C].contiguous().view(torch.float32)
+        all_idx: List[Optional[torch.Tensor]] = []
+        off = C
+        for t, w in zip(topk_idx, widths[1:]):
+            all_idx.append(None if t is None else flat[:, off:off + w].to(torch.int64))
+            off += w
+        return all_logits, all_idx
+
+
+_packed_gather = PackedGather()
 
 
 def gather_outputs(logits: torch.Tensor, topk_idx: Sequence[Optional[torch.Tensor]], global_batch: int
                    ) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
-    """Gather the sharded forward outputs on every rank, in global clip order.
+    """Gather the sharded forward outputs on every rank, in global clip order, with ONE packed collective.
 
     ``topk_idx`` is the per-block list a forward returns (None where a block does not prune).
-    Indices travel as int32 (<= 4096 tokens) and are widened back to int64 at the API boundary.
-    """
-    world = dist.get_world_size()
-    counts = [shard_bounds(global_batch, world, r)[1] - shard_bounds(global_batch, world, r)[0] for r in range(world)]
-    all_logits = _gather_ragged(logits, counts)
-    all_idx: List[Optional[torch.Tensor]] = []
-    for t in topk_idx:
-        all_idx.append(None if t is None else _gather_ragged(t.to(torch.int32), counts).to(torch.int64))
-    return all_logits, all_idx
+    Indices travel as int32 and are widened back to int64 at the API boundary."""
+    return _packed_gather(logits, topk_idx, global_batch)
 
 
 def sharded_forward(model, x_global: torch.Tensor, keep_rate_list=None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:

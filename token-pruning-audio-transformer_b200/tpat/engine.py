@@ -55,6 +55,49 @@ def tokens_entering(n_patches: int, prune: Sequence[int], keep: Sequence[int], f
     return out
 
 
+class EnginePool:
+    """One ForwardEngine per CUDA device, created on first use under a lock.
+
+    ``nn.DataParallel`` (the reference's AST training wrapper, ast/src/traintest.py:79,286) replicates a module by
+    shallow-copying ``__dict__``: every replica therefore shares this pool object, and each replica thread asks it
+    for the engine of ITS device -- packed weights, bf16 copies, workspace and graphs are never shared across GPUs."""
+
+    def __init__(self, *engine_args):
+        import threading
+        self._args = engine_args
+        self._lock = threading.Lock()
+        self._engines: Dict[int, "ForwardEngine"] = {}
+        self.ln_fold = os.environ.get("TPAT_LN_FOLD", "0")
+        self.graph_static_io = False
+
+    def get(self, device: torch.device) -> "ForwardEngine":
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        with self._lock:
+            e = self._engines.get(idx)
+            if e is None:
+                e = ForwardEngine(*self._args)
+                e.ln_fold, e.graph_static_io = self.ln_fold, self.graph_static_io
+                self._engines[idx] = e
+            return e
+
+    def invalidate(self) -> None:
+        with self._lock:
+            for e in self._engines.values():
+                e.invalidate()
+
+
+def param_key(module) -> tuple:
+    """(data_ptr, _version) of every parameter tensor reachable from ``module`` -- also on an nn.DataParallel
+    replica, whose ``parameters()`` is empty (its tensors are plain attributes listed in ``_former_parameters``)."""
+    out = []
+    for m in module.modules():
+        params = m._parameters if m._parameters else getattr(m, "_former_parameters", {})   # replica: see replicate()
+        for p in params.values():
+            if p is not None:
+                out.append((p.data_ptr(), p._version))
+    return tuple(out)
+
+
 class ForwardEngine:
     """One instance per model.  ``tensors`` maps a small fixed vocabulary of names to device tensors:
     patch_w [D,1,16,16], patch_b, extra_tok [extra,D], pos [extra+P,D], blocks[i].{ln1_g,...},
@@ -76,6 +119,7 @@ class ForwardEngine:
         self._bf16: Dict[int, torch.Tensor] = {}
         self._workspace: Optional[torch.Tensor] = None
         self._graphs: Dict[tuple, tuple] = {}
+        self.graph_static_io = False     # see _run_graph
         self.last_launch_count = 0
         self.last_pooled: Optional[torch.Tensor] = None
 
@@ -107,6 +151,13 @@ class ForwardEngine:
         self._bf16 = {}
         self._graphs = {}
         self._pack_key = key
+
+    def invalidate(self) -> None:
+        """Drop the packed weight views, bf16 copies and captured graphs.  The pack key is (data_ptr, _version) per
+        parameter; writes through ``p.data`` (EMA / weight averaging code) do not bump ``_version``, so such callers
+        must call this (``model.invalidate_packed()``) after changing weights in place."""
+        self._pack_key = None
+        self._packed, self._fold, self._bf16, self._graphs = {}, {}, {}, {}
 
     def _mat(self, t: torch.Tensor, impl: int) -> torch.Tensor:
         if impl == _lib.IMPL_SIMT:
@@ -226,12 +277,24 @@ class ForwardEngine:
         return logits, scores, idxs
 
     def _run_graph(self, spec, prune, keep, want_all_scores, impl, num_classes, fuse_token=False):
+        """CUDA-graph replay of ``tpat_forward``.  Two flavours (``self.graph_static_io``):
+
+        * False (default): the graph reads a private static input; every call copies ``spec`` into it and returns
+          clones of the outputs (safe for any caller, ~10 ATen launches per step).
+        * True: the graph reads the CALLER's tensor in place (one graph per distinct input buffer, keyed by its
+          address) and the outputs are returned as views of the graph's own output buffers, valid until the next
+          replay of the same graph -- a step is ``g.replay()`` and nothing else (no ATen kernel on the path).  This is
+          what a serving loop with fixed staging buffers (bench.py) uses."""
+        static_io = bool(self.graph_static_io)
         key = (tuple(spec.shape), tuple(prune), tuple(keep), bool(want_all_scores), impl, num_classes, spec.device.index,
-               bool(fuse_token))
+               bool(fuse_token), spec.data_ptr() if static_io else None)
         ent = self._graphs.get(key)
         if ent is None:
-            static_in = torch.empty_like(spec)
-            static_in.copy_(spec)
+            if static_io:
+                static_in = spec
+            else:
+                static_in = torch.empty_like(spec)
+                static_in.copy_(spec)
             logits, scores, idxs = self._alloc_outputs(spec, prune, keep, want_all_scores, num_classes, fuse_token)
             args = self._fill_args(static_in, prune, keep, want_all_scores, impl, num_classes, logits, scores, idxs, None,
                                    fuse_token)
@@ -247,10 +310,14 @@ class ForwardEngine:
             with torch.cuda.graph(g):
                 check(lib.tpat_forward(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "tpat_forward")
             ent = (g, static_in, logits, scores, idxs, ws, pooled)
-            if len(self._graphs) >= 8:                       # bounded cache: drop the oldest captured schedule
+            if len(self._graphs) >= 16:                      # bounded cache: drop the oldest captured schedule
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
         g, static_in, logits, scores, idxs, _, pooled = ent
+        if static_io:
+            g.replay()
+            self.last_pooled = pooled
+            return logits, list(scores), list(idxs)
         static_in.copy_(spec)
         g.replay()
         self.last_pooled = pooled.clone()

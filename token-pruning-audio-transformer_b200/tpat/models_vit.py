@@ -34,7 +34,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .engine import ForwardEngine, resolve_precision
+from .engine import EnginePool, param_key, resolve_precision
 
 
 def to_2tuple(v):
@@ -181,8 +181,9 @@ class VisionTransformer(nn.Module):
         self.fuse_token = bool(fuse_token)
         self.precision = resolve_precision(precision)
         self.use_cuda_graph = False
+        self.graph_static_io = False     # with use_cuda_graph: replay on the caller's input buffer, outputs as views (engine._run_graph)
         self._mlp_hidden = int(embed_dim * mlp_ratio)
-        self._engine = ForwardEngine(_lib.VARIANT_AUDIOMAE, depth, embed_dim, num_heads, self._mlp_hidden)
+        self._engines = EnginePool(_lib.VARIANT_AUDIOMAE, depth, embed_dim, num_heads, self._mlp_hidden)
         self.last_scores = None      # device tensors of the most recent forward
         self.last_topk_idx = None
 
@@ -211,7 +212,19 @@ class VisionTransformer(nn.Module):
         }
 
     def _pack_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return param_key(self)
+
+    def _device_of_params(self):
+        return self.cls_token.device
+
+    @property
+    def _engine(self):
+        """The ForwardEngine of the device this (replica of the) model lives on."""
+        return self._engines.get(self._device_of_params())
+
+    def invalidate_packed(self):
+        """Call after changing weights through ``p.data`` (no version bump): drops bf16 copies and captured graphs."""
+        self._engines.invalidate()
 
     def _check_supported(self, x):
         if self.embed_dim != 64 * self.num_heads or tuple(self.patch_embed.patch_size) != (16, 16):
@@ -284,6 +297,7 @@ class VisionTransformer(nn.Module):
                                                      retain_min=self.retain_min, retain_max=self.retain_max)
             self.last_scores, self.last_topk_idx = None, info["topk_idx"]
             return logits                                                     # None when no token is retained (:384-385)
+        self._engine.graph_static_io = self.graph_static_io
         logits, scores, idxs = self._engine.run(spec, rates, self.num_classes, want_all_scores=flag_extract_features,
                                                 precision=self.precision, use_graph=self.use_cuda_graph, fuse_token=self.fuse_token)
         self.last_scores, self.last_topk_idx = scores, idxs
