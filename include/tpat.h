@@ -27,13 +27,17 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 6
+#define TPAT_VERSION 7
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
 
 /* element types */
-enum { TPAT_F32 = 0, TPAT_BF16 = 1 };
+enum {
+  TPAT_F32 = 0,
+  TPAT_BF16 = 1,
+  TPAT_BF16_SPLIT3 = 2 /* tpat_layernorm output only: [rows, 3 * D] bf16 = [hi | lo | hi], hi = bf16(y), lo = bf16(y - hi) */
+};
 /* GEMM epilogues */
 enum {
   TPAT_EPI_BIAS = 0,          /* C = A W^T + b                               */
@@ -120,6 +124,9 @@ int tpat_gather_rank(const float* rank, const int64_t* idx, float* out, int B, i
 /*
  * LayerNorm over the last dim.  Replaces nn.LayerNorm (models_vit.py:197,205; ast_models.py:209,217,500).
  *   x [rows, D] fp32 -> y [rows, D] (y_dtype).  D % 128 == 0, D <= 2048.
+ *   y_dtype TPAT_BF16_SPLIT3 (D in {384, 768, 1024}): y is [rows, 3 * D] bf16 = [hi | lo | hi]; against weights laid out
+ *   [w_hi | w_hi | w_lo] a K = 3 * D bf16 GEMM yields y w to ~2^-16 relative (split-bf16, "bf16x3"): the q / k projection of
+ *   the pruning blocks in the "bf16+score32" precision mode.  Segment 0 is the plain bf16 output (lda 3 D).
  */
 int tpat_layernorm(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                    int rows, int D, float eps, tpat_stream_t stream);
@@ -177,6 +184,18 @@ int tpat_gemm_ln(const void* A, int a_dtype, int lda, const void* W, int w_dtype
  *   softmax is exact (max-subtracted, normalised over all N keys), fp32.
  */
 int tpat_attention_qtiles(int N, int impl);
+/* fp32 [rows, cols] -> split-bf16 planes [rows, 2 * cols] = [hi | lo]  (cols % 4 == 0) */
+int tpat_split_bf16(const float* x, void* out, int rows, int cols, tpat_stream_t stream);
+/*
+ * tpat_attention whose SCORE tiles (all tiles for COLMEAN, the cls tile for CLS_ROW) take q and k as split-bf16 planes
+ *   qk_planes [B * N, 4 * H * hd] bf16 = [q_hi k_hi | q_lo k_lo]  (tpat_split_bf16 of the fp32 q | k projection)
+ * and form S = Q_hi K_hi^T + Q_hi K_lo^T + Q_lo K_hi^T on the tensor cores (scores to ~2^-16 instead of 2^-8 relative:
+ * models_vit.py:113-114 / ast_models.py:124-125 decide the kept tokens from them).  v, and q / k of the non-score tiles,
+ * still come from `qkv`.  qk_planes == NULL: identical to tpat_attention.  tcgen05 path only.
+ */
+int tpat_attention_split(const void* qkv, const void* qk_planes, void* out, int dtype, float* score_partial,
+                         int score_mode, int B, int N, int H, int hd, int num_extra, float scale, int impl,
+                         tpat_stream_t stream);
 int tpat_attention(const void* qkv, void* out, int dtype, float* score_partial, int score_mode,
                    int B, int N, int H, int hd, int num_extra, float scale, int impl,
                    tpat_stream_t stream);
@@ -252,6 +271,8 @@ typedef struct {
    *   pass over x: fc2 / proj emit bf16(x) + partial moments, qkv / fc1 normalise in their epilogue. */
   const void* qkv_w_ln;  const float* qkv_colsum;  const float* qkv_b_ln;
   const void* fc1_w_ln;  const float* fc1_colsum;  const float* fc1_b_ln;
+  /* Optional (TPAT_IMPL_TC, args.score32): [2D, 3D] bf16 = [w_hi | w_hi | w_lo] of the q and k rows of qkv_w (split-bf16) */
+  const void* qk_w_split;
 } tpat_block_weights;
 
 typedef struct {
@@ -264,6 +285,8 @@ typedef struct {
                                 with fuse_token a pruning block hands keep[i] + 1 tokens to the next one   */
   int fuse_token;            /* EViT fused inattentive token appended after the kept tokens (unpinned)    */
   int want_all_scores;       /* extract mode: emit the score of every block                    */
+  int score32;               /* TPAT_IMPL_TC only: pruning blocks compute q / k (split-bf16 GEMM) and Q K^T of the score tiles
+                                (tpat_attention_split) to ~fp32 accuracy; needs blocks[i].qk_w_split where prune[i]  */
   float ln_eps;              /* 1e-6 for every block norm                                      */
   /* weights: matrices in the impl's operand dtype, vectors fp32 */
   const void* patch_w; const float* patch_b;       /* [D, 256], columns in the order of `variant` */

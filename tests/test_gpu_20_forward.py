@@ -15,9 +15,12 @@ bf16 mode  (tcgen05 kernels, bf16 operands / fp32 accumulate, fp32 residual + LN
              * block-0 score within 5e-3 of max|score| (same tokens on both sides);
              * first pruning block: every token kept on one side only has a reference fp64 score
                within 1 % of the cut score (a near-tie flip, not a wrong selection);
-             * every block: kept-set overlap (mel coordinates, vs the fp64 oracle) >= 1 - max(0.03, 3/k);
-             * logits within 3e-2 of max|logit| when no token flipped, 1e-1 otherwise (a flipped
-               near-tie token changes the pooled mean, exactly as it does for the reference's bf16).
+             * every block: kept-set overlap (mel coordinates, vs the fp64 oracle) >= the value MEASURED for that golden
+               config minus two flipped tokens (BF16_MEASURED below);
+             * logits within 1.6x the measured error of that config, and within the north-star 1e-2 wherever that was
+               measured (trained weight statistics, unpruned, ablation and masked paths).
+           The per-block statement the kernels CAN be held to -- >= 99.9 % overlap given the reference's block input,
+           with the "bf16+score32" split-precision score path -- is tests/test_gpu_25_parity_protocol.py.
 """
 import pytest
 import torch
@@ -102,12 +105,39 @@ def test_forward_fp32_matches_reference_golden(name):
     assert torch.equal(logits, logits_plain)            # extract mode changes outputs reported, not math
 
 
+# Measured on B200 (profiles/r01g_parity.txt, r02 parity file): per golden config, kept-set overlap vs the fp64 oracle at
+# each pruning block and logits error / max|logit| of the plain bf16 mode.  The asserts below hold the kernels to
+# these measurements (one or two more flipped tokens, 1.5x the logit error) instead of a blanket bound, so a
+# regression from 0.995 to 0.97 overlap or from 6e-3 to 9e-2 logits fails.
+BF16_MEASURED = {
+    "ast_spc2_b8_kr07": ([0.9972, 0.9961, 0.9946], 2.12e-2),
+    "ast_spc2_b8_kr07_pert": ([0.9972, 0.9961, 0.9891], 2.11e-2),
+    "audiomae_1024_b2_kr07": ([0.9986, 0.9960, 0.9944], 1.96e-2),
+    "audiomae_1024_b2_kr07_pert": ([0.9986, 0.9940, 0.9915], 1.44e-2),
+    "ast_1024_b2_kr05": ([0.9941, 0.9883, 0.9688], 1.19e-2),
+    "ast_1024_b2_kr09_pert": ([0.9989, 0.9976, 0.9987], 5.48e-3),
+    "audiomae_256_b3_list": ([1.0, 0.9906, 0.9815, 0.9540], 6.87e-2),
+    "audiomae_1024_b4_kr07_trained": ([0.9986, 0.9931, 0.9859], 6.30e-3),
+    "ast_1024_b4_kr07_trained": ([0.9965, 0.9921, 0.9915], 5.20e-3),
+    "ast_spc2_b4_unpruned": ([], 6.10e-3),
+}
+
+
+def bf16_bounds(name, ks, batch):
+    """(min overlap per block, max logits error) from the measured table: two more flipped tokens per block over the
+    whole batch than measured, and 1.6x the measured logits error; the north-star 1e-2 wherever it was met."""
+    ovs, lg = BF16_MEASURED[name]
+    lo = [m - 2.0 / (k * batch) - 1e-4 for m, k in zip(ovs, ks)]
+    return lo, (1e-2 if lg < 6.4e-3 else 1.6 * lg)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16+score32"])
 @pytest.mark.parametrize("name", list(GOLDEN_CONFIGS))
-def test_forward_bf16_against_reference_golden(name):
+def test_forward_bf16_against_reference_golden(name, precision):
     g = load_golden(name)
     meta, ref, f64 = g["meta"], g["ref"], g["f64"]
     sd, x = make_case(meta)
-    model = build_model(meta, sd, "bf16")
+    model = build_model(meta, sd, precision)
     with torch.no_grad():
         logits, feats = model(x.to(dev()), keep_rate_list=meta["keep_rate_list"], flag_extract_features=True)
     blocks = prune_blocks(ref)
@@ -117,7 +147,7 @@ def test_forward_bf16_against_reference_golden(name):
         overlaps = [set_overlap(a, b) for a, b in zip(got, exp)]
     err = rel_err(logits.cpu(), f64["logits"])
     s0 = rel_err(feats["block-0.attn_score"], f64["block-0.attn_score"])
-    print(f"[bf16] {name}: kept-set overlap vs fp64 {['%.4f' % o for o in overlaps]}, logits err {err:.2e}, "
+    print(f"[{precision}] {name}: kept-set overlap vs fp64 {['%.4f' % o for o in overlaps]}, logits err {err:.2e}, "
           f"block-0 score err {s0:.2e}")
     # near-uniform scores (random-init weights): 5e-3; peaked attention ("trained" statistics, logits of std ~3): the bf16
     # rounding of q / k moves individual probabilities by a few per cent and the score by < 1.5e-2 of its maximum
@@ -135,9 +165,10 @@ def test_forward_bf16_against_reference_golden(name):
             diff = set(feats[f"block-{b0}.topk_idx"][c].tolist()) ^ set(f64[f"block-{b0}.topk_idx"][c].tolist())
             for tkn in diff:
                 assert abs(sc[c, tkn].item() - cut) <= max(1e-2 * abs(cut), 2.0 * max_abs), (b0, c, tkn)
-        for o, e in zip(overlaps, exp):
-            assert o >= 1.0 - max(0.03, 3.0 / e.shape[1]), (overlaps,)
-    assert err < (3e-2 if all(o == 1.0 for o in overlaps) else 1e-1)
+    lo, lg_max = bf16_bounds(name, [e.shape[1] for e in exp] if blocks else [], x.shape[0])
+    for o, l in zip(overlaps, lo):
+        assert o >= l, (overlaps, lo)
+    assert err < lg_max, (err, lg_max)
 
 
 @pytest.mark.parametrize("name", ["ast_spc2_b4_unpruned", "audiomae_1024_b2_kr07_pert", "audiomae_256_b3_list"])
@@ -162,7 +193,7 @@ def test_forward_bf16_with_layernorm_fold(name):
     print(f"[ln fold] {name}: launches {n_plain} -> {n_fold}, logits err vs fp64 {ea:.2e} (plain) {eb:.2e} (folded), same kept sets: {same_tokens}")
     n_prune = len(ia)
     assert n_fold == n_plain - (11 + 12 - n_prune)
-    assert eb < (3e-2 if same_tokens else 1e-1)
+    assert eb < 1.6 * max(BF16_MEASURED[name][1], 8.2e-3)
 
 
 def test_forward_is_deterministic_and_batch_invariant():
@@ -223,6 +254,11 @@ def test_model_on_a_second_device_runs_there():
     assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())
 
 
+# 1.5x the values measured on B200 (profiles/r02*_parity.txt): (logits err, block-3 overlap)
+TOL_2048 = {"audiomae": (5e-2, 0.98), "ast": (5e-2, 0.98)}
+TOL_VIT_SIZES = {"vit_small_patch16": 4.0e-3, "vit_large_patch16": 6.5e-2}   # measured 2.64e-3 / 4.33e-2
+
+
 @pytest.mark.parametrize("variant", ["audiomae", "ast"])
 def test_long_clip_2048_frames(variant):
     """Twice the reference's longest input (2048 frames = 1024 patches, N = 1025 / 1026: nine query tiles, a one- / two-row
@@ -246,8 +282,10 @@ def test_long_clip_2048_frames(variant):
         for a, b in zip(t.tolist(), feats[f"block-{blk}.topk_idx"].tolist()):
             assert set(a) == set(b), blk
     assert [t.shape[1] for t in i16] == [717, 502, 352]
-    assert torch.isfinite(got16).all() and rel_err(got16.cpu(), exp) < 5e-2
-    assert set_overlap(i16[0], i32[0]) > 0.98
+    e16, o16 = rel_err(got16.cpu(), exp), set_overlap(i16[0], i32[0])
+    print(f"[bf16 2048 frames] {variant}: logits err {e16:.2e}, block-3 overlap vs fp32 {o16:.4f}")
+    assert torch.isfinite(got16).all() and e16 < TOL_2048[variant][0]
+    assert o16 > TOL_2048[variant][1]
 
 
 @pytest.mark.parametrize("variant", ["audiomae", "ast"])
@@ -316,7 +354,7 @@ def test_other_vit_sizes_match_the_oracle(factory, dim, depth, heads):
     drop_loc = (1, 3, depth - 2)
     with torch.no_grad():
         ref_logits, ref_feats = vo.forward("audiomae", sd, x, None, drop_loc, 0.7, num_heads=heads)
-    for precision, tol in (("fp32", 2e-5), ("bf16", 1e-1)):
+    for precision, tol in (("fp32", 2e-5), ("bf16", TOL_VIT_SIZES[factory])):
         m = getattr(models_vit, factory)(num_classes=C, drop_path_rate=0.0, mean_pooling=True, mask_2d=True,
                                          target_length=T, drop_loc=drop_loc, base_keep_rate=0.7, precision=precision)
         m.patch_embed = models_vit.PatchEmbed((T, 128), 16, 1, dim)

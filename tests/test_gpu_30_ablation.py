@@ -4,7 +4,7 @@
 
 custom_rank ranks tokens by the mean / std of their 16x16 spectrogram patch: the ranking does not depend on the
 network, so the kept sets must be identical in BOTH precisions unless two patches tie to within fp32 rounding of
-the statistic (reported, not hidden); logits: fp32 2e-5, bf16 3e-2 of max|logit|.
+the statistic (reported, not hidden); logits: fp32 2e-5, bf16 1.1e-2 of max|logit| (measured 3.4e-3 ... 7.1e-3).
 """
 import pytest
 import torch
@@ -54,7 +54,7 @@ def test_ablation_paths_match_reference_golden(name, precision):
                 assert set(a[c].tolist()) == set(b[c].tolist()), f"{name} block {blk} clip {c}"
     err = rel_err(logits.cpu(), ref)
     print(f"[ablation {precision}] {name}: logits err {err:.2e}")
-    assert err < (2e-5 if precision == "fp32" else 3e-2)
+    assert err < (2e-5 if precision == "fp32" else 1.1e-2)
 
 
 def test_patch_stats_and_rank_gather_kernels():
@@ -103,4 +103,4 @@ def test_masked_forward_matches_reference_golden(name, precision):
                     mask_f_prob=meta["mask_f_prob"])
     err = rel_err(got.cpu(), g["ref"]["logits"])
     print(f"[masked {precision}] {name}: logits err {err:.2e}")
-    assert err < (2e-5 if precision == "fp32" else 3e-2)
+    assert err < (2e-5 if precision == "fp32" else 1.1e-2)

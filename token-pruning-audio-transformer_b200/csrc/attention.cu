@@ -9,7 +9,14 @@ extern "C" int tpat_attention_qtiles(int N, int impl) {
 extern "C" int tpat_attention(const void* qkv, void* out, int dtype, float* score_partial, int score_mode,
                               int B, int N, int H, int hd, int num_extra, float scale, int impl,
                               tpat_stream_t stream) {
+  return tpat_attention_split(qkv, nullptr, out, dtype, score_partial, score_mode, B, N, H, hd, num_extra, scale, impl, stream);
+}
+
+extern "C" int tpat_attention_split(const void* qkv, const void* qk_planes, void* out, int dtype, float* score_partial,
+                                    int score_mode, int B, int N, int H, int hd, int num_extra, float scale, int impl,
+                                    tpat_stream_t stream) {
   using namespace tpat;
+  TPAT_CHECK(qk_planes == nullptr || (impl == TPAT_IMPL_TC && aligned16(qk_planes)), "tpat_attention_split: planes need the tcgen05 path and 16-byte alignment");
   TPAT_CHECK(qkv && out, "tpat_attention: null pointer");
   TPAT_CHECK(B >= 0 && N > 0 && H > 0, "tpat_attention: bad sizes B=%d N=%d H=%d", B, N, H);
   TPAT_CHECK(hd == 64, "tpat_attention: head dim must be 64 (got %d)", hd);
@@ -22,7 +29,7 @@ extern "C" int tpat_attention(const void* qkv, void* out, int dtype, float* scor
   if (impl == TPAT_IMPL_SIMT) return attention_simt(qkv, out, dtype, score_partial, score_mode, B, N, H, num_extra, scale, as_stream(stream));
   if (impl == TPAT_IMPL_TC) {
     TPAT_CHECK(dtype == TPAT_BF16, "tpat_attention: the tcgen05 path takes bf16 operands");
-    return attention_tc(qkv, out, score_partial, score_mode, B, N, H, num_extra, scale, as_stream(stream));
+    return attention_tc(qkv, out, score_partial, score_mode, B, N, H, num_extra, scale, as_stream(stream), qk_planes);
   }
   set_error("tpat_attention: bad impl %d", impl);
   return 1;

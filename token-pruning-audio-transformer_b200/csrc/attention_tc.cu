@@ -60,6 +60,7 @@ struct AttnTcParams {
   int score_mode;
   int N, H, num_extra, n_qt, nb, qt_offset;
   int desc;          // 1 = clips are visited from the last one down (see g_walk_desc)
+  int lo_off;        // SPLIT: column distance between the hi and lo planes of q / k in the plane buffer (2 * H * 64)
   float scale_log2;  // scale * log2(e)
 };
 
@@ -72,17 +73,24 @@ __device__ __forceinline__ void store_p_half(uint8_t* p_row, int hf, int r_local
                    pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
 }
 
-template <bool TWO_PASS>
-__global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
+// SPLIT (score blocks of the "bf16+score32" precision mode, two-pass tiles only): Q and K arrive as split-bf16 planes
+// (hi = bf16(x), lo = bf16(x - hi); tmap_q / tmap_kv cover the plane buffer [B][N][q_hi k_hi | q_lo k_lo], tmap_v the
+// ordinary qkv buffer) and S = Q_hi K_hi^T + Q_hi K_lo^T + Q_lo K_hi^T: three tcgen05.mma per K = 16 step instead of one,
+// i.e. scores exact to ~2^-16 relative instead of 2^-8, on the 3 of 12 blocks whose scores decide which tokens survive.
+template <bool TWO_PASS, bool SPLIT>
+__global__ void __launch_bounds__(AT_THREADS, SPLIT ? 1 : AT_CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                    const AttnTcParams p) {
+  constexpr int Q_BYTES = SPLIT ? 2 * AT_Q_BYTES : AT_Q_BYTES;        // hi (, lo) query tiles; the hi tile later stages O
+  constexpr int SLOT_BYTES = SPLIT ? 2 * AT_KV_BYTES : AT_KV_BYTES;   // K tile: hi (, lo); V tile: first 8 KB
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment computed as an OFFSET from the __shared__ array so that the compiler keeps the shared
   // address space (a round trip through uintptr_t turns every staging access into a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* q_s = smem;                                   // 16 KB
-  uint8_t* kv_s = q_s + AT_Q_BYTES;                      // AT_SLOTS x 8 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_s + AT_SLOTS * AT_KV_BYTES);
+  uint8_t* kv_s = q_s + Q_BYTES;                         // AT_SLOTS x 8 KB (16 KB when SPLIT)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_s + AT_SLOTS * SLOT_BYTES);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* kv_full = bars + 1;            // [SLOTS]
   uint64_t* kv_empty = kv_full + AT_SLOTS; // [SLOTS]
@@ -135,13 +143,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 0) {
     // ===== TMA producer =====
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
+      ptx::mbar_arrive_expect_tx(q_full, Q_BYTES);
       ptx::tma_load_3d(q_s, &tmap_q, q_full, col_q, q0, b);
+      if (SPLIT) ptx::tma_load_3d(q_s + AT_Q_BYTES, &tmap_q, q_full, p.lo_off + col_q, q0, b);
       int slot = 0; uint32_t phase = 0;
       auto load_tile = [&](int col, int key0) {
         ptx::mbar_wait(&kv_empty[slot], phase ^ 1);
-        ptx::mbar_arrive_expect_tx(&kv_full[slot], AT_KV_BYTES);
-        ptx::tma_load_3d(kv_s + slot * AT_KV_BYTES, &tmap_kv, &kv_full[slot], col, key0, b);
+        const bool is_v = col == col_v;
+        ptx::mbar_arrive_expect_tx(&kv_full[slot], (SPLIT && !is_v) ? 2 * AT_KV_BYTES : AT_KV_BYTES);
+        ptx::tma_load_3d(kv_s + slot * SLOT_BYTES, is_v ? &tmap_v : &tmap_kv, &kv_full[slot], col, key0, b);
+        if (SPLIT && !is_v) ptx::tma_load_3d(kv_s + slot * SLOT_BYTES + AT_KV_BYTES, &tmap_kv, &kv_full[slot], p.lo_off + col, key0, b);
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
       };
       if (TWO_PASS)
@@ -166,10 +177,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::mbar_wait(&kv_full[slot], phase);
         ptx::mbar_wait(&s_empty[sb], ((sidx / AT_SBUF) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint64_t k_desc = ptx::smem_desc_sw128(ptx::smem_u32(kv_s + slot * AT_KV_BYTES), 16, 1024);
+        const uint64_t k_desc = ptx::smem_desc_sw128(ptx::smem_u32(kv_s + slot * SLOT_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k)
           ptx::mma_f16_ss(tmem_base + sb * AT_BK, q_desc + (uint64_t)(2 * k), k_desc + (uint64_t)(2 * k), idesc_s, k != 0);
+        if (SPLIT) {
+          // the two cross terms; lo tiles sit 16 KB (Q) / 8 KB (K) behind the hi tiles: descriptor address field is >> 4
+          constexpr uint64_t q_lo = AT_Q_BYTES >> 4, k_lo = AT_KV_BYTES >> 4;
+#pragma unroll
+          for (int k = 0; k < AT_HD / 16; ++k)
+            ptx::mma_f16_ss(tmem_base + sb * AT_BK, q_desc + (uint64_t)(2 * k), k_desc + k_lo + (uint64_t)(2 * k), idesc_s, 1);
+#pragma unroll
+          for (int k = 0; k < AT_HD / 16; ++k)
+            ptx::mma_f16_ss(tmem_base + sb * AT_BK, q_desc + q_lo + (uint64_t)(2 * k), k_desc + (uint64_t)(2 * k), idesc_s, 1);
+        }
         ptx::tc_commit(&kv_empty[slot]);
         ptx::tc_commit(&s_full[sb]);
         if (++slot == AT_SLOTS) { slot = 0; phase ^= 1; }
@@ -185,7 +206,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::mbar_wait(&kv_full[slot], phase);           // V_j
         ptx::mbar_wait(&p_full[pb], (j >> 1) & 1);       // P_j written by the softmax warps
         ptx::tc_fence_after();
-        const uint32_t v_addr = ptx::smem_u32(kv_s + slot * AT_KV_BYTES);
+        const uint32_t v_addr = ptx::smem_u32(kv_s + slot * SLOT_BYTES);
         const int valid = min(AT_BK, p.N - j * AT_BK);   // keys of this block that exist
         const int ksteps = (valid + 15) >> 4;            // P is zero beyond `valid`, V rows beyond N are zero-filled
         for (int k = 0; k < ksteps; ++k) {
@@ -485,11 +506,11 @@ extern "C" int tpat_debug_attn_trace(long long* host_out) {   // debug builds on
 
 int attention_tc_qtiles(int N) { return (N + AT_BM - 1) / AT_BM; }
 
-template <bool TWO_PASS>
-static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to, const AttnTcParams& p,
-                       dim3 grid, size_t smem, cudaStream_t st) {
+template <bool TWO_PASS, bool SPLIT = false>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tv, const CUtensorMap& to,
+                       const AttnTcParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   static DeviceOnce once;
-  auto kern = attention_tc_kernel<TWO_PASS>;
+  auto kern = attention_tc_kernel<TWO_PASS, SPLIT>;
   if (once.first()) {
     TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_LIMIT));
     TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -500,15 +521,20 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUte
     }
     once.mark();
   }
-  TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(AT_THREADS), smem, st, tq, tkv, to, p));
+  TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(AT_THREADS), smem, st, tq, tkv, tv, to, p));
   TPAT_LAUNCH_CHECK();
   return 0;
 }
 
 int attention_tc(const void* qkv, void* out, float* score_partial, int score_mode, int B, int N, int H,
-                 int num_extra, float scale, cudaStream_t st) {
+                 int num_extra, float scale, cudaStream_t st, const void* qk_planes) {
   TPAT_CHECK(N <= 4096, "tpat_attention(tc): N=%d too large (max 4096)", N);
-  CUtensorMap tm_q, tm_kv, tm_o;
+  TPAT_CHECK(qk_planes == nullptr || score_mode != TPAT_SCORE_NONE, "tpat_attention(tc): split q / k planes are for score blocks only");
+  CUtensorMap tm_q, tm_kv, tm_o, tm_qs, tm_ks;
+  if (qk_planes != nullptr) {
+    if (int rc = encode_tmap_3d_qkv(&tm_qs, qk_planes, B, N, 4 * H * AT_HD, AT_BM)) return rc;
+    if (int rc = encode_tmap_3d_qkv(&tm_ks, qk_planes, B, N, 4 * H * AT_HD, AT_BK)) return rc;
+  }
   if (int rc = encode_tmap_3d_qkv(&tm_q, qkv, B, N, 3 * H * AT_HD, AT_BM)) return rc;
   if (int rc = encode_tmap_3d_qkv(&tm_kv, qkv, B, N, 3 * H * AT_HD, AT_BK)) return rc;
   if (int rc = encode_tmap_3d_qkv(&tm_o, out, B, N, H * AT_HD, AT_BM)) return rc;
@@ -525,20 +551,27 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
   p.nb = (N + AT_BK - 1) / AT_BK;
   p.qt_offset = 0;
   p.desc = g_walk_desc;
+  p.lo_off = 2 * H * AT_HD;
   p.scale_log2 = scale * 1.4426950408889634f;
+  const size_t split_extra = qk_planes ? (size_t)AT_Q_BYTES + AT_SLOTS * AT_KV_BYTES : 0;
   const size_t base_smem = 1024 + AT_Q_BYTES + AT_SLOTS * AT_KV_BYTES + 256 + 2 * AT_BM * sizeof(float2) + 64;
   const size_t colsum_bytes = (size_t)4 * p.nb * AT_BK * sizeof(float);
   TPAT_CHECK(base_smem + (score_mode == TPAT_SCORE_COLMEAN ? colsum_bytes : 0) <= (size_t)AT_SMEM_LIMIT,
              "tpat_attention(tc): N=%d needs %zu bytes of shared memory", N, base_smem + colsum_bytes);
-  if (score_mode == TPAT_SCORE_COLMEAN)       // every tile contributes normalised column sums
-    return launch_attn<true>(tm_q, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem + colsum_bytes, st);
+  TPAT_CHECK(base_smem + split_extra + (score_mode == TPAT_SCORE_COLMEAN ? colsum_bytes : 0) <= (size_t)AT_SMEM_LIMIT,
+             "tpat_attention(tc, split): N=%d needs too much shared memory", N);
+  if (score_mode == TPAT_SCORE_COLMEAN) {     // every tile contributes normalised column sums
+    if (qk_planes) return launch_attn<true, true>(tm_qs, tm_ks, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem + split_extra + colsum_bytes, st);
+    return launch_attn<true>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem + colsum_bytes, st);
+  }
   if (score_mode == TPAT_SCORE_CLS_ROW) {     // only the tile holding query row 0 must normalise
-    if (int rc = launch_attn<true>(tm_q, tm_kv, tm_o, p, dim3(1, H, B), base_smem, st)) return rc;
+    if (qk_planes) { if (int rc = launch_attn<true, true>(tm_qs, tm_ks, tm_kv, tm_o, p, dim3(1, H, B), base_smem + split_extra, st)) return rc; }
+    else if (int rc = launch_attn<true>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(1, H, B), base_smem, st)) return rc;
     if (p.n_qt == 1) return 0;
     p.qt_offset = 1;
-    return launch_attn<false>(tm_q, tm_kv, tm_o, p, dim3(p.n_qt - 1, H, B), base_smem, st);
+    return launch_attn<false>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt - 1, H, B), base_smem, st);
   }
-  return launch_attn<false>(tm_q, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem, st);
+  return launch_attn<false>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem, st);
 }
 
 }  // namespace tpat

@@ -24,6 +24,9 @@ struct Workspace {
   int32_t* rest;      // not-kept token indices (fused token) [B*Nmax]
   float* pooled;
   float* part;      // [B*D]
+  void* y3;           // score32: split-bf16 LayerNorm output [B*Nmax*3D] bf16
+  float* qk32;        // score32: fp32 q | k projection       [B*Nmax*2D]
+  void* qkp;          // score32: split-bf16 planes of it     [B*Nmax*4D] bf16
   size_t bytes;
 };
 
@@ -42,6 +45,8 @@ static int validate(const tpat_forward_args* a) {
     TPAT_CHECK(a->keep[i] > 0 && a->keep[i] <= n, "tpat_forward: keep[%d]=%d must be in (0, %d]", i, a->keep[i], n);
     TPAT_CHECK(a->prune[i] || a->keep[i] == n, "tpat_forward: block %d drops tokens (%d -> %d) but prune[%d] is 0", i, n, a->keep[i], i);
     if (a->prune[i]) TPAT_CHECK(a->topk_idx[i] != nullptr, "tpat_forward: block %d prunes but topk_idx[%d] is NULL", i, i);
+    if (a->prune[i] && a->score32 && a->impl == TPAT_IMPL_TC)
+      TPAT_CHECK(a->blocks[i].qk_w_split != nullptr, "tpat_forward: score32 needs blocks[%d].qk_w_split", i);
     n = a->keep[i] + ((a->prune[i] && a->fuse_token && a->keep[i] < n) ? 1 : 0);
   }
   return 0;
@@ -50,6 +55,7 @@ static int validate(const tpat_forward_args* a) {
 // LayerNorm fold (tpat_gemm_ln): norm1 of block i > 0 is folded when the block carries the gamma-scaled qkv weights (the
 // fc2 of block i - 1 then emits bf16(x) + moments); norm2 is folded in blocks that do not prune (the gather comes first).
 static bool fold_ln1(const tpat_forward_args* a, int i) {
+  if (i < a->depth && a->prune[i] && a->score32) return false;   // the split-bf16 LayerNorm of a score32 pruning block is a real pass
   return a->impl == TPAT_IMPL_TC && i > 0 && i < a->depth && a->blocks[i].qkv_w_ln && a->blocks[i].qkv_colsum && a->blocks[i].qkv_b_ln;
 }
 static bool fold_ln2(const tpat_forward_args* a, int i) {
@@ -77,6 +83,12 @@ static Workspace carve(const tpat_forward_args* a, uint8_t* base) {
   w.rest = (int32_t*)take(B * Nmax * 4);
   w.pooled = (float*)take(B * D * 4);
   w.part = (float*)take(B * Nmax * (D / 32) * 2 * 4);   // LayerNorm fold: partial moments of every row of x
+  w.y3 = nullptr; w.qk32 = nullptr; w.qkp = nullptr;
+  if (a->score32 && a->impl == TPAT_IMPL_TC) {
+    w.y3 = take(B * Nmax * 3 * D * 2);
+    w.qk32 = (float*)take(B * Nmax * 2 * D * 4);
+    w.qkp = take(B * Nmax * 4 * D * 2);
+  }
   w.bytes = off;
   return w;
 }
@@ -98,6 +110,7 @@ extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
     const bool prune = a->prune[i] != 0;
     const bool score = prune || a->want_all_scores;
     n += fold_ln1(a, i) ? 3 : 4;              // (LN1,) QKV, attention, proj
+    if (prune && a->score32 && a->impl == TPAT_IMPL_TC) n += 2;   // split q | k GEMM + plane split
     // AST score blocks on the tensor-core path: the cls tile (two-pass) and the other tiles are separate launches
     if (score && a->variant == TPAT_VARIANT_AST && a->impl == TPAT_IMPL_TC && tpat_attention_qtiles(extra + cur, a->impl) > 1) n += 1;
     if (score) n += 1;                        // score / top-k
@@ -145,7 +158,19 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
     const bool prune = a->prune[i] != 0;
     const bool want_score = prune || a->want_all_scores;
     float* x = w.x[xi];
-    if (fold_ln1(a, i)) {
+    const bool split = prune && a->score32 && impl == TPAT_IMPL_TC;
+    if (split) {
+      // "bf16+score32": LayerNorm -> split-bf16 triple; qkv from its hi segment as usual; q | k again as a K = 3D
+      // split GEMM in fp32, re-split into hi / lo planes for the score tiles of the attention kernel
+      flip();
+      if (int rc = tpat_layernorm(x, bw.ln1_g, bw.ln1_b, w.y3, TPAT_BF16_SPLIT3, M, D, a->ln_eps, stream)) return rc;
+      flip();
+      if (int rc = tpat_gemm(w.y3, act, 3 * D, bw.qkv_w, act, bw.qkv_b, w.qkv, act, 3 * D, nullptr, 0, nullptr, 0, 0,
+                             M, 3 * D, D, TPAT_EPI_BIAS, impl, stream)) return rc;
+      if (int rc = tpat_gemm(w.y3, act, 3 * D, bw.qk_w_split, act, bw.qkv_b, w.qk32, TPAT_F32, 2 * D, nullptr, 0, nullptr, 0, 0,
+                             M, 2 * D, 3 * D, TPAT_EPI_BIAS, impl, stream)) return rc;
+      if (int rc = tpat_split_bf16(w.qk32, w.qkp, M, 2 * D, stream)) return rc;
+    } else if (fold_ln1(a, i)) {
       // norm1 folded: w.y holds bf16(x) and w.part its row moments (written by the previous block's fc2)
       const tpat_ln_fold f{nullptr, 0, nullptr, w.part, bw.qkv_colsum, a->ln_eps};
       flip();
@@ -160,7 +185,7 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
     }
     const int smode = !want_score ? TPAT_SCORE_NONE : (ast ? TPAT_SCORE_CLS_ROW : TPAT_SCORE_COLMEAN);
     flip();
-    if (int rc = tpat_attention(w.qkv, w.ao, act, w.partial, smode, B, N, H, 64, extra, scale, impl, stream)) return rc;
+    if (int rc = tpat_attention_split(w.qkv, split ? w.qkp : nullptr, w.ao, act, w.partial, smode, B, N, H, 64, extra, scale, impl, stream)) return rc;
     flip();
     {
       // proj + residual; when norm2 is folded it also emits bf16(x) (into w.y) and the row moments

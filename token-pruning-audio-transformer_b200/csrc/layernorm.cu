@@ -74,6 +74,62 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   ln_row_store<NV, OutT>(v, mean, rstd, gamma, beta, y + (size_t)row * D, lane);
 }
 
+// LayerNorm whose output is written as a split-bf16 triple [hi | lo | hi] (row pitch 3 * D): hi = bf16(y),
+// lo = bf16(y - hi).  Against weights laid out [w_hi | w_hi | w_lo] a plain K = 3 * D bf16 GEMM then computes
+// y_hi w_hi + y_lo w_hi + y_hi w_lo ~ y w to ~2^-16 relative -- the "precision where it matters" path of the
+// pruning blocks' q / k projection.  Segment 0 doubles as the ordinary bf16 LayerNorm output
+// (lda = 3 * D) for the v projection.
+template <int NV>
+__global__ void __launch_bounds__(32 * LN_WARPS)
+layernorm_split3_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        __nv_bfloat16* __restrict__ y, int rows, float eps, int desc) {
+  constexpr int D = NV * 128;
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  if (desc) row = rows - 1 - row;
+  float4 v[NV];
+  ln_row_load<NV>(x + (size_t)row * D, lane, v);
+  float mean, rstd;
+  ln_row_stats<NV>(v, 1.0f / D, eps, mean, rstd);
+  uint2* out = reinterpret_cast<uint2*>(y + (size_t)row * 3 * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    const float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+    const float h0 = __bfloat162float(__float2bfloat16_rn(y0)), h1 = __bfloat162float(__float2bfloat16_rn(y1));
+    const float h2 = __bfloat162float(__float2bfloat16_rn(y2)), h3 = __bfloat162float(__float2bfloat16_rn(y3));
+    const uint2 hi = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    const uint2 lo = make_uint2(pack_bf16x2(y0 - h0, y1 - h1), pack_bf16x2(y2 - h2, y3 - h3));
+    out[c4] = hi;
+    out[D / 4 + c4] = lo;
+    out[2 * (D / 4) + c4] = hi;
+  }
+}
+
+// fp32 [rows, cols] -> split-bf16 planes [rows, 2 * cols] = [hi | lo] (the q / k operands of the split QK^T)
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
+  const int c4n = cols / 4;
+  const size_t total = (size_t)rows * c4n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / c4n; const int c4 = (int)(i - r * c4n);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
+    const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
+    uint2* o = reinterpret_cast<uint2*>(out + r * 2 * cols);
+    o[c4] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    o[c4n + c4] = make_uint2(pack_bf16x2(v.x - h0, v.y - h1), pack_bf16x2(v.z - h2, v.w - h3));
+  }
+}
+
 // Token compaction fused with norm2: output row (b, j) <- input row (b, j < extra ? j : extra + idx[b, j-extra]).
 template <int NV, typename OutT>
 __global__ void __launch_bounds__(32 * LN_WARPS)
@@ -329,6 +385,20 @@ static int launch_layernorm(const float* x, const float* g, const float* b, OutT
   return 0;
 }
 
+static int launch_layernorm_split3(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, int D, float eps,
+                                   cudaStream_t st) {
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+#define TPAT_LN_CASE(nv) \
+  case nv: TPAT_CUDA(launch_kernel(layernorm_split3_kernel<nv>, dim3(grid), dim3(32 * LN_WARPS), 0, st, x, g, b, y, rows, eps, g_walk_desc)); break;
+  switch (D / 128) {
+    TPAT_LN_CASE(3) TPAT_LN_CASE(6) TPAT_LN_CASE(8)
+    default: set_error("tpat_layernorm(split3): unsupported D=%d", D); return 1;
+  }
+#undef TPAT_LN_CASE
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename OutT>
 static int launch_gather_ln(const float* x, const int64_t* idx, float* xo, const float* g, const float* b, OutT* yo,
                             int B, int N_in, int k, int extra, int out_rows, int D, float eps, cudaStream_t st) {
@@ -357,8 +427,22 @@ extern "C" int tpat_layernorm(const float* x, const float* gamma, const float* b
   if (rows == 0) return 0;
   if (y_dtype == TPAT_F32) return launch_layernorm<float>(x, gamma, beta, (float*)y, rows, D, eps, as_stream(stream));
   if (y_dtype == TPAT_BF16) return launch_layernorm<__nv_bfloat16>(x, gamma, beta, (__nv_bfloat16*)y, rows, D, eps, as_stream(stream));
+  if (y_dtype == TPAT_BF16_SPLIT3) return launch_layernorm_split3(x, gamma, beta, (__nv_bfloat16*)y, rows, D, eps, as_stream(stream));
   set_error("tpat_layernorm: bad dtype %d", y_dtype);
   return 1;
+}
+
+extern "C" int tpat_split_bf16(const float* x, void* out, int rows, int cols, tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(x && out, "tpat_split_bf16: null pointer");
+  TPAT_CHECK(rows >= 0 && cols > 0 && cols % 4 == 0, "tpat_split_bf16: cols must be a positive multiple of 4 (cols=%d)", cols);
+  TPAT_CHECK(aligned16(x) && aligned16(out), "tpat_split_bf16: pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const size_t total = (size_t)rows * (cols / 4);
+  const int grid = (int)((total + 255) / 256 < (size_t)sm_count() * 16 ? (total + 255) / 256 : (size_t)sm_count() * 16);
+  TPAT_CUDA(launch_kernel(split_bf16_kernel, dim3(grid), dim3(256), 0, as_stream(stream), x, (__nv_bfloat16*)out, rows, cols));
+  TPAT_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int tpat_gather_layernorm(const float* x, const int64_t* topk_idx, float* x_out, const float* gamma,

@@ -13,7 +13,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("TPAT_LIB_PATH") or os.path.join(_PKG_ROOT, "lib", "libtpat.so")   # override: kernel experiments
 
 TPAT_MAX_DEPTH = 32
-F32, BF16 = 0, 1
+F32, BF16, BF16_SPLIT3 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_POS = 0, 1, 2, 3
 IMPL_SIMT, IMPL_TC = 0, 1
 SCORE_NONE, SCORE_CLS_ROW, SCORE_COLMEAN = 0, 1, 2
@@ -24,7 +24,7 @@ VARIANT_AUDIOMAE, VARIANT_AST = 0, 1
 class BlockWeights(Structure):
     _fields_ = [(n, c_void_p) for n in (
         "ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
-        "qkv_w_ln", "qkv_colsum", "qkv_b_ln", "fc1_w_ln", "fc1_colsum", "fc1_b_ln")]
+        "qkv_w_ln", "qkv_colsum", "qkv_b_ln", "fc1_w_ln", "fc1_colsum", "fc1_b_ln", "qk_w_split")]
 
 
 class LnFold(Structure):
@@ -38,7 +38,7 @@ class ForwardArgs(Structure):
         ("variant", c_int), ("impl", c_int), ("B", c_int), ("T", c_int), ("F", c_int),
         ("depth", c_int), ("D", c_int), ("H", c_int), ("Dh", c_int), ("num_classes", c_int),
         ("prune", c_int * TPAT_MAX_DEPTH), ("keep", c_int * TPAT_MAX_DEPTH), ("fuse_token", c_int),
-        ("want_all_scores", c_int), ("ln_eps", c_float),
+        ("want_all_scores", c_int), ("score32", c_int), ("ln_eps", c_float),
         ("patch_w", c_void_p), ("patch_b", c_void_p), ("extra_tok", c_void_p), ("pos", c_void_p),
         ("blocks", BlockWeights * TPAT_MAX_DEPTH),
         ("norm_g", c_void_p), ("norm_b", c_void_p), ("norm_eps", c_float),
@@ -66,6 +66,9 @@ SIGNATURES = {
     "tpat_attention_qtiles": (c_int, [c_int, c_int]),
     "tpat_attention": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                c_int, c_void_p]),
+    "tpat_split_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "tpat_attention_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_float, c_int, c_void_p]),
     "tpat_score_topk": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tpat_gather_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_float, c_void_p]),

@@ -15,7 +15,10 @@ import torch
 from . import _lib
 from ._lib import ForwardArgs, check, lib
 
-PRECISIONS = ("bf16", "fp32")
+# "bf16+score32": bf16 tensor-core kernels, but the pruning blocks compute their q / k projection and Q K^T of the score
+# tiles in split-bf16 (three tcgen05.mma per product, ~fp32 accuracy): the token SELECTION follows the reference to its
+# fp32 accuracy (given the same block input) for a few per cent of extra time.
+PRECISIONS = ("bf16", "fp32", "bf16+score32")
 
 
 def resolve_precision(p: Optional[str]) -> str:
@@ -120,6 +123,7 @@ class ForwardEngine:
         self._workspace: Optional[torch.Tensor] = None
         self._graphs: Dict[tuple, tuple] = {}
         self.graph_static_io = False     # see _run_graph
+        self._score32 = False
         self.last_launch_count = 0
         self.last_pooled: Optional[torch.Tensor] = None
 
@@ -168,6 +172,19 @@ class ForwardEngine:
             self._bf16[id(t)] = c
         return c
 
+    def _qk_split(self, i: int) -> torch.Tensor:
+        """[2D, 3D] bf16 = [w_hi | w_hi | w_lo] of the q and k rows of block i's qkv weight (pairs with the
+        [hi | lo | hi] LayerNorm output: a_hi w_hi + a_lo w_hi + a_hi w_lo)."""
+        key = ("qk_split", i)
+        c = self._bf16.get(key)
+        if c is None:
+            w = self._packed["blocks"][i]["qkv_w"][: 2 * self.D]
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            c = torch.cat([hi, hi, lo], dim=1).contiguous()
+            self._bf16[key] = c
+        return c
+
     def _folded(self, i: int) -> Dict[str, torch.Tensor]:
         """Weights of the LayerNorm fold for block i (tpat_gemm_ln): W' = bf16(W * gamma), colsum = sum_k W', b' = W beta + b."""
         f = self._fold.get(i)
@@ -188,6 +205,7 @@ class ForwardEngine:
                    fuse_token=False):
         pk = self._packed
         a = ForwardArgs()
+        a.score32 = 1 if self._score32 else 0
         a.fuse_token = 1 if fuse_token else 0
         a.variant, a.impl = self.variant, impl
         a.B, a.T, a.F = spec.shape
@@ -210,6 +228,8 @@ class ForwardEngine:
                 for name, t in self._folded(i).items():
                     if self.ln_fold == "all" or name.startswith("qkv"):
                         setattr(bw, name, t.data_ptr())
+            if impl == _lib.IMPL_TC and self._score32 and prune[i]:
+                bw.qk_w_split = self._qk_split(i).data_ptr()
         a.norm_g, a.norm_b, a.norm_eps = pk["norm_g"].data_ptr(), pk["norm_b"].data_ptr(), 1e-6
         if pk["head_ln_g"] is not None:
             a.head_ln_g, a.head_ln_b, a.head_ln_eps = pk["head_ln_g"].data_ptr(), pk["head_ln_b"].data_ptr(), 1e-5
@@ -260,7 +280,8 @@ class ForwardEngine:
             raise RuntimeError("tpat: the current device is not compute capability 10.x (B200, sm_100a)")
         if spec.dtype != torch.float32 or not spec.is_contiguous():
             spec = spec.float().contiguous()
-        impl = _lib.IMPL_TC if precision == "bf16" else _lib.IMPL_SIMT
+        impl = _lib.IMPL_SIMT if precision == "fp32" else _lib.IMPL_TC
+        self._score32 = precision == "bf16+score32"
         B, T, F = spec.shape
         prune, keep = pruning_schedule((T // 16) * (F // 16), self.num_extra, keep_rates, fuse_token)
         if use_graph:
@@ -287,7 +308,7 @@ class ForwardEngine:
           what a serving loop with fixed staging buffers (bench.py) uses."""
         static_io = bool(self.graph_static_io)
         key = (tuple(spec.shape), tuple(prune), tuple(keep), bool(want_all_scores), impl, num_classes, spec.device.index,
-               bool(fuse_token), spec.data_ptr() if static_io else None)
+               bool(fuse_token), spec.data_ptr() if static_io else None, self._score32)
         ent = self._graphs.get(key)
         if ent is None:
             if static_io:
@@ -358,7 +379,7 @@ class ForwardEngine:
             raise ValueError(f"custom_rank should be in ['mean', 'std'], got {use_custom_rank}")
         if spec.dtype != torch.float32 or not spec.is_contiguous():
             spec = spec.float().contiguous()
-        impl = _lib.IMPL_TC if precision == "bf16" else _lib.IMPL_SIMT
+        impl = _lib.IMPL_SIMT if precision == "fp32" else _lib.IMPL_TC      # (the stepwise paths have no score32 variant)
         act = torch.bfloat16 if impl == _lib.IMPL_TC else torch.float32
         pk, extra, D, H = self._packed, self.num_extra, self.D, self.H
         ast = self.variant == _lib.VARIANT_AST

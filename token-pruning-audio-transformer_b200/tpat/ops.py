@@ -68,22 +68,40 @@ def gather_rank(rank: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype) -> torch.Tensor:
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_dtype: torch.dtype,
+              split3: bool = False) -> torch.Tensor:
+    """LayerNorm over the last dim.  ``split3``: bf16 output [..., 3 * D] = [hi | lo | hi] (split-bf16 triple)."""
     _req(x, torch.float32, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
     D = x.shape[-1]
     rows = x.numel() // D
-    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    check(lib.tpat_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _DT[out_dtype], rows, D,
+    if split3:
+        y = torch.empty(tuple(x.shape[:-1]) + (3 * D,), device=x.device, dtype=torch.bfloat16)
+        dt = _lib.BF16_SPLIT3
+    else:
+        y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+        dt = _DT[out_dtype]
+    check(lib.tpat_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), dt, rows, D,
                              float(eps), _stream()), "tpat_layernorm")
     return y
 
 
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, 2 * cols] = [hi | lo]."""
+    _req(x, torch.float32, "x")
+    rows, cols = x.shape
+    out = torch.empty(rows, 2 * cols, device=x.device, dtype=torch.bfloat16)
+    check(lib.tpat_split_bf16(x.data_ptr(), out.data_ptr(), rows, cols, _stream()), "tpat_split_bf16")
+    return out
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dtype: torch.dtype, epilogue: int = 0,
          impl: int = _lib.IMPL_SIMT, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         pos: Optional[torch.Tensor] = None, P: int = 0, num_extra: int = 0) -> torch.Tensor:
-    """out = epilogue(a @ w.T + bias).  a [M,K], w [N,K] (nn.Linear layout)."""
+         pos: Optional[torch.Tensor] = None, P: int = 0, num_extra: int = 0, k_cols: Optional[int] = None) -> torch.Tensor:
+    """out = epilogue(a @ w.T + bias).  a [M,K], w [N,K] (nn.Linear layout).  ``k_cols``: use only the first k_cols
+    columns of ``a`` (row pitch stays a.shape[1])."""
     _req(a, name="a"); _req(w, a.dtype, "w")
-    M, K = a.shape
+    M, lda = a.shape
+    K = lda if k_cols is None else k_cols
     N = w.shape[0]
     if out is None:
         rows = M if epilogue != _lib.EPI_BIAS_POS else (M // P) * (P + num_extra)
@@ -91,7 +109,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dty
     _req(out, out_dtype, "out")
     if residual is not None:
         _req(residual, torch.float32, "residual")
-    check(lib.tpat_gemm(a.data_ptr(), _DT[a.dtype], K, w.data_ptr(), _DT[w.dtype], _ptr(bias), out.data_ptr(),
+    check(lib.tpat_gemm(a.data_ptr(), _DT[a.dtype], lda, w.data_ptr(), _DT[w.dtype], _ptr(bias), out.data_ptr(),
                         _DT[out_dtype], N, _ptr(residual), N if residual is not None else 0, _ptr(pos), P, num_extra,
                         M, N, K, epilogue, impl, _stream()), "tpat_gemm")
     return out
@@ -127,17 +145,21 @@ def attention_qtiles(N: int, impl: int) -> int:
     return lib.tpat_attention_qtiles(N, impl)
 
 
-def attention(qkv: torch.Tensor, B: int, N: int, H: int, num_extra: int, score_mode: int, impl: int):
-    """qkv [B*N, 3*H*64] -> (out [B*N, H*64], score_partial or None)."""
+def attention(qkv: torch.Tensor, B: int, N: int, H: int, num_extra: int, score_mode: int, impl: int,
+              qk_planes: Optional[torch.Tensor] = None):
+    """qkv [B*N, 3*H*64] -> (out [B*N, H*64], score_partial or None).  ``qk_planes`` [B*N, 4*H*64] bf16 = split-bf16
+    [q_hi k_hi | q_lo k_lo] for the score tiles (tpat_attention_split)."""
     _req(qkv, name="qkv")
+    if qk_planes is not None:
+        _req(qk_planes, torch.bfloat16, "qk_planes")
     out = torch.empty(B * N, H * 64, device=qkv.device, dtype=qkv.dtype)
     partial = None
     if score_mode == _lib.SCORE_CLS_ROW:
         partial = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32)
     elif score_mode == _lib.SCORE_COLMEAN:
         partial = torch.empty(B, H * attention_qtiles(N, impl), N, device=qkv.device, dtype=torch.float32)
-    check(lib.tpat_attention(qkv.data_ptr(), out.data_ptr(), _DT[qkv.dtype], _ptr(partial), score_mode, B, N, H, 64,
-                             num_extra, 64 ** -0.5, impl, _stream()), "tpat_attention")
+    check(lib.tpat_attention_split(qkv.data_ptr(), _ptr(qk_planes), out.data_ptr(), _DT[qkv.dtype], _ptr(partial), score_mode,
+                                   B, N, H, 64, num_extra, 64 ** -0.5, impl, _stream()), "tpat_attention")
     return out, partial
 
 
