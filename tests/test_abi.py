@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_struct_layout():
     from tpat import _lib
-    assert _lib.lib.tpat_version() == 6
+    assert _lib.lib.tpat_version() == _lib.TPAT_VERSION
     assert _lib.lib.tpat_sizeof_forward_args() == ctypes.sizeof(_lib.ForwardArgs)
 
 

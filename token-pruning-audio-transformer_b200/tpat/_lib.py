@@ -13,6 +13,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("TPAT_LIB_PATH") or os.path.join(_PKG_ROOT, "lib", "libtpat.so")   # override: kernel experiments
 
 TPAT_MAX_DEPTH = 32
+TPAT_VERSION = 7          # must equal TPAT_VERSION in include/tpat.h (checked at load)
 F32, BF16, BF16_SPLIT3 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_POS = 0, 1, 2, 3
 IMPL_SIMT, IMPL_TC = 0, 1
@@ -108,6 +109,8 @@ def _load():
         fn = getattr(lib, name)  # AttributeError here = the .so does not export what tpat.h declares
         fn.restype = res
         fn.argtypes = args
+    if lib.tpat_version() != TPAT_VERSION:
+        raise ImportError(f"libtpat.so is version {lib.tpat_version()}, tpat/_lib.py expects {TPAT_VERSION}")
     if lib.tpat_sizeof_forward_args() != ctypes.sizeof(ForwardArgs):
         raise ImportError("ForwardArgs layout does not match the tpat_forward_args compiled into libtpat.so")
     return lib

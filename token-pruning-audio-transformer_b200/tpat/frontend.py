@@ -75,20 +75,26 @@ class FbankFrontend:
     def num_frames(self, n_samples: int) -> int:
         return 1 + (n_samples - self.win) // self.shift if n_samples >= self.win else 0
 
-    def __call__(self, wave: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def __call__(self, wave: torch.Tensor, lengths: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None
+                 ) -> torch.Tensor:
         if not wave.is_cuda:
             raise RuntimeError("tpat: the front end takes CUDA tensors; there is no CPU path")
         if wave.dim() != 2 or wave.dtype != torch.float32 or not wave.is_contiguous():
             raise RuntimeError("wave must be a contiguous fp32 [B, L] tensor (mono)")
         with torch.cuda.device(wave.device):
-            return self._call(wave, lengths)
+            return self._call(wave, lengths, out)
 
-    def _call(self, wave: torch.Tensor, lengths: Optional[torch.Tensor]) -> torch.Tensor:
+    def _call(self, wave: torch.Tensor, lengths: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, L = wave.shape
         w, mel, ms, ml = self._tables(wave.device)
         if lengths is not None:
             lengths = lengths.to(device=wave.device, dtype=torch.int32).contiguous()
-        spec = torch.empty(B, self.T, self.n_mel, device=wave.device, dtype=torch.float32)
+        if out is not None:      # caller-owned spectrogram buffer (a fixed address keeps a static-IO CUDA graph valid)
+            if tuple(out.shape) != (B, self.T, self.n_mel) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != wave.device:
+                raise RuntimeError("out must be a contiguous fp32 [B, target_length, num_mel_bins] tensor on the input's device")
+            spec = out
+        else:
+            spec = torch.empty(B, self.T, self.n_mel, device=wave.device, dtype=torch.float32)
         ws = torch.empty(32 * B, device=wave.device, dtype=torch.float32)
         check(lib.tpat_fbank(wave.data_ptr(), None if lengths is None else lengths.data_ptr(), B, L,
                              1 if self.subtract_clip_mean else 0, ws.data_ptr(), w.data_ptr(), self.win,
