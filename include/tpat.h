@@ -43,7 +43,8 @@ enum {
   TPAT_EPI_BIAS = 0,          /* C = A W^T + b                               */
   TPAT_EPI_BIAS_GELU = 1,     /* C = gelu_erf(A W^T + b)                     */
   TPAT_EPI_BIAS_RESIDUAL = 2, /* C = R + A W^T + b   (C may alias R)         */
-  TPAT_EPI_BIAS_POS = 3       /* patch-embed: C[b, extra+p] = A W^T + b + pos[extra+p] */
+  TPAT_EPI_BIAS_POS = 3,      /* patch-embed: C[b, extra+p] = A W^T + b + pos[extra+p] */
+  TPAT_EPI_DGELU = 4          /* training (tpat_gemm_train): C = (A W^T) * gelu'(aux)      */
 };
 /* GEMM / attention implementation */
 enum {

@@ -8,21 +8,56 @@ extern "C" int tpat_gemm(const void* A, int a_dtype, int lda, const void* W, int
                       impl, nullptr, stream);
 }
 
+static int gemm_entry(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
+                      void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
+                      int P, int num_extra, int M, int N, int K, int epilogue, int impl, const tpat_ln_fold* fold,
+                      const tpat_gemm_extra* extra, tpat_stream_t stream);
+
 extern "C" int tpat_gemm_ln(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
                             void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
                             int P, int num_extra, int M, int N, int K, int epilogue, int impl, const tpat_ln_fold* fold,
                             tpat_stream_t stream) {
+  return gemm_entry(A, a_dtype, lda, W, w_dtype, bias, C, c_dtype, ldc, residual, ldr, pos, P, num_extra, M, N, K, epilogue, impl, fold,
+                    nullptr, stream);
+}
+
+extern "C" int tpat_gemm_train(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
+                               void* C, int c_dtype, int ldc, const float* residual, int ldr, int M, int N, int K,
+                               int epilogue, int impl, const tpat_gemm_extra* extra, tpat_stream_t stream) {
+  return gemm_entry(A, a_dtype, lda, W, w_dtype, bias, C, c_dtype, ldc, residual, ldr, nullptr, 0, 0, M, N, K, epilogue, impl, nullptr,
+                    extra, stream);
+}
+
+static int gemm_entry(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
+                      void* C, int c_dtype, int ldc, const float* residual, int ldr, const float* pos,
+                      int P, int num_extra, int M, int N, int K, int epilogue, int impl, const tpat_ln_fold* fold,
+                      const tpat_gemm_extra* extra, tpat_stream_t stream) {
   using namespace tpat;
   TPAT_CHECK(A && W && C, "tpat_gemm: null pointer");
   TPAT_CHECK(M >= 0 && N > 0 && K > 0, "tpat_gemm: bad sizes M=%d N=%d K=%d", M, N, K);
   TPAT_CHECK(a_dtype == w_dtype && (a_dtype == TPAT_F32 || a_dtype == TPAT_BF16), "tpat_gemm: A and W must share a dtype (f32 or bf16)");
   TPAT_CHECK(c_dtype == TPAT_F32 || c_dtype == TPAT_BF16, "tpat_gemm: bad C dtype %d", c_dtype);
-  TPAT_CHECK(epilogue >= TPAT_EPI_BIAS && epilogue <= TPAT_EPI_BIAS_POS, "tpat_gemm: bad epilogue %d", epilogue);
+  TPAT_CHECK(epilogue >= TPAT_EPI_BIAS && epilogue <= TPAT_EPI_DGELU, "tpat_gemm: bad epilogue %d", epilogue);
+  if (epilogue == TPAT_EPI_DGELU)
+    TPAT_CHECK(extra && extra->aux && extra->ld_aux >= N && bias == nullptr && aligned16(extra->aux) && (extra->ld_aux * dtype_size(c_dtype)) % 16 == 0,
+               "tpat_gemm_train: the DGELU epilogue needs extra->aux (dtype of C, 16-byte aligned rows) and no bias");
   TPAT_CHECK(lda >= K && ldc >= N, "tpat_gemm: lda/ldc too small");
   if (epilogue == TPAT_EPI_BIAS_RESIDUAL) TPAT_CHECK(residual && ldr >= N && c_dtype == TPAT_F32, "tpat_gemm: residual epilogue needs residual, ldr >= N and fp32 C");
   if (epilogue == TPAT_EPI_BIAS_POS) TPAT_CHECK(pos && P > 0 && num_extra >= 0 && M % P == 0 && ldc == N && c_dtype == TPAT_F32, "tpat_gemm: pos epilogue needs pos, P | M, ldc == N and fp32 C");
   if (M == 0) return 0;
   EpiParams ep{bias, residual, ldr, pos, P, num_extra, epilogue};
+  if (extra != nullptr) {
+    if (extra->pre_out != nullptr) {
+      TPAT_CHECK(epilogue == TPAT_EPI_BIAS_GELU && extra->ld_pre >= N && aligned16(extra->pre_out) && (extra->ld_pre * dtype_size(c_dtype)) % 16 == 0,
+                 "tpat_gemm_train: pre_out needs the bias+GELU epilogue and 16-byte aligned rows");
+      ep.pre_out = extra->pre_out; ep.ld_pre = extra->ld_pre;
+    }
+    if (epilogue == TPAT_EPI_DGELU) { ep.aux = extra->aux; ep.ld_aux = extra->ld_aux; }
+    if (extra->row_scale != nullptr) {
+      TPAT_CHECK(epilogue == TPAT_EPI_BIAS_RESIDUAL && extra->rows_per_clip > 0, "tpat_gemm_train: row_scale needs the residual epilogue and rows_per_clip > 0");
+      ep.row_scale = extra->row_scale; ep.rows_per_clip = extra->rows_per_clip;
+    }
+  }
   if (fold != nullptr && (fold->xb != nullptr || fold->ln_part != nullptr)) {
     TPAT_CHECK(impl == TPAT_IMPL_TC, "tpat_gemm_ln: the LayerNorm fold exists on the tcgen05 path only");
     if (fold->xb != nullptr) {

@@ -237,13 +237,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           ptx::mbar_wait(&rb[buf], buf ? rph1 : rph0);
           if (buf) rph1 ^= 1; else rph0 ^= 1;
           uint8_t* rowp = stg + buf * 4096 + lane * 128;
+          // DropPath (training): the branch of clip b is scaled by row_scale[b] (0 or 1 / keep_prob)
+          const float sc = (EPI == TPAT_EPI_BIAS_RESIDUAL && p.row_scale != nullptr) ? __ldg(p.row_scale + min(m0 + lane, p.M - 1) / p.rows_per_clip) : 1.0f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4* cell = reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4));
             const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 x = *cell;
-            x.x += __uint_as_float(r[4 * j]) + bb.x; x.y += __uint_as_float(r[4 * j + 1]) + bb.y;
-            x.z += __uint_as_float(r[4 * j + 2]) + bb.z; x.w += __uint_as_float(r[4 * j + 3]) + bb.w;
+            x.x = fmaf(sc, __uint_as_float(r[4 * j]) + bb.x, x.x); x.y = fmaf(sc, __uint_as_float(r[4 * j + 1]) + bb.y, x.y);
+            x.z = fmaf(sc, __uint_as_float(r[4 * j + 2]) + bb.z, x.z); x.w = fmaf(sc, __uint_as_float(r[4 * j + 3]) + bb.w, x.w);
             *cell = x;
             r[4 * j] = __float_as_uint(x.x); r[4 * j + 1] = __float_as_uint(x.y);      // keep the row for the fold below
             r[4 * j + 2] = __float_as_uint(x.z); r[4 * j + 3] = __float_as_uint(x.w);
@@ -318,6 +320,7 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.xb = (__nv_bfloat16*)ep.xb; p.ldxb = ep.ldxb; p.part_out = reinterpret_cast<float2*>(ep.part_out); p.part_ld = ep.part_ld;
   p.ln_part = reinterpret_cast<const float2*>(ep.ln_part); p.ln_chunks = ep.ln_chunks; p.ln_colsum = ep.ln_colsum; p.ln_eps = ep.ln_eps;
+  p.pre_out = ep.pre_out; p.ld_pre = ep.ld_pre; p.aux = ep.aux; p.ld_aux = ep.ld_aux; p.row_scale = ep.row_scale; p.rows_per_clip = ep.rows_per_clip;
   p.tiles_m = (M + 255) / 256; p.tiles_n = (N + TG_BN - 1) / TG_BN;
   p.bn = TG_BN;
   p.desc = g_walk_desc;
@@ -333,6 +336,8 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
       if (p.ln_part != nullptr && c_dtype == TPAT_BF16) return launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16, false, true>(ta, tw, ta, ta, p, st);
       TPAT_CHECK(p.ln_part == nullptr, "tpat_gemm_ln: the folded GEMM writes bf16");
       return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16>(ta, tw, ta, ta, p, st) : launch_tc2<TPAT_EPI_BIAS_GELU, float>(ta, tw, ta, ta, p, st);
+    case TPAT_EPI_DGELU:
+      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_DGELU, __nv_bfloat16>(ta, tw, ta, ta, p, st) : launch_tc2<TPAT_EPI_DGELU, float>(ta, tw, ta, ta, p, st);
     case TPAT_EPI_BIAS_RESIDUAL: {
       // Long-K GEMMs (fc2, K = 3072) hide the register-path epilogue behind the main loop and prefer the fifth
       // pipeline stage; short-K ones (proj, K = 768) are bound by the residual read-modify-write and use the

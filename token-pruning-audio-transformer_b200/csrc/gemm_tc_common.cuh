@@ -34,6 +34,10 @@ struct TcGemmParams {
   const float2* ln_part; int ln_chunks;
   const float* ln_colsum;
   float ln_eps;
+  // training extras (see EpiParams)
+  void* pre_out; int ld_pre;
+  const void* aux; int ld_aux;
+  const float* row_scale; int rows_per_clip;
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
 };
 
@@ -58,6 +62,19 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h * x));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+
+// d/dx of gelu_erf_fast (same fitted form, one MUFU): 0.5 (1 + t) + 0.5 x (1 - t^2) u'(x), u = x (a0 + a1 x^2 + a2 x^4)
+__device__ __forceinline__ float gelu_erf_fast_grad(float x) {
+  const float x2 = fminf(x * x, 81.0f);
+  float h = fmaf(x2, -2.8633e-4f, 0.036609f);
+  h = fmaf(h, x2, 0.797786f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h * x));
+  float du = fmaf(x2, 5.0f * -2.8633e-4f, 3.0f * 0.036609f);
+  du = fmaf(du, x2, 0.797786f);
+  const float s = fmaf(-t, t, 1.0f);                 // 1 - t^2
+  return fmaf(0.5f * x * s, du, fmaf(0.5f, t, 0.5f));
 }
 
 // (mean, rstd) of one row from the partial moments of its 32-element chunks (Chan's pairwise update, fixed order)
@@ -177,12 +194,47 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
     }
     __syncwarp();   // all lanes have read the transpose buffer: the next chunk may overwrite it
     if constexpr (EPI == TPAT_EPI_BIAS_GELU) {
+      if (p.pre_out != nullptr) {            // training: keep the pre-activation for the GELU backward
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = m0 + it * 4 + rl;
+          if (m >= p.M) continue;
+          if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.pre_out) + (size_t)m * p.ld_pre + ncol) = v[it];
+          else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.pre_out) + (size_t)m * p.ld_pre + ncol) =
+                   make_uint2(pack_bf16x2(v[it].x, v[it].y), pack_bf16x2(v[it].z, v[it].w));
+        }
+      }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         v[it].x = gelu_erf_fast(v[it].x); v[it].y = gelu_erf_fast(v[it].y);
         v[it].z = gelu_erf_fast(v[it].z); v[it].w = gelu_erf_fast(v[it].w);
       }
+    } else if constexpr (EPI == TPAT_EPI_DGELU) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int m = m0 + it * 4 + rl;
+        if (m >= p.M) continue;
+        float h0, h1, h2, h3;
+        if constexpr (sizeof(OutT) == 4) {
+          const float4 hh = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (size_t)m * p.ld_aux + ncol));
+          h0 = hh.x; h1 = hh.y; h2 = hh.z; h3 = hh.w;
+        } else {
+          const uint2 hh = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)m * p.ld_aux + ncol));
+          const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162*>(&hh.x), hb = *reinterpret_cast<const __nv_bfloat162*>(&hh.y);
+          h0 = __low2float(ha); h1 = __high2float(ha); h2 = __low2float(hb); h3 = __high2float(hb);
+        }
+        v[it].x *= gelu_erf_fast_grad(h0); v[it].y *= gelu_erf_fast_grad(h1);
+        v[it].z *= gelu_erf_fast_grad(h2); v[it].w *= gelu_erf_fast_grad(h3);
+      }
     } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS) {
+      if (EPI == TPAT_EPI_BIAS_RESIDUAL && p.row_scale != nullptr) {     // DropPath: per-clip scale of the branch
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = min(m0 + it * 4 + rl, p.M - 1);
+          const float sc = __ldg(p.row_scale + m / p.rows_per_clip);
+          v[it].x *= sc; v[it].y *= sc; v[it].z *= sc; v[it].w *= sc;
+        }
+      }
 #pragma unroll
       for (int it = 0; it < 8; ++it) { v[it].x += extra[it].x; v[it].y += extra[it].y; v[it].z += extra[it].z; v[it].w += extra[it].w; }
     }

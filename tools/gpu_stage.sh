@@ -12,7 +12,9 @@ run t00 600 python -m pytest tests/test_gpu_00_kernels.py -q -m gpu -x
 run t10a 600 python -m pytest tests/test_gpu_10_tensorcore.py -q -m gpu -k gemm
 run t10b 600 python -m pytest tests/test_gpu_10_tensorcore.py -q -m gpu -k attention
 run t20 1200 python -m pytest tests/test_gpu_20_forward.py -q -m gpu -s
+run t25 900 python -m pytest tests/test_gpu_25_parity_protocol.py -q -m gpu -s
 run t30 900 python -m pytest tests/test_gpu_30_ablation.py -q -m gpu -s
 run t40 600 python -m pytest tests/test_gpu_40_frontend.py -q -m gpu -s
+run t50 900 python -m pytest tests/test_gpu_50_multigpu.py -q -m gpu -s
 run smoke 300 python __graft_entry__.py --smoke
 run bench 900 python bench.py --steps 10 --warmup 3
