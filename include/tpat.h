@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 7
+#define TPAT_VERSION 8
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -314,6 +314,111 @@ size_t tpat_forward_workspace_bytes(const tpat_forward_args* args);
 int tpat_forward(const tpat_forward_args* args, tpat_stream_t stream);
 /* number of kernels tpat_forward launches for `args` (for bench.py's gpu_launches) */
 int tpat_forward_launch_count(const tpat_forward_args* args);
+
+/* ======================================================================================================
+ * Fine-tune step (BASELINE.json configs[3]): forward that keeps what the backward
+ * needs, and the backward of every op of the path.  Replaces PyTorch autograd over Block.forward
+ * (audiomae/models_vit.py:191-207), Attention.forward (:68-135), Mlp (:40-46), PatchEmbed (:241-247),
+ * forward_features(_mask) (:334-396,466-497) and the head (:522), as driven by train_one_epoch
+ * (audiomae/engine_finetune.py:102-105 forward + loss, util/misc.py:259-273 backward + optimizer step).
+ * ====================================================================================================== */
+
+/* extras of tpat_gemm_train: all optional */
+typedef struct tpat_gemm_extra {
+  void* pre_out; int ld_pre;                     /* TPAT_EPI_BIAS_GELU: also store acc + bias (dtype of C): the GELU backward needs it */
+  const void* aux; int ld_aux;                   /* TPAT_EPI_DGELU: pre-activation h (dtype of C); C = (A W^T) * gelu'(h)            */
+  const float* row_scale; int rows_per_clip;     /* TPAT_EPI_BIAS_RESIDUAL: C = R + row_scale[m / rows_per_clip] * (A W^T + b):
+                                                    timm DropPath's per-sample scale 0 | 1 / keep_prob (models_vit.py:149,198,205)   */
+} tpat_gemm_extra;
+int tpat_gemm_train(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias, void* C, int c_dtype,
+                    int ldc, const float* residual, int ldr, int M, int N, int K, int epilogue, int impl,
+                    const tpat_gemm_extra* extra, tpat_stream_t stream);
+
+/* C[M, N] (+)= op(A) op(B), fp32 CUDA cores, fixed summation order.  trans_a: A is stored [K, M]; trans_b: B is stored
+ * [N, K].  The fp32-parity weight gradient dW += dY^T X (trans_a = 1) and the classifier-head GEMMs of every mode. */
+int tpat_gemm_f32(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc,
+                  int M, int N, int K, int accumulate, tpat_stream_t stream);
+
+/* dst[c][r] = cast(src[r][c]); destination rows padded with zeros up to ld_dst (>= rows).  dtype pairs f32->f32,
+ * f32->bf16, bf16->bf16. */
+int tpat_transpose(const void* src, int src_dtype, int ld_src, void* dst, int dst_dtype, int ld_dst, int rows, int cols,
+                   tpat_stream_t stream);
+
+/* tpat_attention that also writes lse[B, H, N] = log sum_j exp(scale * q_i . k_j) (fp32) for the backward */
+int tpat_attention_train(const void* qkv, void* out, int dtype, float* score_partial, int score_mode, float* lse,
+                         int B, int N, int H, int hd, int num_extra, float scale, int impl, tpat_stream_t stream);
+/* Attention backward: dqkv [B * N, 3 * H * hd] (dtype) from qkv, out (= O), d_out and lse; P is recomputed, nothing of
+ * size N x N touches HBM; no gradient through the importance score / top-k (indices).  delta_ws: B * H * N floats. */
+int tpat_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int dtype,
+                       int B, int N, int H, int hd, float scale, int impl, float* delta_ws, tpat_stream_t stream);
+
+/* floats a `partials_ws` scratch buffer must hold for the three functions below */
+size_t tpat_bwd_partials_floats(int D_max);
+/* inv[b, idx[b, j]] = j, -1 elsewhere: inverse of a top-k list (idx [B, k] int64 with values in [0, n)) */
+int tpat_inverse_index(const int64_t* idx, int32_t* inv, int B, int n, int k, tpat_stream_t stream);
+/*
+ * One pass over the gradient stream (one warp per OUTPUT row):
+ *   g = g_up[src row] (+ LayerNorm backward of dy at the saved LayerNorm input x, when dy != NULL)
+ *   src row of output row (b, j): j + src_offset, or -- with inv -- j < extra ? j : extra + inv[b, j - extra]
+ *   (inv < 0: the token was pruned after this point: zeros; this is the backward of gather + cat, models_vit.py:200-203)
+ *   g_out = g (fp32), gb_out = row_scale[b] * g (gb_dtype; the dY operand of the Linear that produced the branch)
+ *   dgamma += sum dy * xhat, dbeta += sum dy, dbias += column sums of gb_out   (any may be NULL; fixed-order reduction)
+ */
+int tpat_row_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma, const float* g_up, float* g_out,
+                 void* gb_out, int gb_dtype, const float* row_scale, const int32_t* inv, float* partials_ws,
+                 float* dgamma, float* dbeta, float* dbias, int B, int rows_src, int rows_out, int num_extra,
+                 int src_offset, int D, float eps, tpat_stream_t stream);
+/* dst[c] += sum_m x[m, c]  (bias gradient of a Linear from its dY); C % 4 == 0, C <= 4096 */
+int tpat_colsum(const void* x, int dtype, int ld, int M, int C, float* partials_ws, float* dst, tpat_stream_t stream);
+/* out[i] (+)= sum_b x[b * stride + i], i < n  (parameters broadcast over the clips; small column sums) */
+int tpat_batch_sum(const float* x, float* out, int B, size_t stride, int n, int accumulate, tpat_stream_t stream);
+/* backward of tpat_pool_norm: dx [B, N, D] from dpooled [B, D]; dg1 / db1 (and dg2 / db2 for AST) accumulated */
+int tpat_pool_norm_bwd(const float* x, const float* dpooled, float* dx, const float* g1, const float* b1, float eps1,
+                       const float* g2, float eps2, float* partials_ws, float* dg1, float* db1, float* dg2, float* db2,
+                       int B, int N, int D, int variant, tpat_stream_t stream);
+
+/*
+ * torch.optim.AdamW's update over flat buffers (reference optimizer: main_finetune.py:478 on the layer-wise lr-decay
+ * groups of util/lr_decay.py:15-75): p *= 1 - lr_g wd_g; m, v moments; p -= lr_g / bc1 * m / (sqrt(v) / sqrt(bc2) + eps),
+ * g = grad * grad_scale (1 / world size after a SUM all-reduce).  chunks [n_chunks][4] int32 = (offset, length, group, 0),
+ * groups [n_groups][2] fp32 = (lr scale, weight decay).  p_bf16 (optional): bf16 copy of p refreshed in the same pass.
+ */
+int tpat_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunks, int n_chunks,
+               const float* groups, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+               tpat_stream_t stream);
+
+typedef struct {
+  float* ln1_g; float* ln1_b; float* qkv_w; float* qkv_b; float* proj_w; float* proj_b;
+  float* ln2_g; float* ln2_b; float* fc1_w; float* fc1_b; float* fc2_w; float* fc2_b;
+} tpat_block_grads;
+typedef struct { const void* qkv_wt; const void* proj_wt; const void* fc1_wt; const void* fc2_wt; } tpat_block_wt;
+
+typedef struct {
+  tpat_forward_args fwd;     /* model, weights, input, logits / scores / topk_idx, workspace (tpat_forward's fields; fuse_token,
+                                score32 and the LayerNorm fold are not available in training) */
+  void* saved; size_t saved_bytes;                 /* activations kept for the backward (tpat_train_saved_bytes) */
+  const float* drop_scale[TPAT_MAX_DEPTH][2];      /* DropPath: per block, [0] attention branch, [1] MLP branch: [B] fp32 of
+                                                      0 | 1 / keep_prob, or NULL (no drop)                          */
+  const int64_t* mask_keep_idx; int n_keep;        /* fine-tune 2-D masking: patch tokens kept right after the patch embedding
+                                                      ([B, n_keep], models_vit.py:425-497), or NULL                 */
+  /* ---- backward ---- */
+  const float* dlogits;                            /* [B, C] fp32                                                  */
+  tpat_block_wt wt[TPAT_MAX_DEPTH];                /* [in, out] copies of the four matrices, operand dtype (dX = dY W) */
+  tpat_block_grads grads[TPAT_MAX_DEPTH];          /* fp32, ACCUMULATED into (the caller zeroes them); NULL = skip  */
+  float* d_patch_w; float* d_patch_b; float* d_extra_tok; float* d_pos;   /* d_pos NULL for a frozen pos_embed      */
+  float* d_norm_g; float* d_norm_b; float* d_head_ln_g; float* d_head_ln_b; float* d_head_w; float* d_head_b;
+  void* bwd_workspace; size_t bwd_workspace_bytes;
+} tpat_train_args;
+
+size_t tpat_sizeof_train_args(void);
+size_t tpat_train_saved_bytes(const tpat_train_args* args);
+size_t tpat_train_bwd_workspace_bytes(const tpat_train_args* args);
+/* forward in training mode: same math as tpat_forward (+ DropPath scales, + masking), activations kept in `saved` */
+int tpat_train_forward(const tpat_train_args* args, tpat_stream_t stream);
+/* backward stages hi .. lo (inclusive, descending): depth + 1 = head + pooling, i + 1 = block i, 0 = patch embedding.
+ * A full backward is (depth + 1, 0); a caller overlapping the gradient all-reduce with compute (one bucket per block,
+ * main_finetune.py:459-461's DDP) calls it stage by stage.  The gradient stream lives in bwd_workspace between calls. */
+int tpat_train_backward(const tpat_train_args* args, int stage_hi, int stage_lo, tpat_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -72,3 +72,20 @@ MASKED_CONFIGS = {
                                                keep_rate_list=None, flavour="perturbed", wseed=3, xseed=6,
                                                mask_t_prob=0.2, mask_f_prob=0.0, mseed=12),
 }
+
+
+# Fine-tune step: forward + backward of the REAL reference in train mode (DropPath 0.1 as
+# main_finetune.py builds it, BCEWithLogits on seeded multi-hot targets); ``dseed`` seeds the global generator right
+# before the forward (masking noise first, then the DropPath draws).  tests/golden/grad_<name>.pt keeps a compact
+# summary of every parameter gradient (norm, sum, 64 strided samples).
+GRAD_CONFIGS = {
+    "audiomae_256_b2_train": dict(variant="audiomae", T=256, B=2, num_classes=20, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                  keep_rate_list=None, flavour="perturbed", wseed=11, xseed=12, tseed=13, dseed=5,
+                                  mask_t_prob=0.0, mask_f_prob=0.0),
+    "audiomae_256_b2_train_masked": dict(variant="audiomae", T=256, B=2, num_classes=20, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                                         keep_rate_list=(1.0,) * 12, flavour="perturbed", wseed=14, xseed=15, tseed=16, dseed=6,
+                                         mask_t_prob=0.3, mask_f_prob=0.25),
+    "ast_128_b2_train": dict(variant="ast", T=128, B=2, num_classes=35, drop_loc=(3, 6, 9), base_keep_rate=0.7,
+                             keep_rate_list=None, flavour="perturbed", wseed=17, xseed=18, tseed=19, dseed=7,
+                             mask_t_prob=0.0, mask_f_prob=0.0),
+}

@@ -23,7 +23,7 @@ import sys
 import torch
 
 from . import ref_loader, weights, vit_oracle as vo
-from .golden_configs import ABLATION_CONFIGS, GOLDEN_CONFIGS, MASKED_CONFIGS
+from .golden_configs import ABLATION_CONFIGS, GOLDEN_CONFIGS, GRAD_CONFIGS, MASKED_CONFIGS
 
 OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -147,6 +147,70 @@ def main_masked(names=None):
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), kept {keep_idx.shape[1]} of {Tp * 8} patches")
 
 
+def grad_summary(g: torch.Tensor) -> dict:
+    """Compact fingerprint of one gradient tensor: l2 norm, sum, and 64 samples at a fixed stride."""
+    f = g.detach().reshape(-1).double()
+    stride = max(1, f.numel() // 64)
+    return {"norm": f.norm().item(), "sum": f.sum().item(), "numel": f.numel(), "samples": f[::stride][:64].clone()}
+
+
+def make_targets(B, C, seed):
+    return (torch.rand(B, C, generator=torch.Generator().manual_seed(seed)) < 0.1).float()
+
+
+def train_rng_draws(cfg, rates):
+    """The random draws of one reference training forward, in its order: 2-D masking noise (models_vit.py:425-463:
+    time first, then frequency), then the DropPath masks block by block."""
+    torch.manual_seed(cfg["dseed"])
+    keep_idx = None
+    if cfg["mask_t_prob"] > 0 or cfg["mask_f_prob"] > 0:
+        noise_t, noise_f = torch.rand(cfg["B"], cfg["T"] // 16), torch.rand(cfg["B"], 8)
+        keep_idx = vo.masking_2d_keep_indices(noise_t, noise_f, cfg["mask_t_prob"], cfg["mask_f_prob"])
+    return keep_idx, vo.drop_path_scales(rates, cfg["B"])
+
+
+def main_grads(names=None):
+    """tests/golden/grad_<name>.pt: gradients of the real reference's fine-tune step (train mode, autograd)."""
+    assert ref_loader.reference_available(), "run in the build container (needs /root/reference)"
+    for name, cfg in GRAD_CONFIGS.items():
+        if names and name not in names:
+            continue
+        sd, x = make_inputs(cfg)
+        y = make_targets(cfg["B"], cfg["num_classes"], cfg["tseed"])
+        model = build_reference(cfg)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+        model.train()
+        blocks = model.blocks if cfg["variant"] == "audiomae" else model.v.blocks
+        rates = [float(getattr(b.drop_path, "drop_prob", 0.0)) for b in blocks]
+        torch.manual_seed(cfg["dseed"])
+        if cfg["variant"] == "audiomae":
+            logits = model(x, keep_rate_list=cfg["keep_rate_list"], mask_t_prob=cfg["mask_t_prob"], mask_f_prob=cfg["mask_f_prob"])
+        else:
+            logits = model(x, keep_rate_list=cfg["keep_rate_list"])
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)
+        loss.backward()
+        ref_grads = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+        # the restatement under autograd must reproduce them (same draws, fp32): pin before writing
+        keep_idx, scales = train_rng_draws(cfg, rates)
+        frozen = ("pos_embed",) if cfg["variant"] == "audiomae" else ()
+        o_loss, o_logits, o_grads = vo.loss_and_grads(cfg["variant"], sd, x, y, cfg["keep_rate_list"], cfg["drop_loc"],
+                                                      cfg["base_keep_rate"], dtype=torch.float32, drop_scales=scales,
+                                                      mask_keep_idx=keep_idx, frozen=frozen)
+        assert torch.allclose(logits.detach(), o_logits, rtol=0, atol=2e-6 * logits.abs().max().item()), name
+        assert sorted(ref_grads) == sorted(o_grads), (name, sorted(set(ref_grads) ^ set(o_grads)))
+        worst = max(((ref_grads[k] - o_grads[k]).norm() / ref_grads[k].norm().clamp_min(1e-30)).item() for k in ref_grads)
+        assert worst < 1e-4, (name, worst)
+        blob = {"meta": dict(cfg, name=name, torch=torch.__version__, sd_digest=weights.state_dict_digest(sd),
+                             x_digest=hashlib.sha256(x.numpy().tobytes()).hexdigest(), drop_rates=rates),
+                "loss": loss.item(), "logits": logits.detach(), "keep_idx": keep_idx,
+                "grads": {k: grad_summary(v) for k, v in ref_grads.items()}}
+        path = os.path.join(OUT_DIR, "grad_" + name + ".pt")
+        torch.save(blob, path)
+        print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB), {len(ref_grads)} gradient tensors, loss {loss.item():.6f}, "
+              f"oracle(fp32 autograd) vs reference worst rel diff {worst:.2e}")
+
+
 def main_schedule():
     """tests/golden/keep_rate_schedule.pt: outputs of the reference's OWN ``get_scheduled_keep_rate_list``
     (audiomae/engine_finetune.py:29-53).  The module cannot be imported as a whole here (it needs timm.data.Mixup),
@@ -191,6 +255,9 @@ def main_fbank():
 
 if __name__ == "__main__":
     args = sys.argv[1:]
+    if args and args[0] == "grads":
+        main_grads(args[1:])
+        sys.exit(0)
     if args and args[0] == "schedule":
         main_schedule()
         sys.exit(0)

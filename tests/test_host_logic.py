@@ -173,3 +173,54 @@ def test_extract_contract_helpers(tmp_path):
     keep = torch.zeros(2, 64, dtype=torch.bool); keep.scatter_(1, mel[2], True)
     ref = (patches * keep.reshape(2, 1, 8, 1, 8, 1)).reshape(2, 1, 128, 128)
     assert torch.equal(masked, ref)
+
+
+def test_llrd_groups_match_reference_rule():
+    """tpat.lr_decay.param_groups_lrd: layer ids, scales and decay flags as util/lr_decay.py:15-75 assigns them."""
+    from tpat.lr_decay import get_layer_id_for_vit, param_groups_lrd
+    m = build_audiomae(T=128, C=10)
+    m.pos_embed.requires_grad_(False)
+    groups = param_groups_lrd(m, 0.05, no_weight_decay_list=m.no_weight_decay(), layer_decay=0.75)
+    assert len(groups) == 28
+    names = {id(p): n for n, p in m.named_parameters()}
+    for g in groups:
+        ids = {get_layer_id_for_vit(names[id(p)], 13) for p in g["params"]}
+        assert len(ids) == 1
+        lid = ids.pop()
+        assert abs(g["lr_scale"] - 0.75 ** (13 - lid)) < 1e-12
+        for p in g["params"]:
+            no_decay = p.ndim == 1 or names[id(p)] in ("cls_token", "pos_embed")
+            assert g["weight_decay"] == (0.0 if no_decay else 0.05)
+    assert get_layer_id_for_vit("cls_token", 13) == 0 and get_layer_id_for_vit("blocks.11.mlp.fc2.bias", 13) == 12
+    assert get_layer_id_for_vit("fc_norm.weight", 13) == 13 and get_layer_id_for_vit("head.bias", 13) == 13
+    assert sum(len(g["params"]) for g in groups) == 151
+
+
+def test_train_engine_flattens_parameters_by_backward_stage():
+    """TrainEngine.attach (no GPU needed): p.data become views of one flat buffer ordered head -> blocks -> patch embed,
+    each stage's gradients are one contiguous slice (the all-reduce buckets), load_state_dict keeps the views."""
+    from tpat.train import TrainEngine
+    from tpat import _lib
+    m = build_audiomae(T=128, C=10)
+    m.pos_embed.requires_grad_(False)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    eng = TrainEngine(_lib.VARIANT_AUDIOMAE, 12, 768, 12, 3072)
+    roles = m._train_roles()
+    eng.attach(m._train_entries(roles), {})
+    assert len(eng.entries) == 151 and eng.flat_p.numel() % 64 == 0
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    base = eng.flat_p.data_ptr()
+    for _, _, p in eng.entries:
+        off, n = eng.offsets[id(p)]
+        assert p.data_ptr() == base + 4 * off and off % 64 == 0
+    spans = [eng.stage_slices[s] for s in range(13, -1, -1)]
+    assert spans[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert spans[-1][0] + spans[-1][1] == eng.flat_p.numel()
+    flat_id = eng.flat_p.data_ptr()
+    eng.attach(m._train_entries(m._train_roles()), {})           # second call: nothing to rebuild
+    assert eng.flat_p.data_ptr() == flat_id
+    m.load_state_dict(before)                                     # copies INTO the views
+    assert m.head.weight.data_ptr() == base + 4 * eng.offsets[id(m.head.weight)][0]
+    g = eng.grad_view(m.head.bias)
+    assert g.shape == m.head.bias.shape and g.data_ptr() == eng.flat_g.data_ptr() + 4 * eng.offsets[id(m.head.bias)][0]

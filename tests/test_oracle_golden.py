@@ -129,3 +129,58 @@ def test_fbank_oracle_matches_golden_and_mel_table_matches_torchaudio():
             assert int(start[m]) == int(nz[0]) and int(start[m] + length[m] - 1) == int(nz[-1])
     fe = FbankFrontend()
     assert (fe.win, fe.shift, fe.nfft, fe.num_frames(163840)) == (400, 160, 512, 1022)
+
+
+# ---- fine-tune step: the oracle's autograd against the REAL reference's gradients (tests/golden/grad_*.pt) ----------
+
+def _grad_case(cfg):
+    import hashlib
+    from oracle import weights
+    mk = weights.make_audiomae_state_dict if cfg["variant"] == "audiomae" else weights.make_ast_state_dict
+    sd = mk(cfg["num_classes"], cfg["T"], cfg["wseed"], cfg["flavour"])
+    x = weights.make_spectrogram(cfg["variant"], cfg["B"], cfg["T"], cfg["xseed"])
+    assert weights.state_dict_digest(sd) == cfg["sd_digest"] and hashlib.sha256(x.numpy().tobytes()).hexdigest() == cfg["x_digest"]
+    y = (torch.rand(cfg["B"], cfg["num_classes"], generator=torch.Generator().manual_seed(cfg["tseed"])) < 0.1).float()
+    return sd, x, y
+
+
+@pytest.mark.parametrize("name", ["audiomae_256_b2_train", "audiomae_256_b2_train_masked", "ast_128_b2_train"])
+def test_oracle_autograd_reproduces_reference_gradients(name):
+    """Train-mode forward + backward of the restatement (DropPath draws and 2-D masking noise replayed in the reference's
+    RNG order) against the gradient fingerprints of the real reference: loss, logits, and for every parameter the l2
+    norm and 64 strided samples."""
+    g = load_golden("grad_" + name)
+    cfg = g["meta"]
+    sd, x, y = _grad_case(cfg)
+    torch.manual_seed(cfg["dseed"])
+    keep_idx = None
+    if cfg["mask_t_prob"] > 0 or cfg["mask_f_prob"] > 0:
+        noise_t, noise_f = torch.rand(cfg["B"], cfg["T"] // 16), torch.rand(cfg["B"], 8)
+        keep_idx = vo.masking_2d_keep_indices(noise_t, noise_f, cfg["mask_t_prob"], cfg["mask_f_prob"])
+        assert torch.equal(keep_idx, g["keep_idx"])
+    scales = vo.drop_path_scales(cfg["drop_rates"], cfg["B"])
+    frozen = ("pos_embed",) if cfg["variant"] == "audiomae" else ()
+    loss, logits, grads = vo.loss_and_grads(cfg["variant"], sd, x, y, cfg["keep_rate_list"], cfg["drop_loc"], cfg["base_keep_rate"],
+                                            dtype=torch.float32, drop_scales=scales, mask_keep_idx=keep_idx, frozen=frozen)
+    assert abs(loss.item() - g["loss"]) < 1e-6
+    assert torch.allclose(logits, g["logits"], rtol=0, atol=2e-6 * g["logits"].abs().max().item())
+    assert sorted(grads) == sorted(g["grads"])
+    for k, summ in g["grads"].items():
+        f = grads[k].reshape(-1).double()
+        stride = max(1, f.numel() // 64)
+        assert f.numel() == summ["numel"]
+        assert abs(f.norm().item() - summ["norm"]) <= 1e-5 * summ["norm"] + 1e-12, k
+        assert ((f[::stride][:64] - summ["samples"]).norm() / summ["samples"].norm().clamp_min(1e-30)).item() < 1e-4, k
+
+
+def test_oracle_gradient_structure():
+    """No gradient through the score / top-k; dropped tokens still feed the patch-embed gradient through earlier blocks;
+    a clip whose DropPath mask is 0 in every block contributes nothing to the block weights."""
+    from oracle import weights
+    sd = weights.make_audiomae_state_dict(5, 128, 3, "perturbed", depth=2)
+    x = weights.make_spectrogram("audiomae", 2, 128, 4)
+    y = torch.zeros(2, 5); y[:, 1] = 1
+    drops = [(torch.tensor([0.0, 2.0]), torch.tensor([0.0, 2.0]))] * 2
+    _, _, g = vo.loss_and_grads("audiomae", sd, x, y, (0.5, 1.0), (0,), 0.5, num_heads=12, dtype=torch.float64, drop_scales=drops)
+    assert "pos_embed" not in g and len(g) == len([k for k in sd if k != "pos_embed"])
+    assert all(torch.isfinite(v).all() for v in g.values())

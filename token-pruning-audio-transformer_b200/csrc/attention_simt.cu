@@ -35,7 +35,7 @@ template <> struct Ld4<__nv_bfloat16> {
 template <typename T>
 __global__ void __launch_bounds__(256)
 attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ score_partial, int score_mode,
-                      int N, int H, int num_extra, float scale, int n_qt) {
+                      int N, int H, int num_extra, float scale, int n_qt, float* __restrict__ lse) {
   extern __shared__ float sm[];
   pdl_trigger();
   pdl_wait();
@@ -104,6 +104,8 @@ attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __r
       float sum = 0.f;
       for (int j = lane; j < N; j += 32) { const float e = expf(row[j] - mx); row[j] = e; sum += e; }
       sum = warp_sum(sum);
+      // training: log-sum-exp of the scaled scores of this query row (the attention backward recomputes P from it)
+      if (lse != nullptr && lane == 0 && q0 + w * 4 + rr < N) lse[((size_t)b * H + h) * N + q0 + w * 4 + rr] = mx + logf(sum);
       const float inv = 1.0f / sum;
       for (int j = lane; j < Npad; j += 32) row[j] = (j < N) ? row[j] * inv : 0.f;
     }
@@ -171,7 +173,7 @@ attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __r
 int attention_simt_qtiles(int N) { return (N + AS_QT - 1) / AS_QT; }
 
 int attention_simt(const void* qkv, void* out, int dtype, float* score_partial, int score_mode, int B, int N, int H,
-                   int num_extra, float scale, cudaStream_t st) {
+                   int num_extra, float scale, cudaStream_t st, float* lse) {
   const int n_qt = (N + AS_QT - 1) / AS_QT;
   const int Npad = (N + AS_KC - 1) / AS_KC * AS_KC;
   const size_t smem = ((size_t)AS_QT * (Npad + 4) + AS_QT * (AS_HD + 1) + 64 * (AS_HD + 4)) * sizeof(float);
@@ -180,11 +182,11 @@ int attention_simt(const void* qkv, void* out, int dtype, float* score_partial, 
   if (dtype == TPAT_F32) {
     auto kern = attention_simt_kernel<float>;
     TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, (const float*)qkv, (float*)out, score_partial, score_mode, N, H, num_extra, scale, n_qt));
+    TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, (const float*)qkv, (float*)out, score_partial, score_mode, N, H, num_extra, scale, n_qt, lse));
   } else {
     auto kern = attention_simt_kernel<__nv_bfloat16>;
     TPAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, score_partial, score_mode, N, H, num_extra, scale, n_qt));
+    TPAT_CUDA(launch_kernel(kern, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, score_partial, score_mode, N, H, num_extra, scale, n_qt, lse));
   }
   TPAT_LAUNCH_CHECK();
   return 0;

@@ -57,6 +57,7 @@ constexpr float AT_RESCALE_LOG2 = 64.0f;  // online softmax: the reference max i
 struct AttnTcParams {
   long long* trace;   // debug only (TPAT_ATTN_TRACE builds): clock stamps of one softmax thread
   float* score_partial;
+  float* lse;         // training: [B, H, N] natural-log sum of exp(scale * s) per query row, or NULL
   int score_mode;
   int N, H, num_extra, n_qt, nb, qt_offset;
   int desc;          // 1 = clips are visited from the last one down (see g_walk_desc)
@@ -310,6 +311,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     // exponent offset: p = 2^(s*c - off).  Two-pass tiles fold log2(l) in (normalised probabilities).
     float off = TWO_PASS ? fmaf(m_run, c, __log2f(l_run)) : 0.f;
+    if (TWO_PASS && p.lse != nullptr && half == 0 && warp_live && row < p.N)
+      p.lse[((size_t)b * p.H + h) * p.N + row] = off * 0.69314718055994531f;
     const float row_w = (row >= p.num_extra && row < p.N) ? 1.0f : 0.f;
     const bool cls_writer = TWO_PASS && (p.score_mode == TPAT_SCORE_CLS_ROW) && (row == 0);
     float* colsum_w = colsum_s + (size_t)quarter * nb * AT_BK;
@@ -452,7 +455,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float l_own = (l2a + l2b) + (l2c + l2d);
       my_x->y = l_own;
       pair_sync();
-      o_scale = 1.0f / (l_own + other_x->y);
+      const float l_tot = l_own + other_x->y;
+      o_scale = 1.0f / l_tot;
+      if (p.lse != nullptr && half == 0 && row < p.N)
+        p.lse[((size_t)b * p.H + h) * p.N + row] = fmaf(m_run, c, __log2f(l_tot)) * 0.69314718055994531f;
     }
     // ---- epilogue: O (TMEM) -> bf16 -> swizzled smem tile -> one TMA store ----
     ATTN_TRACE(9);
@@ -527,7 +533,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUte
 }
 
 int attention_tc(const void* qkv, void* out, float* score_partial, int score_mode, int B, int N, int H,
-                 int num_extra, float scale, cudaStream_t st, const void* qk_planes) {
+                 int num_extra, float scale, cudaStream_t st, const void* qk_planes, float* lse) {
   TPAT_CHECK(N <= 4096, "tpat_attention(tc): N=%d too large (max 4096)", N);
   TPAT_CHECK(qk_planes == nullptr || score_mode != TPAT_SCORE_NONE, "tpat_attention(tc): split q / k planes are for score blocks only");
   CUtensorMap tm_q, tm_kv, tm_o, tm_qs, tm_ks;
@@ -545,6 +551,7 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
     extern long long* g_attn_trace_buf; g_attn_trace_buf = dbg; }
 #endif
   p.score_partial = score_partial;
+  p.lse = lse;
   p.score_mode = score_mode;
   p.N = N; p.H = H; p.num_extra = num_extra;
   p.n_qt = attention_tc_qtiles(N);

@@ -32,7 +32,8 @@ struct Workspace {
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
-static int validate(const tpat_forward_args* a) {
+int validate_forward_args(const tpat_forward_args* a) {
+  // (shared with train.cu)
   TPAT_CHECK(a != nullptr, "tpat_forward: null args");
   TPAT_CHECK(a->variant == TPAT_VARIANT_AUDIOMAE || a->variant == TPAT_VARIANT_AST, "tpat_forward: bad variant %d", a->variant);
   TPAT_CHECK(a->impl == TPAT_IMPL_SIMT || a->impl == TPAT_IMPL_TC, "tpat_forward: bad impl %d", a->impl);
@@ -96,12 +97,12 @@ static Workspace carve(const tpat_forward_args* a, uint8_t* base) {
 }  // namespace tpat
 
 extern "C" size_t tpat_forward_workspace_bytes(const tpat_forward_args* a) {
-  if (tpat::validate(a) != 0) return 0;
+  if (tpat::validate_forward_args(a) != 0) return 0;
   return tpat::carve(a, nullptr).bytes;
 }
 
 extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
-  if (tpat::validate(a) != 0) return -1;
+  if (tpat::validate_forward_args(a) != 0) return -1;
   using tpat::fold_ln1; using tpat::fold_ln2;
   int n = 2;  // patchify + patch GEMM
   const int extra = a->variant == TPAT_VARIANT_AST ? 2 : 1;
@@ -123,7 +124,7 @@ extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
 
 extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
   using namespace tpat;
-  if (int rc = validate(a)) return rc;
+  if (int rc = validate_forward_args(a)) return rc;
   TPAT_CHECK(a->spec && a->logits && a->workspace, "tpat_forward: null spec / logits / workspace");
   TPAT_CHECK(aligned16(a->workspace), "tpat_forward: workspace must be 16-byte aligned");
   Workspace w = carve(a, reinterpret_cast<uint8_t*>(a->workspace));

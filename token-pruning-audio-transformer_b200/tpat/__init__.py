@@ -6,7 +6,7 @@ CUDA behind the C-ABI in include/tpat.h).  Importing this package loads the shar
 fails loudly if it is missing: there is no CPU or PyTorch fallback.
 """
 from . import _lib  # noqa: F401  (loads libtpat.so, verifies every symbol of include/tpat.h)
-from . import ops, engine, models_vit, ast_models, extract, frontend, schedule  # noqa: F401
+from . import ops, engine, models_vit, ast_models, extract, frontend, schedule, train, optim, lr_decay  # noqa: F401
 from .models_vit import VisionTransformer, vit_base_patch16  # noqa: F401
 from .ast_models import ASTModel  # noqa: F401
 from .frontend import FbankFrontend  # noqa: F401

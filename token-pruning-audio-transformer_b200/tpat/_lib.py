@@ -13,9 +13,9 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("TPAT_LIB_PATH") or os.path.join(_PKG_ROOT, "lib", "libtpat.so")   # override: kernel experiments
 
 TPAT_MAX_DEPTH = 32
-TPAT_VERSION = 7          # must equal TPAT_VERSION in include/tpat.h (checked at load)
+TPAT_VERSION = 8          # must equal TPAT_VERSION in include/tpat.h (checked at load)
 F32, BF16, BF16_SPLIT3 = 0, 1, 2
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_POS = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_POS, EPI_DGELU = 0, 1, 2, 3, 4
 IMPL_SIMT, IMPL_TC = 0, 1
 SCORE_NONE, SCORE_CLS_ROW, SCORE_COLMEAN = 0, 1, 2
 TOKENS_TIME_MAJOR, TOKENS_FREQ_MAJOR = 0, 1
@@ -52,6 +52,40 @@ class ForwardArgs(Structure):
     ]
 
 
+class GemmExtra(Structure):
+    """tpat_gemm_extra (include/tpat.h)."""
+    _fields_ = [("pre_out", c_void_p), ("ld_pre", c_int), ("aux", c_void_p), ("ld_aux", c_int), ("row_scale", c_void_p),
+                ("rows_per_clip", c_int)]
+
+
+BLOCK_GRAD_NAMES = ("ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
+
+
+class BlockGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in BLOCK_GRAD_NAMES]
+
+
+class BlockWt(Structure):
+    _fields_ = [(n, c_void_p) for n in ("qkv_wt", "proj_wt", "fc1_wt", "fc2_wt")]
+
+
+class TrainArgs(Structure):
+    """tpat_train_args (include/tpat.h)."""
+    _fields_ = [
+        ("fwd", ForwardArgs),
+        ("saved", c_void_p), ("saved_bytes", c_size_t),
+        ("drop_scale", (c_void_p * 2) * TPAT_MAX_DEPTH),
+        ("mask_keep_idx", c_void_p), ("n_keep", c_int),
+        ("dlogits", c_void_p),
+        ("wt", BlockWt * TPAT_MAX_DEPTH),
+        ("grads", BlockGrads * TPAT_MAX_DEPTH),
+        ("d_patch_w", c_void_p), ("d_patch_b", c_void_p), ("d_extra_tok", c_void_p), ("d_pos", c_void_p),
+        ("d_norm_g", c_void_p), ("d_norm_b", c_void_p), ("d_head_ln_g", c_void_p), ("d_head_ln_b", c_void_p),
+        ("d_head_w", c_void_p), ("d_head_b", c_void_p),
+        ("bwd_workspace", c_void_p), ("bwd_workspace_bytes", c_size_t),
+    ]
+
+
 # every symbol include/tpat.h declares: (restype, argtypes)
 SIGNATURES = {
     "tpat_version": (c_int, []),
@@ -82,6 +116,29 @@ SIGNATURES = {
                            c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_void_p]),
     "tpat_patch_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tpat_gather_rank": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tpat_gemm_train": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                c_int, c_int, c_int, c_int, c_int, POINTER(GemmExtra), c_void_p]),
+    "tpat_gemm_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_transpose": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_attention_train": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_float, c_int, c_void_p]),
+    "tpat_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                   c_int, c_void_p, c_void_p]),
+    "tpat_bwd_partials_floats": (c_size_t, [c_int]),
+    "tpat_inverse_index": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "tpat_row_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "tpat_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tpat_batch_sum": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_int, c_int, c_void_p]),
+    "tpat_pool_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_float,
+                           c_float, c_float, c_int, c_float, c_void_p]),
+    "tpat_sizeof_train_args": (c_size_t, []),
+    "tpat_train_saved_bytes": (c_size_t, [POINTER(TrainArgs)]),
+    "tpat_train_bwd_workspace_bytes": (c_size_t, [POINTER(TrainArgs)]),
+    "tpat_train_forward": (c_int, [POINTER(TrainArgs), c_void_p]),
+    "tpat_train_backward": (c_int, [POINTER(TrainArgs), c_int, c_int, c_void_p]),
     "tpat_sizeof_forward_args": (c_size_t, []),
     "tpat_forward_workspace_bytes": (c_size_t, [POINTER(ForwardArgs)]),
     "tpat_forward": (c_int, [POINTER(ForwardArgs), c_void_p]),
@@ -113,6 +170,8 @@ def _load():
         raise ImportError(f"libtpat.so is version {lib.tpat_version()}, tpat/_lib.py expects {TPAT_VERSION}")
     if lib.tpat_sizeof_forward_args() != ctypes.sizeof(ForwardArgs):
         raise ImportError("ForwardArgs layout does not match the tpat_forward_args compiled into libtpat.so")
+    if lib.tpat_sizeof_train_args() != ctypes.sizeof(TrainArgs):
+        raise ImportError("TrainArgs layout does not match the tpat_train_args compiled into libtpat.so")
     return lib
 
 

@@ -200,6 +200,46 @@ class ASTModel(nn.Module):
         """Call after changing weights through ``p.data`` (no version bump): drops bf16 copies and captured graphs."""
         self._engines.invalidate()
 
+    # ---- fine-tune step (training mode, autograd enabled) ---------------------------------------
+    def _train_roles(self):
+        v = self.v
+        top = {"patch_w": v.patch_embed.proj.weight, "patch_b": v.patch_embed.proj.bias,
+               # cls and dist sit next to each other in the flat parameter buffer: one [2, D] extra-token table
+               "extra_tok": v.cls_token, "extra_tok_first": v.cls_token, "pos": v.pos_embed,
+               "norm_g": v.norm.weight, "norm_b": v.norm.bias,
+               "head_ln_g": self.mlp_head[0].weight, "head_ln_b": self.mlp_head[0].bias,
+               "head_w": self.mlp_head[1].weight, "head_b": self.mlp_head[1].bias}
+        return top, [block_tensors(b) for b in v.blocks[:self.depth]]
+
+    def _train_entries(self, roles):
+        top, blocks = roles
+        depth = len(blocks)
+        ent = [(depth + 1, r, top[r]) for r in ("head_w", "head_b", "head_ln_g", "head_ln_b", "norm_g", "norm_b")]
+        for i in reversed(range(depth)):
+            ent += [(i + 1, r, blocks[i][r]) for r in _lib.BLOCK_GRAD_NAMES]
+        ent += [(0, "patch_w", top["patch_w"]), (0, "patch_b", top["patch_b"]), (0, "cls", self.v.cls_token),
+                (0, "dist", self.v.dist_token), (0, "pos", self.v.pos_embed)]
+        return ent
+
+    def _forward_train(self, x, rates):
+        """ast_models.py:424-508 in training mode (DropPath of timm 0.4.5), recorded for the native backward.  The
+        unused DeiT heads (v.head, v.head_dist) get no gradient, as in the reference."""
+        from .train import drop_path_scales, run_train_step_forward
+        B = x.shape[0]
+        if not (self.v.cls_token.requires_grad and self.v.dist_token.requires_grad):
+            raise NotImplementedError("cls_token and dist_token must both be trainable (they share one extra-token table)")
+        engine = self._engines.get_train(self._device_of_params())
+        roles = self._train_roles()
+        engine.attach(self._train_entries(roles), {})
+        scales = getattr(self, "_drop_scales_override", None)
+        if scales is None:
+            scales = drop_path_scales([b.drop_path_rate for b in self.v.blocks[:self.depth]], B, x.device, timm_04_style=True)
+        with torch.cuda.device(x.device):
+            logits, scores, idxs = run_train_step_forward(engine, self.v.cls_token, x, rates, self.label_dim, self.precision,
+                                                          roles, drop_scales=scales)
+        self.last_scores, self.last_topk_idx = scores, idxs
+        return logits
+
     def forward(self, x, keep_rate_list: Union[list, tuple, type(None)] = None, flag_extract_features: bool = False):
         """x [B, time_frame_num, frequency_bins], e.g. (12, 1024, 128) (ast_models.py:431)."""
         if (keep_rate_list is not None) and (len(keep_rate_list) != len(self.v.blocks)):
@@ -209,6 +249,9 @@ class ASTModel(nn.Module):
         if self.v.pos_embed.shape[1] != n_patches + 2:
             raise RuntimeError(f"pos_embed has {self.v.pos_embed.shape[1]} rows but the input has {n_patches} patches + 2")
         rates = resolve_keep_rates(keep_rate_list, self.v.blocks)
+        if self.training and torch.is_grad_enabled() and self.use_custom_rank is None and self.drop_token_blk_idx is None:
+            assert flag_extract_features == False, "extract mode is an eval-time path"
+            return self._forward_train(x, rates)
         self._engine.pack(self._engine_tensors, self._pack_key())
         if self.use_custom_rank is not None or self.drop_token_blk_idx is not None:
             # ablation paths (ast_models.py:445-457,480-497): kernel-by-kernel forward

@@ -70,6 +70,7 @@ class EnginePool:
         self._args = engine_args
         self._lock = threading.Lock()
         self._engines: Dict[int, "ForwardEngine"] = {}
+        self._train: Dict[int, object] = {}
         self.ln_fold = os.environ.get("TPAT_LN_FOLD", "0")
         self.graph_static_io = False
 
@@ -83,10 +84,22 @@ class EnginePool:
                 self._engines[idx] = e
             return e
 
+    def get_train(self, device: torch.device):
+        """The TrainEngine (fine-tune step: flat parameter / gradient buffers, saved activations) of ``device``."""
+        from .train import TrainEngine
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        with self._lock:
+            e = self._train.get(idx)
+            if e is None:
+                e = self._train[idx] = TrainEngine(*self._args)
+            return e
+
     def invalidate(self) -> None:
         with self._lock:
             for e in self._engines.values():
                 e.invalidate()
+            for e in self._train.values():
+                e.mark_updated()
 
 
 def param_key(module) -> tuple:

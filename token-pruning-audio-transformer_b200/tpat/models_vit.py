@@ -17,10 +17,11 @@ parameters to ``engine.ForwardEngine`` which makes one ``tpat_forward`` call int
 (hand-written sm_100a kernels).  There is no CPU fallback.
 
 Differences from the reference, stated (not hidden):
-  * forward is inference-only in this round (no autograd graph); DropPath is therefore identity,
-    as in the reference's eval mode.  The ablation paths (custom_rank, drop_token_blk_idx) and
-    the forward half of the fine-tune 2-D token masking (mask_t_prob / mask_f_prob > 0; row a11) run kernel by
-    kernel through ``ForwardEngine.run_stepwise``; there is no backward pass.
+  * in training mode with autograd enabled ``forward`` runs the native fine-tune step (tpat/train.py: DropPath, 2-D
+    token masking, activations kept, ONE autograd node whose backward is ``tpat_train_backward``); parameters then
+    live in one flat buffer (``p.data`` / ``p.grad`` are views).  In eval mode / under ``no_grad`` it is the
+    inference path (DropPath identity).  The ablation paths (custom_rank, drop_token_blk_idx) and
+    eval-mode masking run kernel by kernel through ``ForwardEngine.run_stepwise`` (no backward).
   * torch.topk leaves the order of exactly tied scores unspecified; here ties go to the lower index.
   * extra constructor keyword ``fuse_token`` (default False): EViT's fused inattentive token, which BASELINE.json
     configs[2] names but the reference forward never implemented -- semantics from upstream EViT.
@@ -249,6 +250,45 @@ class VisionTransformer(nn.Module):
         ids_f = torch.argsort(noise_f, dim=1)[:, :len_keep_F]
         return (ids_t[:, :, None] * F + ids_f[:, None, :]).reshape(B, len_keep_T * len_keep_F).contiguous()
 
+    # ---- fine-tune step (training mode, autograd enabled) ---------------------------------------
+    def _train_roles(self):
+        top = {"patch_w": self.patch_embed.proj.weight, "patch_b": self.patch_embed.proj.bias,
+               "extra_tok": self.cls_token, "extra_tok_first": self.cls_token, "pos": self.pos_embed,
+               "norm_g": self.fc_norm.weight, "norm_b": self.fc_norm.bias, "head_ln_g": None, "head_ln_b": None,
+               "head_w": self.head.weight, "head_b": self.head.bias}
+        return top, [block_tensors(b) for b in self.blocks]
+
+    def _train_entries(self, roles):
+        """(stage, role, parameter) in backward order: head / final norm, blocks last to first, patch embedding."""
+        top, blocks = roles
+        depth = len(blocks)
+        ent = [(depth + 1, r, top[r]) for r in ("head_w", "head_b", "norm_g", "norm_b")]
+        for i in reversed(range(depth)):
+            ent += [(i + 1, r, blocks[i][r]) for r in _lib.BLOCK_GRAD_NAMES]
+        ent += [(0, "patch_w", top["patch_w"]), (0, "patch_b", top["patch_b"]), (0, "cls", self.cls_token), (0, "pos", self.pos_embed)]
+        return ent
+
+    def _forward_train(self, x, rates, mask_t_prob, mask_f_prob):
+        """models_vit.py:502-522 in training mode: 2-D token masking (:425-497) while mask probabilities are set,
+        DropPath (:149,198,205) with the block's stochastic-depth rate, everything recorded for the native backward."""
+        from .train import drop_path_scales, run_train_step_forward
+        B, _, T, F = x.shape
+        engine = self._engines.get_train(self._device_of_params())
+        roles = self._train_roles()
+        engine.attach(self._train_entries(roles), {})
+        keep_idx = None
+        if mask_t_prob > 0.0 or mask_f_prob > 0.0:
+            keep_idx = self.random_masking_2d_indices(B, x.device, mask_t_prob, mask_f_prob,
+                                                      noise=getattr(self, "_mask_noise_override", None))
+        scales = getattr(self, "_drop_scales_override", None)       # tests inject the oracle's draws (CPU generator)
+        if scales is None:
+            scales = drop_path_scales([b.drop_path_rate for b in self.blocks], B, x.device)
+        with torch.cuda.device(x.device):
+            logits, scores, idxs = run_train_step_forward(engine, self.cls_token, x.reshape(B, T, F), rates, self.num_classes,
+                                                          self.precision, roles, drop_scales=scales, mask_keep_idx=keep_idx)
+        self.last_scores, self.last_topk_idx = scores, idxs
+        return logits
+
     def forward_features(self, x, keep_rate_list=None, flag_extract_features: bool = False):
         """``fc_norm(x[:, 1:].mean(1))`` after the 12 blocks (models_vit.py:334-396): the classifier input, [B, D] fp32 --
         or ``(outcome, feature_dict)`` in extract mode.  Computed by the same native call as ``forward`` (the head GEMM
@@ -276,6 +316,9 @@ class VisionTransformer(nn.Module):
         if self.pos_embed.shape[1] != n_patches + 1:
             raise RuntimeError(f"pos_embed has {self.pos_embed.shape[1]} rows but the input has {n_patches} patches + cls")
         rates = resolve_keep_rates(keep_rate_list, self.blocks)
+        if self.training and torch.is_grad_enabled() and self.use_custom_rank is None and self.drop_token_blk_idx is None:
+            assert flag_extract_features == False, "extract mode is an eval-time path"
+            return self._forward_train(x, rates, mask_t_prob, mask_f_prob)
         self._engine.pack(self._engine_tensors, self._pack_key())
         spec = x.reshape(B, T, F)
         if masking:

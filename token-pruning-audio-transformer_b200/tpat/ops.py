@@ -214,3 +214,146 @@ def head(pooled: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) ->
     out = torch.empty(B, C, device=pooled.device, dtype=torch.float32)
     check(lib.tpat_head(pooled.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), B, D, C, _stream()), "tpat_head")
     return out
+
+
+# ---- fine-tune step: per-kernel wrappers (tests / hand assembly; the model classes use train.TrainEngine) ----------
+
+_partials_ws = {}
+
+
+def _partials(device) -> torch.Tensor:
+    t = _partials_ws.get(device)
+    if t is None:
+        t = _partials_ws[device] = torch.empty(lib.tpat_bwd_partials_floats(4096), device=device, dtype=torch.float32)
+    return t
+
+
+def gemm_f32(a: torch.Tensor, b: torch.Tensor, trans_a: int = 0, trans_b: int = 0, out: Optional[torch.Tensor] = None,
+             accumulate: bool = False) -> torch.Tensor:
+    """out (+)= op(a) @ op(b), fp32 CUDA cores.  trans_a: a is stored [K, M]; trans_b: b is stored [N, K]."""
+    _req(a, torch.float32, "a"); _req(b, torch.float32, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    check(lib.tpat_gemm_f32(a.data_ptr(), a.shape[1], int(trans_a), b.data_ptr(), b.shape[1], int(trans_b), out.data_ptr(), N, M, N, K,
+                            1 if accumulate else 0, _stream()), "tpat_gemm_f32")
+    return out
+
+
+def transpose(x: torch.Tensor, out_dtype: torch.dtype, ld_dst: Optional[int] = None) -> torch.Tensor:
+    """x [rows, cols] -> [cols, ld_dst] (zero-padded beyond rows), cast to out_dtype."""
+    _req(x, name="x")
+    rows, cols = x.shape
+    ld = rows if ld_dst is None else ld_dst
+    out = torch.empty(cols, ld, device=x.device, dtype=out_dtype)
+    check(lib.tpat_transpose(x.data_ptr(), _DT[x.dtype], cols, out.data_ptr(), _DT[out_dtype], ld, rows, cols, _stream()), "tpat_transpose")
+    return out
+
+
+def row_bwd(dy: Optional[torch.Tensor], x: Optional[torch.Tensor], gamma: Optional[torch.Tensor], g_up: Optional[torch.Tensor],
+            op_dtype: torch.dtype, row_scale: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None, n_in: int = 0,
+            extra: int = 0, eps: float = 1e-6, src_offset: int = 0, rows_out: Optional[int] = None):
+    """tpat_row_bwd: (g_out fp32, gb op_dtype, dgamma, dbeta, dbias).  With ``idx`` [B, k] the rows are scattered back to
+    [B, extra + n_in, D] (backward of the token gather)."""
+    ref = dy if dy is not None else g_up
+    B, rows_src, D = ref.shape
+    inv = None
+    if idx is not None:
+        inv = torch.empty(B, n_in, device=ref.device, dtype=torch.int32)
+        check(lib.tpat_inverse_index(idx.contiguous().data_ptr(), inv.data_ptr(), B, n_in, idx.shape[1], _stream()), "tpat_inverse_index")
+        r_out = extra + n_in
+    else:
+        r_out = rows_out if rows_out is not None else rows_src - src_offset
+    g_out = torch.empty(B, r_out, D, device=ref.device, dtype=torch.float32)
+    gb = torch.empty(B, r_out, D, device=ref.device, dtype=op_dtype)
+    dg = torch.zeros(D, device=ref.device); db = torch.zeros(D, device=ref.device); dbias = torch.zeros(D, device=ref.device)
+    check(lib.tpat_row_bwd(_ptr(dy), _DT[dy.dtype] if dy is not None else _lib.F32, _ptr(x), _ptr(gamma), _ptr(g_up), g_out.data_ptr(),
+                           gb.data_ptr(), _DT[op_dtype], _ptr(row_scale), _ptr(inv), _partials(ref.device).data_ptr(), dg.data_ptr(),
+                           db.data_ptr(), dbias.data_ptr(), B, rows_src, r_out, extra, src_offset, D, float(eps), _stream()), "tpat_row_bwd")
+    return g_out, gb, dg, db, dbias
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    _req(x, name="x")
+    M, C = x.shape
+    out = torch.zeros(C, device=x.device, dtype=torch.float32)
+    check(lib.tpat_colsum(x.data_ptr(), _DT[x.dtype], C, M, C, _partials(x.device).data_ptr(), out.data_ptr(), _stream()), "tpat_colsum")
+    return out
+
+
+def batch_sum(x: torch.Tensor) -> torch.Tensor:
+    """x [B, n] fp32 -> sum over dim 0."""
+    _req(x, torch.float32, "x")
+    B, n = x.shape
+    out = torch.empty(n, device=x.device, dtype=torch.float32)
+    check(lib.tpat_batch_sum(x.data_ptr(), out.data_ptr(), B, n, n, 0, _stream()), "tpat_batch_sum")
+    return out
+
+
+def pool_norm_bwd(x: torch.Tensor, dpooled: torch.Tensor, variant: int, g1, b1, eps1: float, g2=None, eps2: float = 0.0):
+    _req(x, torch.float32, "x"); _req(dpooled, torch.float32, "dpooled")
+    B, N, D = x.shape
+    dx = torch.empty_like(x)
+    outs = [torch.zeros(D, device=x.device) for _ in range(4)]
+    check(lib.tpat_pool_norm_bwd(x.data_ptr(), dpooled.data_ptr(), dx.data_ptr(), g1.data_ptr(), b1.data_ptr(), float(eps1), _ptr(g2),
+                                 float(eps2), _partials(x.device).data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                                 outs[3].data_ptr(), B, N, D, variant, _stream()), "tpat_pool_norm_bwd")
+    return (dx, *outs)
+
+
+def attention_train(qkv: torch.Tensor, B: int, N: int, H: int, num_extra: int, score_mode: int, impl: int):
+    """Training forward of the fused attention: (out, lse [B, H, N] fp32)."""
+    _req(qkv, name="qkv")
+    out = torch.empty(B * N, H * 64, device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32)
+    partial = None
+    if score_mode == _lib.SCORE_CLS_ROW:
+        partial = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32)
+    elif score_mode == _lib.SCORE_COLMEAN:
+        partial = torch.empty(B, H * attention_qtiles(N, impl), N, device=qkv.device, dtype=torch.float32)
+    check(lib.tpat_attention_train(qkv.data_ptr(), out.data_ptr(), _DT[qkv.dtype], _ptr(partial), score_mode, lse.data_ptr(), B, N, H,
+                                   64, num_extra, 64 ** -0.5, impl, _stream()), "tpat_attention_train")
+    return out, lse
+
+
+def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, lse: torch.Tensor, B: int, N: int, H: int, impl: int
+                  ) -> torch.Tensor:
+    _req(qkv, name="qkv"); _req(out, qkv.dtype, "out"); _req(d_out, qkv.dtype, "d_out"); _req(lse, torch.float32, "lse")
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B * H * N, device=qkv.device, dtype=torch.float32)
+    check(lib.tpat_attention_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), _DT[qkv.dtype], B, N,
+                                 H, 64, 64 ** -0.5, impl, delta.data_ptr(), _stream()), "tpat_attention_bwd")
+    return dqkv
+
+
+def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dtype: torch.dtype, epilogue: int, impl: int,
+               residual: Optional[torch.Tensor] = None, want_pre: bool = False, aux: Optional[torch.Tensor] = None,
+               row_scale: Optional[torch.Tensor] = None, rows_per_clip: int = 0):
+    """tpat_gemm_train: out = epilogue(a @ w.T + bias) with the training extras (pre-activation output, GELU-backward
+    epilogue, DropPath row scale)."""
+    import ctypes
+    _req(a, name="a"); _req(w, a.dtype, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    ex = _lib.GemmExtra()
+    pre = None
+    if want_pre:
+        pre = torch.empty(M, N, device=a.device, dtype=out_dtype)
+        ex.pre_out, ex.ld_pre = pre.data_ptr(), N
+    if aux is not None:
+        _req(aux, out_dtype, "aux")
+        ex.aux, ex.ld_aux = aux.data_ptr(), N
+    if row_scale is not None:
+        ex.row_scale, ex.rows_per_clip = row_scale.data_ptr(), rows_per_clip
+    check(lib.tpat_gemm_train(a.data_ptr(), _DT[a.dtype], K, w.data_ptr(), _DT[w.dtype], _ptr(bias), out.data_ptr(), _DT[out_dtype], N,
+                              _ptr(residual), N if residual is not None else 0, M, N, K, epilogue, impl, ctypes.byref(ex), _stream()),
+          "tpat_gemm_train")
+    return (out, pre) if want_pre else out
+
+
+def adamw(p, g, m, v, p_bf16, chunks, groups, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    check(lib.tpat_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_bf16), chunks.data_ptr(), chunks.shape[0],
+                         groups.data_ptr(), float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_scale), _stream()),
+          "tpat_adamw")
