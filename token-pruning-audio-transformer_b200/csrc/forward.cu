@@ -32,8 +32,8 @@ struct Workspace {
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
-int validate_forward_args(const tpat_forward_args* a) {
-  // (shared with train.cu)
+int validate_forward_args(const tpat_forward_args* a, int n0) {
+  // (shared with train.cu; n0 > 0: patch tokens entering block 0 when the fine-tune 2-D masking dropped some)
   TPAT_CHECK(a != nullptr, "tpat_forward: null args");
   TPAT_CHECK(a->variant == TPAT_VARIANT_AUDIOMAE || a->variant == TPAT_VARIANT_AST, "tpat_forward: bad variant %d", a->variant);
   TPAT_CHECK(a->impl == TPAT_IMPL_SIMT || a->impl == TPAT_IMPL_TC, "tpat_forward: bad impl %d", a->impl);
@@ -41,7 +41,7 @@ int validate_forward_args(const tpat_forward_args* a) {
   TPAT_CHECK(a->depth > 0 && a->depth <= TPAT_MAX_DEPTH, "tpat_forward: depth %d out of range", a->depth);
   TPAT_CHECK(a->D > 0 && a->D % 128 == 0 && a->H > 0 && a->D == a->H * 64, "tpat_forward: need D == 64*H and D %% 128 == 0 (D=%d H=%d)", a->D, a->H);
   TPAT_CHECK(a->Dh > 0 && a->Dh % 64 == 0 && a->num_classes > 0, "tpat_forward: bad Dh=%d or num_classes=%d", a->Dh, a->num_classes);
-  int n = (a->T / 16) * (a->F / 16);
+  int n = n0 > 0 ? n0 : (a->T / 16) * (a->F / 16);
   for (int i = 0; i < a->depth; ++i) {
     TPAT_CHECK(a->keep[i] > 0 && a->keep[i] <= n, "tpat_forward: keep[%d]=%d must be in (0, %d]", i, a->keep[i], n);
     TPAT_CHECK(a->prune[i] || a->keep[i] == n, "tpat_forward: block %d drops tokens (%d -> %d) but prune[%d] is 0", i, n, a->keep[i], i);
@@ -97,12 +97,12 @@ static Workspace carve(const tpat_forward_args* a, uint8_t* base) {
 }  // namespace tpat
 
 extern "C" size_t tpat_forward_workspace_bytes(const tpat_forward_args* a) {
-  if (tpat::validate_forward_args(a) != 0) return 0;
+  if (tpat::validate_forward_args(a, 0) != 0) return 0;
   return tpat::carve(a, nullptr).bytes;
 }
 
 extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
-  if (tpat::validate_forward_args(a) != 0) return -1;
+  if (tpat::validate_forward_args(a, 0) != 0) return -1;
   using tpat::fold_ln1; using tpat::fold_ln2;
   int n = 2;  // patchify + patch GEMM
   const int extra = a->variant == TPAT_VARIANT_AST ? 2 : 1;
@@ -124,7 +124,7 @@ extern "C" int tpat_forward_launch_count(const tpat_forward_args* a) {
 
 extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
   using namespace tpat;
-  if (int rc = validate_forward_args(a)) return rc;
+  if (int rc = validate_forward_args(a, 0)) return rc;
   TPAT_CHECK(a->spec && a->logits && a->workspace, "tpat_forward: null spec / logits / workspace");
   TPAT_CHECK(aligned16(a->workspace), "tpat_forward: workspace must be 16-byte aligned");
   Workspace w = carve(a, reinterpret_cast<uint8_t*>(a->workspace));

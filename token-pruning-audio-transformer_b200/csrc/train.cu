@@ -18,7 +18,7 @@
 
 namespace tpat {
 
-int validate_forward_args(const tpat_forward_args* a);
+int validate_forward_args(const tpat_forward_args* a, int n0);
 
 static size_t al(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -112,8 +112,8 @@ static BwdWs carve_bwd(const tpat_train_args* t, uint8_t* base) {
 
 static int validate_train(const tpat_train_args* t) {
   TPAT_CHECK(t != nullptr, "tpat_train: null args");
-  if (int rc = validate_forward_args(&t->fwd)) return rc;
   const tpat_forward_args* a = &t->fwd;
+  if (int rc = validate_forward_args(a, t->mask_keep_idx ? t->n_keep : 0)) return rc;
   TPAT_CHECK(!a->fuse_token && !a->score32, "tpat_train: fuse_token / score32 are inference-only");
   const int P = (a->T / 16) * (a->F / 16);
   if (t->mask_keep_idx) TPAT_CHECK(t->n_keep > 0 && t->n_keep <= P, "tpat_train: n_keep=%d out of range (0, %d]", t->n_keep, P);
