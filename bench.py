@@ -357,7 +357,7 @@ def run_train(args, rank, world, local_rank):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    last_loss = float(loss)
+    last_loss = float(loss.detach())
     # the same without the gradient all-reduce: what the collective costs after overlap
     ms_nocomm = ms_total
     if world > 1:

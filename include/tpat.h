@@ -348,7 +348,10 @@ int tpat_transpose(const void* src, int src_dtype, int ld_src, void* dst, int ds
 int tpat_attention_train(const void* qkv, void* out, int dtype, float* score_partial, int score_mode, float* lse,
                          int B, int N, int H, int hd, int num_extra, float scale, int impl, tpat_stream_t stream);
 /* Attention backward: dqkv [B * N, 3 * H * hd] (dtype) from qkv, out (= O), d_out and lse; P is recomputed, nothing of
- * size N x N touches HBM; no gradient through the importance score / top-k (indices).  delta_ws: B * H * N floats. */
+ * size N x N touches HBM; no gradient through the importance score / top-k (indices).
+ * delta_ws: tpat_attention_bwd_ws_floats(B, N, H, hd) floats (row sums of dO o O, and the fp32 dQ accumulator of the
+ * tcgen05 kernel, which adds each key tile's contribution with TMA reduce operations). */
+size_t tpat_attention_bwd_ws_floats(int B, int N, int H, int hd);
 int tpat_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int dtype,
                        int B, int N, int H, int hd, float scale, int impl, float* delta_ws, tpat_stream_t stream);
 

@@ -206,12 +206,14 @@ int attention_bwd_simt(const void* qkv, const void* out, const void* d_out, cons
 
 }  // namespace tpat
 
-#ifndef TPAT_HAVE_ATTN_BWD_TC
 namespace tpat {
-// until csrc/attention_bwd_tc.cu exists the bf16 path runs the CUDA-core kernels (fp32 math on bf16 operands)
-int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int N, int H,
-                     float scale, float* delta_ws, cudaStream_t st) {
-  return attention_bwd_simt(qkv, out, d_out, lse, dqkv, TPAT_BF16, B, N, H, scale, delta_ws, st);
+// delta = rowsum(dO o O) for the tcgen05 backward (same kernel as the CUDA-core path)
+int attention_bwd_delta_bf16(const void* out, const void* d_out, float* delta, int B, int N, int H, cudaStream_t st) {
+  const size_t total = (size_t)B * N * H;
+  const int dgrid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  TPAT_CUDA(launch_kernel(attn_delta_kernel<__nv_bfloat16>, dim3(dgrid), dim3(256), 0, st, (const __nv_bfloat16*)out,
+                          (const __nv_bfloat16*)d_out, delta, B, N, H));
+  TPAT_LAUNCH_CHECK();
+  return 0;
 }
 }  // namespace tpat
-#endif

@@ -1,0 +1,319 @@
+// tcgen05 attention backward for sm_100a (bf16 operands, fp32 accumulate / softmax math).
+//
+// Backward of q k^T * scale -> softmax -> attn @ v (reference audiomae/models_vit.py:75-95 under autograd):
+//     P = exp(scale S - lse),  dP = dO V^T,  dS = P o (dP - delta) scale,  dV = P^T dO,  dK = dS^T Q,  dQ = dS K
+// with S recomputed from Q, K and the forward's log-sum-exp; nothing of size N x N reaches HBM.
+//
+// One CTA per (clip, head, 128-KEY tile j); it walks the 128-query tiles i.  dV_j and dK_j accumulate in tensor
+// memory over the whole walk; the dQ_i contribution of this key tile is added into an fp32 accumulator in HBM with
+// a TMA reduce (cp.reduce.async.bulk.tensor ... .add: no per-thread atomics; <= 5 key tiles add into each element).
+//   TMEM (448 of 512 columns):  S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
+//   smem (194 KB):  K_j, V_j (16 KB each, loaded once) | Q_i, dO_i (2 stages x 16 KB each) | P, dS (32 KB each, bf16,
+//                   [query][key] in two 64-key column blocks) | dQ staging (8 x 4 KB)
+//   warp 0   TMA producer;  warp 1   MMA issuer (one elected thread);  warps 2-9  softmax / epilogue:
+//            thread = (query row = TMEM lane, 64-key half)
+// Five products per (i, j), all tcgen05.mma kind::f16 from shared memory:
+//   S  = Q_i K_j^T   (M128 N128 K64, both K-major)        dP = dO_i V_j^T   (same)
+//   dV += P^T dO_i   (M128 N64 K128: A = P MN-major, two 64-key blocks 16 KB apart (LBO); B = dO_i MN-major)
+//   dK += dS^T Q_i   (same shapes with dS, Q_i)           dQ = dS K_j      (M128 N64 K128: A = dS K-major, B = K_j MN-major)
+// The same [query][key] bf16 tile therefore serves as an MN-major A operand (dV, dK) and a K-major one (dQ).
+#include "attention.cuh"
+#include "ptx_sm100.cuh"
+
+#include <cstdlib>
+
+namespace tpat {
+
+int encode_tmap_3d(CUtensorMap* out, const void* gptr, int elem_bytes, int B, int N, int ld, int box_rows, int box_cols);
+
+constexpr int BT_M = 128;                 // queries per tile = keys per tile
+constexpr int BT_HD = 64;
+constexpr int BT_TILE = BT_M * BT_HD * 2; // 16 KB: one [128][64] bf16 operand tile
+constexpr int BT_PS = 2 * BT_TILE;        // 32 KB: P or dS, two 64-key column blocks of [128 queries][128 B]
+constexpr int BT_THREADS = 320;
+constexpr int BT_SMEM = 1024 + 2 * BT_TILE + 4 * BT_TILE + 2 * BT_PS + 8 * 4096 + 256;
+constexpr uint32_t BT_S = 0, BT_DP = 128, BT_DV = 256, BT_DK = 320, BT_DQ = 384;
+
+struct AttnBwdTcParams {
+  const float* lse;      // [B, H, N] natural log
+  const float* delta;    // [B, H, N]
+  int N, H, n_t;
+  float scale, scale_log2;
+};
+
+// 32 values of one query row -> bf16, into the 128B-swizzled [row][64 keys] block: 16-byte pieces piece0 .. piece0 + 3
+__device__ __forceinline__ void bt_store_row32(uint8_t* block, int r_local, int piece0, const float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(block + r_local * 128 + (((piece0 + g) ^ (r_local & 7)) * 16)) =
+        make_uint4(pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                   pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
+}
+
+__global__ void __launch_bounds__(BT_THREADS, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dkv,
+                        const AttnBwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* k_s = smem;
+  uint8_t* v_s = k_s + BT_TILE;
+  uint8_t* q_s = v_s + BT_TILE;            // 2 stages
+  uint8_t* do_s = q_s + 2 * BT_TILE;       // 2 stages
+  uint8_t* p_s = do_s + 2 * BT_TILE;
+  uint8_t* ds_s = p_s + BT_PS;
+  uint8_t* stg = ds_s + BT_PS;             // 8 x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 8 * 4096);
+  uint64_t* kv_full = bars;                // [1]
+  uint64_t* q_full = bars + 1;             // [2]
+  uint64_t* qdo_empty = bars + 3;          // [2]
+  uint64_t* s_full = bars + 5;             // [1]
+  uint64_t* pds_full = bars + 6;           // [1] 8 arrivals
+  uint64_t* dq_full = bars + 7;            // [1]
+  uint64_t* dkv_full = bars + 8;           // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_t = p.n_t;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_qkv); ptx::prefetch_tensormap(&tm_do);
+    ptx::prefetch_tensormap(&tm_dq); ptx::prefetch_tensormap(&tm_dkv);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&q_full[s], 1); ptx::mbar_init(&qdo_empty[s], 1); }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(pds_full, 8);
+    ptx::mbar_init(dq_full, 1);
+    ptx::mbar_init(dkv_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<512>(tmem_slot);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  const int col_q = h * BT_HD, col_k = (p.H + h) * BT_HD, col_v = (2 * p.H + h) * BT_HD;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(kv_full, 2 * BT_TILE);
+      ptx::tma_load_3d(k_s, &tm_qkv, kv_full, col_k, jt * BT_M, b);
+      ptx::tma_load_3d(v_s, &tm_qkv, kv_full, col_v, jt * BT_M, b);
+      for (int i = 0; i < n_t; ++i) {
+        const int st = i & 1;
+        ptx::mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&q_full[st], 2 * BT_TILE);
+        ptx::tma_load_3d(q_s + st * BT_TILE, &tm_qkv, &q_full[st], col_q, i * BT_M, b);
+        ptx::tma_load_3d(do_s + st * BT_TILE, &tm_do, &q_full[st], col_q, i * BT_M, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(128, 128, 0, 0);    // Q / dO (K-major) x K / V (K-major)
+      constexpr uint32_t idesc_kv = ptx::idesc_bf16_f32(128, 64, 1, 1);    // P^T / dS^T (MN-major) x dO / Q (MN-major)
+      constexpr uint32_t idesc_q = ptx::idesc_bf16_f32(128, 64, 0, 1);     // dS (K-major) x K (MN-major)
+      const uint64_t k_desc = ptx::smem_desc_sw128(ptx::smem_u32(k_s), 16, 1024);
+      const uint64_t v_desc = ptx::smem_desc_sw128(ptx::smem_u32(v_s), 16, 1024);
+      auto issue_sdp = [&](int i) {
+        const int st = i & 1;
+        ptx::mbar_wait(&q_full[st], (i >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint64_t q_desc = ptx::smem_desc_sw128(ptx::smem_u32(q_s + st * BT_TILE), 16, 1024);
+        const uint64_t do_desc = ptx::smem_desc_sw128(ptx::smem_u32(do_s + st * BT_TILE), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BT_HD / 16; ++k)
+          ptx::mma_f16_ss(tmem + BT_S, q_desc + (uint64_t)(2 * k), k_desc + (uint64_t)(2 * k), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < BT_HD / 16; ++k)
+          ptx::mma_f16_ss(tmem + BT_DP, do_desc + (uint64_t)(2 * k), v_desc + (uint64_t)(2 * k), idesc_s, k != 0);
+        ptx::tc_commit(s_full);
+      };
+      ptx::mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int i = 0; i < n_t; ++i) {
+        const int st = i & 1;
+        ptx::mbar_wait(pds_full, i & 1);            // P and dS of tile i are in shared memory; S / dP / dQ TMEM are free
+        ptx::tc_fence_after();
+        const uint32_t p_a = ptx::smem_u32(p_s), ds_a = ptx::smem_u32(ds_s);
+        const uint32_t do_a = ptx::smem_u32(do_s + st * BT_TILE), q_a = ptx::smem_u32(q_s + st * BT_TILE), k_a = ptx::smem_u32(k_s);
+        // K index = query row: 16 rows = two 8-row groups of 1024 B; the second 64-key block of P / dS is 16 KB further (LBO)
+#pragma unroll
+        for (int ks = 0; ks < BT_M / 16; ++ks)
+          ptx::mma_f16_ss(tmem + BT_DV, ptx::smem_desc_sw128(p_a + ks * 2048, BT_TILE, 1024),
+                          ptx::smem_desc_sw128(do_a + ks * 2048, 16, 1024), idesc_kv, (i | ks) != 0);
+#pragma unroll
+        for (int ks = 0; ks < BT_M / 16; ++ks)
+          ptx::mma_f16_ss(tmem + BT_DK, ptx::smem_desc_sw128(ds_a + ks * 2048, BT_TILE, 1024),
+                          ptx::smem_desc_sw128(q_a + ks * 2048, 16, 1024), idesc_kv, (i | ks) != 0);
+        // dQ = dS K_j: K index = key: dS K-major (64-key block ks / 4, 32 B per step), K_j MN-major (2048 B per 16 keys)
+#pragma unroll
+        for (int ks = 0; ks < BT_M / 16; ++ks)
+          ptx::mma_f16_ss(tmem + BT_DQ, ptx::smem_desc_sw128(ds_a + (ks >> 2) * BT_TILE + (ks & 3) * 32, 16, 1024),
+                          ptx::smem_desc_sw128(k_a + ks * 2048, 16, 1024), idesc_q, ks != 0);
+        ptx::tc_commit(&qdo_empty[st]);
+        ptx::tc_commit(dq_full);
+        if (i + 1 < n_t) issue_sdp(i + 1);
+      }
+      ptx::tc_commit(dkv_full);
+    }
+  } else {
+    // ===== softmax / epilogue warps =====
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r_local = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float* lse_bh = p.lse + ((size_t)b * p.H + h) * p.N;
+    const float* delta_bh = p.delta + ((size_t)b * p.H + h) * p.N;
+    uint8_t* my_stg = stg + (warp - 2) * 4096;
+    const float c = p.scale_log2;
+    constexpr float LOG2E = 1.4426950408889634f;
+    for (int i = 0; i < n_t; ++i) {
+      const int row = i * BT_M + r_local;
+      const bool row_ok = row < p.N;
+      const float lse2 = row_ok ? __ldg(lse_bh + row) * LOG2E : 0.f;
+      const float dlt = row_ok ? __ldg(delta_bh + row) : 0.f;
+      ptx::mbar_wait(s_full, i & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int col0 = half * 64 + cc * 32;               // column of the 128-key tile
+        uint32_t rs[32], rd[32];
+        ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_S + col0, rs);
+        ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DP + col0, rd);
+        ptx::tmem_ld_wait();
+        float pv[32], dsv[32];
+        const int key0 = jt * BT_M + col0;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const bool ok = row_ok && (key0 + t < p.N);
+          const float pr = ok ? ptx::ex2_ftz(fmaf(__uint_as_float(rs[t]), c, -lse2)) : 0.f;
+          pv[t] = pr;
+          dsv[t] = pr * (__uint_as_float(rd[t]) - dlt) * p.scale;
+        }
+        bt_store_row32(p_s + half * BT_TILE, r_local, cc * 4, pv);
+        bt_store_row32(ds_s + half * BT_TILE, r_local, cc * 4, dsv);
+      }
+      ptx::tc_fence_before();              // the TMEM reads above are complete
+      ptx::fence_proxy_async_smem();       // P / dS visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(pds_full);
+      // ---- dQ_i contribution of this key tile: TMEM -> swizzled fp32 staging -> TMA reduce-add ----
+      ptx::mbar_wait(dq_full, i & 1);
+      ptx::tc_fence_after();
+      {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DQ + half * 32, r);
+        ptx::tmem_ld_wait();
+        if (lane == 0) ptx::tma_store_wait_read<0>();        // the previous reduce has drained this staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<uint4*>(my_stg + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && i * BT_M + quarter * 32 < p.N) {
+          ptx::tma_reduce_add_3d(&tm_dq, my_stg, col_q + half * 32, i * BT_M + quarter * 32, b);   // rows >= N are dropped
+          ptx::tma_store_commit();
+        }
+      }
+    }
+    // ---- dK_j, dV_j: TMEM -> bf16 -> the (dead) K / V tiles -> two TMA stores ----
+    ptx::mbar_wait(dkv_full, 0);
+    ptx::tc_fence_after();
+    {
+      uint32_t r[32];
+      float v[32];
+      ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DK + half * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
+      bt_store_row32(k_s, r_local, half * 4, v);
+      ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DV + half * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
+      bt_store_row32(v_s, r_local, half * 4, v);
+    }
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    if (warp == 2 && lane == 0) {
+      ptx::tma_store_3d(&tm_dkv, k_s, col_k, jt * BT_M, b);      // key rows >= N are clipped by the tensor map
+      ptx::tma_store_3d(&tm_dkv, v_s, col_v, jt * BT_M, b);
+      ptx::tma_store_commit();
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();                    // reduces / stores complete before the CTA retires
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem);
+  }
+}
+
+// dq accumulator fp32 [B * N, H * 64] -> bf16 into the q columns of dqkv [B * N, 3 * H * 64]
+__global__ void __launch_bounds__(256)
+dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, size_t rows, int HD) {
+  pdl_trigger();
+  pdl_wait();
+  const int c4n = HD / 4;
+  const size_t total = rows * c4n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / c4n; const int c4 = (int)(i - r * c4n);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(acc) + i);
+    reinterpret_cast<uint2*>(dqkv + r * 3 * HD)[c4] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+int attention_bwd_delta_bf16(const void* out, const void* d_out, float* delta, int B, int N, int H, cudaStream_t st);
+
+int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int N, int H,
+                     float scale, float* delta_ws, cudaStream_t st) {
+  static const bool force_simt = getenv("TPAT_ATTN_BWD_SIMT") != nullptr;
+  if (force_simt) return attention_bwd_simt(qkv, out, d_out, lse, dqkv, TPAT_BF16, B, N, H, scale, delta_ws, st);
+  // workspace: delta [B * H * N] then the fp32 dQ accumulator [B * N, H * 64] (256-byte aligned)
+  float* delta = delta_ws;
+  const size_t dq_off = ((size_t)B * H * N + 63) / 64 * 64;
+  float* dq_acc = delta_ws + dq_off;
+  if (int rc = attention_bwd_delta_bf16(out, d_out, delta, B, N, H, st)) return rc;
+  TPAT_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * N * H * BT_HD * sizeof(float), st));
+  CUtensorMap tm_qkv, tm_do, tm_dq, tm_dkv;
+  if (int rc = encode_tmap_3d(&tm_qkv, qkv, 2, B, N, 3 * H * BT_HD, BT_M, 64)) return rc;
+  if (int rc = encode_tmap_3d(&tm_do, d_out, 2, B, N, H * BT_HD, BT_M, 64)) return rc;
+  if (int rc = encode_tmap_3d(&tm_dq, dq_acc, 4, B, N, H * BT_HD, 32, 32)) return rc;
+  if (int rc = encode_tmap_3d(&tm_dkv, dqkv, 2, B, N, 3 * H * BT_HD, BT_M, 64)) return rc;
+  AttnBwdTcParams p;
+  p.lse = lse; p.delta = delta; p.N = N; p.H = H; p.n_t = (N + BT_M - 1) / BT_M;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  static DeviceOnce once;
+  if (once.first()) {
+    TPAT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    once.mark();
+  }
+  TPAT_CUDA(launch_kernel(attention_bwd_tc_kernel, dim3(p.n_t, H, B), dim3(BT_THREADS), (size_t)BT_SMEM, st, tm_qkv, tm_do, tm_dq, tm_dkv, p));
+  const size_t rows = (size_t)B * N;
+  const size_t total = rows * (H * BT_HD / 4);
+  const int grid = (int)((total + 255) / 256 < (size_t)sm_count() * 16 ? (total + 255) / 256 : (size_t)sm_count() * 16);
+  TPAT_CUDA(launch_kernel(dq_convert_kernel, dim3(grid), dim3(256), 0, st, (const float*)dq_acc, (__nv_bfloat16*)dqkv, rows, H * BT_HD));
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tpat
+
+extern "C" size_t tpat_attention_bwd_ws_floats(int B, int N, int H, int hd) {
+  return ((size_t)B * H * N + 63) / 64 * 64 + (size_t)B * N * H * hd;
+}

@@ -121,6 +121,36 @@ int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld,
   return 0;
 }
 
+// Generic 3-D map over a [B][N][ld] tensor (clip, token, channel): box = {box_cols, box_rows, 1}, 128-byte swizzle.
+// Rows >= N of a box are zero-filled on load and dropped on store / reduce: a tile never touches the next clip.
+int encode_tmap_3d(CUtensorMap* out, const void* gptr, int elem_bytes, int B, int N, int ld, int box_rows, int box_cols) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{gptr, (uint64_t)N, (uint64_t)ld, (uint64_t)B, (uint32_t)box_rows, (uint32_t)box_cols, elem_bytes + 16, true};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  TPAT_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  TPAT_CHECK(aligned16(gptr) && ((size_t)ld * elem_bytes) % 16 == 0 && box_cols * elem_bytes == 128, "TMA (3d) needs a 16-byte aligned base / pitch and a 128-byte box row");
+  cuuint64_t gdim[3] = {(cuuint64_t)ld, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)N * ld * elem_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(out, dt, 3, const_cast<void*>(gptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TPAT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d (B=%d N=%d ld=%d)", (int)r, B, N, ld);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
 // ---------------- kernel ----------------
 constexpr int TG_STAGES = 4;
 constexpr int TG_EPI_WARPS = 8;

@@ -103,7 +103,7 @@ static BwdWs carve_bwd(const tpat_train_args* t, uint8_t* base) {
   w.t2 = a->impl == TPAT_IMPL_TC ? take(Cmax * Mpad * act) : nullptr;
   w.inv = (int32_t*)take(B * P * 4);
   w.parts = (float*)take(tpat_bwd_partials_floats((int)(Dh > D ? Dh : D)) * 4);
-  w.delta = (float*)take(B * H * Nfull * 4);
+  w.delta = (float*)take(tpat_attention_bwd_ws_floats((int)B, (int)Nfull, (int)H, 64) * 4);
   w.dpooled = (float*)take(B * D * 4);
   w.x0g = t->mask_keep_idx ? (float*)take(Mmax * D * 4) : nullptr;
   w.bytes = off;

@@ -124,6 +124,7 @@ SIGNATURES = {
                                      c_float, c_int, c_void_p]),
     "tpat_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                    c_int, c_void_p, c_void_p]),
+    "tpat_attention_bwd_ws_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "tpat_bwd_partials_floats": (c_size_t, [c_int]),
     "tpat_inverse_index": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "tpat_row_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

@@ -321,7 +321,7 @@ def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, lse
                   ) -> torch.Tensor:
     _req(qkv, name="qkv"); _req(out, qkv.dtype, "out"); _req(d_out, qkv.dtype, "d_out"); _req(lse, torch.float32, "lse")
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty(B * H * N, device=qkv.device, dtype=torch.float32)
+    delta = torch.empty(lib.tpat_attention_bwd_ws_floats(B, N, H, 64), device=qkv.device, dtype=torch.float32)
     check(lib.tpat_attention_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), _DT[qkv.dtype], B, N,
                                  H, 64, 64 ** -0.5, impl, delta.data_ptr(), _stream()), "tpat_attention_bwd")
     return dqkv
