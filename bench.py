@@ -384,12 +384,14 @@ def run_train(args, rank, world, local_rank):
             out_loss.copy_(step(sx, sy).detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    e2e_loop(2)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        e2e_loop(2)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps)
+        barrier()
+        e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total, e2e_s, ms_nocomm], device=device, dtype=torch.float64)
     if world > 1:
@@ -439,6 +441,7 @@ def main():
                     "train = the fine-tune step of BASELINE.json configs[3]")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="train mode: skip the end-to-end region (profiling runs)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager GPU baseline leg")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the 91 kernels eagerly instead of replaying a CUDA graph")
     ap.set_defaults(graph=True)

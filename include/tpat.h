@@ -339,6 +339,12 @@ int tpat_gemm_train(const void* A, int a_dtype, int lda, const void* W, int w_dt
 int tpat_gemm_f32(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc,
                   int M, int N, int K, int accumulate, tpat_stream_t stream);
 
+/* Weight gradient on the tensor cores: dW[Mo, No] (fp32) += dY[K, Mo]^T X[K, No], bf16 operands read in their natural
+ * row-major layout (MN-major tcgen05 operands), reduction over the K tokens split across SM pairs, partial tiles added
+ * with TMA reduce operations.  Mo % 256 == 0, No % 256 == 0. */
+int tpat_gemm_wgrad(const void* dY, int ld_dy, const void* X, int ldx, float* dW, int ldw, int K, int Mo, int No,
+                    tpat_stream_t stream);
+
 /* dst[c][r] = cast(src[r][c]); destination rows padded with zeros up to ld_dst (>= rows).  dtype pairs f32->f32,
  * f32->bf16, bf16->bf16. */
 int tpat_transpose(const void* src, int src_dtype, int ld_src, void* dst, int dst_dtype, int ld_dst, int rows, int cols,

@@ -190,6 +190,21 @@ def test_gemm_train_epilogues(impl_name):
     assert torch.equal(out[:n], res[:n])                                # a dropped clip keeps its residual bit for bit
 
 
+@pytest.mark.parametrize("K,Mo,No", [(513 * 3, 768, 768), (1000, 2304, 768), (4104, 768, 3072), (70, 256, 256), (32832, 3072, 768)])
+def test_gemm_wgrad_tcgen05(K, Mo, No):
+    """dW += dY^T X with both operands in their natural layout (MN-major UMMA operands), split-K + TMA reduce-add."""
+    from tpat import ops
+    torch.manual_seed(K)
+    dy = (torch.randn(K, Mo, device=dev()) * 0.1).to(torch.bfloat16)
+    x = torch.randn(K, No, device=dev()).to(torch.bfloat16)
+    base = torch.randn(Mo, No, device=dev())
+    got = ops.gemm_wgrad(dy, x, out=base.clone())
+    want = base.double() + dy.double().T @ x.double()
+    e = nerr(got, want)
+    print(f"[wgrad tcgen05] K={K} {Mo}x{No}: rel err {e:.2e}")
+    assert e < 2e-5          # products of bf16 values are exact in fp32; only the fp32 summation order differs
+
+
 def test_fused_adamw_matches_torch():
     from tpat import ops
     torch.manual_seed(4)

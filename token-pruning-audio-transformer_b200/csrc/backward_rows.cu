@@ -180,25 +180,38 @@ colsum_kernel(const T* __restrict__ x, int ld, int M, int C, float* __restrict__
   }
 }
 
-// dst_q[c] += sum_p partials[p][q][c], q < nq (<= 4), in a fixed order
+// dst_q[c] += sum_p partials[p][q][c], q < nq (<= 4), in a fixed order.  CTA = 32 columns x 16 part-slices: slice s sums
+// parts s, s + 16, ... (four independent accumulators), the 16 slice sums are combined through shared memory in order --
+// the loop over up to 296 parts is 5 dependent rounds instead of 74.
 struct FinishDst { float* d[4]; };
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 partials_finish_kernel(const float* __restrict__ partials, int nparts, int nq, int C, FinishDst dst) {
+  __shared__ float red[16][33];
   pdl_trigger();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   const int q = blockIdx.y;
-  if (c >= C || dst.d[q] == nullptr) return;
+  if (dst.d[q] == nullptr) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int pi = 0;
-  for (; pi + 3 < nparts; pi += 4) {
-    s0 += partials[((size_t)pi * nq + q) * C + c];
-    s1 += partials[((size_t)(pi + 1) * nq + q) * C + c];
-    s2 += partials[((size_t)(pi + 2) * nq + q) * C + c];
-    s3 += partials[((size_t)(pi + 3) * nq + q) * C + c];
+  if (c < C) {
+    int pi = sy;
+    for (; pi + 48 < nparts; pi += 64) {
+      s0 += partials[((size_t)pi * nq + q) * C + c];
+      s1 += partials[((size_t)(pi + 16) * nq + q) * C + c];
+      s2 += partials[((size_t)(pi + 32) * nq + q) * C + c];
+      s3 += partials[((size_t)(pi + 48) * nq + q) * C + c];
+    }
+    for (; pi < nparts; pi += 16) s0 += partials[((size_t)pi * nq + q) * C + c];
   }
-  for (; pi < nparts; ++pi) s0 += partials[((size_t)pi * nq + q) * C + c];
-  dst.d[q][c] += (s0 + s1) + (s2 + s3);
+  red[sy][cx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (sy == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t += red[k][cx];
+    dst.d[q][c] += t;
+  }
 }
 
 // ---- pooled head backward: one CTA per clip, 256 threads ----
@@ -311,7 +324,7 @@ namespace tpat {
 
 static int finish_partials(const float* partials, int nparts, int nq, int C, float* d0, float* d1, float* d2, float* d3, cudaStream_t st) {
   FinishDst dst{{d0, d1, d2, d3}};
-  TPAT_CUDA(launch_kernel(partials_finish_kernel, dim3((C + 255) / 256, nq), dim3(256), 0, st, partials, nparts, nq, C, dst));
+  TPAT_CUDA(launch_kernel(partials_finish_kernel, dim3((C + 31) / 32, nq), dim3(512), 0, st, partials, nparts, nq, C, dst));
   TPAT_LAUNCH_CHECK();
   return 0;
 }

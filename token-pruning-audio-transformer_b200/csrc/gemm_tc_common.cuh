@@ -150,6 +150,21 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
           extra[it] = m < p.M ? *reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + ncol) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+    } else if constexpr (EPI == TPAT_EPI_DGELU) {
+      if (live) {   // the saved pre-activations are requested before the TMEM read: their latency overlaps it
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = m0 + it * 4 + rl;
+          if constexpr (sizeof(OutT) == 4) {
+            extra[it] = m < p.M ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (size_t)m * p.ld_aux + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+            uint2 hh = make_uint2(0u, 0u);
+            if (m < p.M) hh = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)m * p.ld_aux + ncol));
+            const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162*>(&hh.x), hb = *reinterpret_cast<const __nv_bfloat162*>(&hh.y);
+            extra[it] = make_float4(__low2float(ha), __high2float(ha), __low2float(hb), __high2float(hb));
+          }
+        }
+      }
     } else if constexpr (EPI == TPAT_EPI_BIAS_POS) {
       if (live) {   // the position rows are requested before the TMEM read as well (8 independent loads in flight)
 #pragma unroll
@@ -212,19 +227,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
     } else if constexpr (EPI == TPAT_EPI_DGELU) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        const int m = m0 + it * 4 + rl;
-        if (m >= p.M) continue;
-        float h0, h1, h2, h3;
-        if constexpr (sizeof(OutT) == 4) {
-          const float4 hh = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + (size_t)m * p.ld_aux + ncol));
-          h0 = hh.x; h1 = hh.y; h2 = hh.z; h3 = hh.w;
-        } else {
-          const uint2 hh = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)m * p.ld_aux + ncol));
-          const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162*>(&hh.x), hb = *reinterpret_cast<const __nv_bfloat162*>(&hh.y);
-          h0 = __low2float(ha); h1 = __high2float(ha); h2 = __low2float(hb); h3 = __high2float(hb);
-        }
-        v[it].x *= gelu_erf_fast_grad(h0); v[it].y *= gelu_erf_fast_grad(h1);
-        v[it].z *= gelu_erf_fast_grad(h2); v[it].w *= gelu_erf_fast_grad(h3);
+        v[it].x *= gelu_erf_fast_grad(extra[it].x); v[it].y *= gelu_erf_fast_grad(extra[it].y);
+        v[it].z *= gelu_erf_fast_grad(extra[it].z); v[it].w *= gelu_erf_fast_grad(extra[it].w);
       }
     } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS) {
       if (EPI == TPAT_EPI_BIAS_RESIDUAL && p.row_scale != nullptr) {     // DropPath: per-clip scale of the branch

@@ -16,8 +16,11 @@
 #include "gemm.cuh"
 #include "attention.cuh"
 
+#include <cstdlib>
+
 namespace tpat {
 
+int gemm_wgrad_tc(const void* dY, int ld_dy, const void* X, int ldx, float* dW, int ldw, int K, int Mo, int No, cudaStream_t st);
 int validate_forward_args(const tpat_forward_args* a, int n0);
 
 static size_t al(size_t v) { return (v + 255) & ~size_t(255); }
@@ -134,6 +137,15 @@ static int wgrad(const void* dY, const void* X, float* dW, int M, int Nout, int 
   if (dW == nullptr) return 0;
   if (impl == TPAT_IMPL_SIMT)
     return tpat_gemm_f32((const float*)dY, Nout, 1, (const float*)X, Nin, 0, dW, Nin, Nout, Nin, M, 1, st);
+  {
+    // tcgen05 kernel that reads dY and X as they are (MN-major operands, split-K, TMA reduce-add); shapes it does not
+    // cover (outputs that are not multiples of 256 x 256, e.g. ViT-S) take the transpose route below
+    static const bool force_transpose = getenv("TPAT_WGRAD_TRANSPOSE") != nullptr;
+    if (!force_transpose) {
+      const int rc = gemm_wgrad_tc(dY, Nout, X, Nin, dW, Nin, M, Nout, Nin, as_stream(st));
+      if (rc >= 0) return rc;
+    }
+  }
   const int Mpad = (M + 63) / 64 * 64;
   if (int rc = tpat_transpose(dY, act, Nout, w.t1, act, Mpad, M, Nout, st)) return rc;
   if (int rc = tpat_transpose(X, act, Nin, w.t2, act, Mpad, M, Nin, st)) return rc;

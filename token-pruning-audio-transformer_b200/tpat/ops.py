@@ -357,3 +357,14 @@ def adamw(p, g, m, v, p_bf16, chunks, groups, lr, beta1, beta2, eps, step, grad_
     check(lib.tpat_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_bf16), chunks.data_ptr(), chunks.shape[0],
                          groups.data_ptr(), float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_scale), _stream()),
           "tpat_adamw")
+
+
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out [Mo, No] fp32 += dy[K, Mo].T @ x[K, No] (bf16 operands, tcgen05 split-K kernel)."""
+    _req(dy, torch.bfloat16, "dy"); _req(x, torch.bfloat16, "x")
+    K, Mo = dy.shape
+    No = x.shape[1]
+    if out is None:
+        out = torch.zeros(Mo, No, device=dy.device, dtype=torch.float32)
+    check(lib.tpat_gemm_wgrad(dy.data_ptr(), Mo, x.data_ptr(), No, out.data_ptr(), No, K, Mo, No, _stream()), "tpat_gemm_wgrad")
+    return out
