@@ -513,6 +513,10 @@ def main():
         from tpat import dist as tdist
         comm_ev = None
 
+        out_stream = torch.cuda.Stream()       # gather + D2H of step i overlap the forward of step i + 1
+        fwd_done = [torch.cuda.Event() for _ in range(2)]
+        out_done = [torch.cuda.Event() for _ in range(2)]
+
         def e2e_loop(n):
             with torch.cuda.stream(copy_stream):
                 stage[0].copy_(host[0], non_blocking=True)
@@ -526,22 +530,29 @@ def main():
                         stage[nxt].copy_(host[(i + 1) % NROT], non_blocking=True)
                         ready[nxt].record(copy_stream)
                 main_stream.wait_event(ready[cur])
+                if i >= 2:
+                    main_stream.wait_event(out_done[cur])      # the outputs of this graph (views) have been consumed
                 lg = model(stage[cur])
                 freed[cur].record(main_stream)
+                fwd_done[cur].record(main_stream)
                 idxs = model.last_topk_idx
-                if world > 1:
-                    # the north-star eval collective (engine_finetune.py:246-248): ONE packed all_gather of logits + kept
-                    # indices over NCCL, inside the timed region; every rank then holds the global batch's outputs
-                    if comm_ev is not None and i < len(comm_ev):
-                        comm_ev[i][0].record(main_stream)
-                    g_lg, g_idx = tdist.gather_outputs(lg, idxs, B * world)
-                    if comm_ev is not None and i < len(comm_ev):
-                        comm_ev[i][1].record(main_stream)
-                    s0 = rank * B
-                    lg, idxs = g_lg[s0:s0 + B], [None if t is None else t[s0:s0 + B] for t in g_idx]
-                out_logits.copy_(lg, non_blocking=True)
-                for dst, src in zip(out_idx, [t for t in idxs if t is not None]):
-                    dst.copy_(src, non_blocking=True)
+                with torch.cuda.stream(out_stream):
+                    out_stream.wait_event(fwd_done[cur])
+                    if world > 1:
+                        # the north-star eval collective (engine_finetune.py:246-248): ONE packed all_gather of logits + kept
+                        # indices over NCCL, inside the timed region; every rank then holds the global batch's outputs
+                        if comm_ev is not None and i < len(comm_ev):
+                            comm_ev[i][0].record(out_stream)
+                        g_lg, g_idx = tdist.gather_outputs(lg, idxs, B * world)
+                        if comm_ev is not None and i < len(comm_ev):
+                            comm_ev[i][1].record(out_stream)
+                        s0 = rank * B
+                        lg, idxs = g_lg[s0:s0 + B], [None if t is None else t[s0:s0 + B] for t in g_idx]
+                    out_logits.copy_(lg, non_blocking=True)
+                    for dst, src in zip(out_idx, [t for t in idxs if t is not None]):
+                        dst.copy_(src, non_blocking=True)
+                    out_done[cur].record(out_stream)
+            out_stream.synchronize()
             main_stream.synchronize()
 
         e2e_loop(2)

@@ -49,3 +49,45 @@ def test_sharded_forward_gathers_in_global_order(batch):
     ok = mp.get_context("spawn").Manager().list([False, False])
     mp.spawn(_worker, args=(2, port, batch, ok), nprocs=2, join=True)
     assert list(ok) == [True, True]
+
+
+def _grad_sync_worker(rank, world, port, ok):
+    """The bucketed gradient all-reduce of the fine-tune step (TrainEngine.allreduce_stage / finish_sync) on CPU tensors
+    over gloo: every backward stage's gradients are ONE contiguous slice of the flat buffer, reduced in place."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch.nn as nn
+        from tpat import models_vit, _lib
+        from tpat.train import TrainEngine
+        torch.manual_seed(0)
+        m = models_vit.vit_base_patch16(num_classes=10, drop_path_rate=0.0, mean_pooling=True, mask_2d=True, target_length=128,
+                                        drop_loc=(3, 6, 9), base_keep_rate=0.7)
+        m.patch_embed = models_vit.PatchEmbed((128, 128), 16, 1, 768)
+        m.pos_embed = nn.Parameter(torch.zeros(1, 65, 768), requires_grad=False)
+        eng = TrainEngine(_lib.VARIANT_AUDIOMAE, 12, 768, 12, 3072)
+        eng.attach(m._train_entries(m._train_roles()), {})
+        for _, _, p in eng.entries:                      # rank-dependent "gradients", written through the views
+            p.grad = eng.grad_view(p)
+            p.grad.fill_(float(rank + 1))
+        m.head.bias.grad[3] = 10.0 * (rank + 1)
+        world_seen = eng.sync_world()
+        works = [w for w in (eng.allreduce_stage(s, world_seen) for s in range(13, -1, -1)) if w is not None]
+        eng.finish_sync(works, world_seen)
+        good = world_seen == 2 and len(works) == 14
+        good &= all(bool(torch.all(p.grad.flatten()[:2] == 1.5)) for _, _, p in eng.entries if p is not m.head.bias)
+        good &= abs(m.head.bias.grad[3].item() - 15.0) < 1e-6 and abs(m.head.bias.grad[0].item() - 1.5) < 1e-6
+        eng.grad_sync = False                            # accumulation steps: no collective
+        good &= eng.sync_world() == 1 and eng.allreduce_stage(5, eng.sync_world()) is None
+        ok[rank] = bool(good)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_over_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ok = mp.get_context("spawn").Manager().list([False, False])
+    mp.spawn(_grad_sync_worker, args=(2, port, ok), nprocs=2, join=True)
+    assert list(ok) == [True, True]

@@ -271,15 +271,30 @@ class TrainEngine:
             if p.grad is None:
                 p.grad = self.grad_view(p)
         stream = torch.cuda.current_stream()
-        world = dist.get_world_size() if (self.grad_sync and dist.is_available() and dist.is_initialized()) else 1
+        world = self.sync_world()
         works = []
         for stage in range(self.depth + 1, -1, -1):
             check(lib.tpat_train_backward(ctypes.byref(a), stage, stage, stream.cuda_stream), "tpat_train_backward")
-            if world > 1 and stage in self.stage_slices:
-                # DDP-equivalent bucket: this stage's gradients are one contiguous slice of flat_g; the NCCL kernel waits
-                # for the kernels enqueued so far and overlaps the next stage's compute
-                off, n = self.stage_slices[stage]
-                works.append(dist.all_reduce(self.flat_g[off:off + n], op=dist.ReduceOp.SUM, async_op=True))
+            w = self.allreduce_stage(stage, world)
+            if w is not None:
+                works.append(w)
+        self.finish_sync(works, world)
+        ent["dlogits"] = dlogits
+
+
+    # ---- gradient synchronisation (DDP-equivalent, main_finetune.py:459-461) -------------------------
+    def sync_world(self) -> int:
+        return dist.get_world_size() if (self.grad_sync and dist.is_available() and dist.is_initialized()) else 1
+
+    def allreduce_stage(self, stage: int, world: int):
+        """In-place SUM all-reduce of the contiguous gradient slice of one backward stage (the bucket), asynchronous:
+        the collective waits for the kernels enqueued so far and overlaps the next stage's compute."""
+        if world <= 1 or stage not in self.stage_slices:
+            return None
+        off, n = self.stage_slices[stage]
+        return dist.all_reduce(self.flat_g[off:off + n], op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish_sync(self, works, world: int) -> None:
         for w in works:
             w.wait()
         if world > 1:
@@ -287,7 +302,6 @@ class TrainEngine:
                 self.pending_grad_scale = 1.0 / world    # DDP averages: folded into the FusedAdamW kernel
             else:
                 self.flat_g.mul_(1.0 / world)
-        ent["dlogits"] = dlogits
 
 
 class _TrainFn(torch.autograd.Function):
