@@ -30,27 +30,28 @@ template <> __device__ __forceinline__ void ab_ld4<__nv_bfloat16>(const __nv_bfl
   o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
 }
 
-// delta[b, h, i] = sum_d dO[b, i, h, d] * O[b, i, h, d]: one thread per (row, head)
+// delta[b, h, i] = sum_d dO[b, i, h, d] * O[b, i, h, d]: eight lanes per (row, head), 8 elements each, so that a warp
+// instruction covers four contiguous 128-byte (bf16) head rows; shuffle reduction, lane 0 of the group writes
 template <typename T>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const T* __restrict__ o, const T* __restrict__ d_o, float* __restrict__ delta, int B, int N, int H) {
   pdl_trigger();
   pdl_wait();
   const size_t total = (size_t)B * N * H;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  const int sub = threadIdx.x & 7;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < total; i += ((size_t)gridDim.x * blockDim.x) >> 3) {
     const int h = (int)(i % H);
     const size_t row = i / H;                   // b * N + n
-    const T* po = o + row * (size_t)(H * AB_HD) + h * AB_HD;
-    const T* pd = d_o + row * (size_t)(H * AB_HD) + h * AB_HD;
-    float s = 0.f;
-#pragma unroll
-    for (int d = 0; d < AB_HD; d += 4) {
-      float a[4], g[4];
-      ab_ld4<T>(po + d, a); ab_ld4<T>(pd + d, g);
-      s += (a[0] * g[0] + a[1] * g[1]) + (a[2] * g[2] + a[3] * g[3]);
+    const T* po = o + row * (size_t)(H * AB_HD) + h * AB_HD + sub * 8;
+    const T* pd = d_o + row * (size_t)(H * AB_HD) + h * AB_HD + sub * 8;
+    float a[4], g[4], a2[4], g2[4];
+    ab_ld4<T>(po, a); ab_ld4<T>(pd, g); ab_ld4<T>(po + 4, a2); ab_ld4<T>(pd + 4, g2);
+    float s = ((a[0] * g[0] + a[1] * g[1]) + (a[2] * g[2] + a[3] * g[3])) + ((a2[0] * g2[0] + a2[1] * g2[1]) + (a2[2] * g2[2] + a2[3] * g2[3]));
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0) {
+      const int b = (int)(row / N), n = (int)(row % N);
+      delta[((size_t)b * H + h) * N + n] = s;
     }
-    const int b = (int)(row / N), n = (int)(row % N);
-    delta[((size_t)b * H + h) * N + n] = s;
   }
 }
 
@@ -189,7 +190,7 @@ static int launch_attn_bwd_simt(const void* qkv, const void* out, const void* d_
     once.mark();
   }
   const size_t total = (size_t)B * N * H;
-  const int dgrid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  const int dgrid = (int)((total * 8 + 255) / 256 < 8192 ? (total * 8 + 255) / 256 : 8192);
   TPAT_CUDA(launch_kernel(attn_delta_kernel<T>, dim3(dgrid), dim3(256), 0, st, (const T*)out, (const T*)d_out, delta_ws, B, N, H));
   const dim3 grid((N + AB_T - 1) / AB_T, H, B);
   TPAT_CUDA(launch_kernel(kq, dim3(grid), dim3(256), AB_SMEM, st, (const T*)qkv, (const T*)d_out, lse, (const float*)delta_ws, (T*)dqkv, N, H, scale));
@@ -210,7 +211,7 @@ namespace tpat {
 // delta = rowsum(dO o O) for the tcgen05 backward (same kernel as the CUDA-core path)
 int attention_bwd_delta_bf16(const void* out, const void* d_out, float* delta, int B, int N, int H, cudaStream_t st) {
   const size_t total = (size_t)B * N * H;
-  const int dgrid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  const int dgrid = (int)((total * 8 + 255) / 256 < 8192 ? (total * 8 + 255) / 256 : 8192);
   TPAT_CUDA(launch_kernel(attn_delta_kernel<__nv_bfloat16>, dim3(dgrid), dim3(256), 0, st, (const __nv_bfloat16*)out,
                           (const __nv_bfloat16*)d_out, delta, B, N, H));
   TPAT_LAUNCH_CHECK();

@@ -7,7 +7,7 @@
 // One CTA per (clip, head, 128-KEY tile j); it walks the 128-query tiles i.  dV_j and dK_j accumulate in tensor
 // memory over the whole walk; the dQ_i contribution of this key tile is added into an fp32 accumulator in HBM with
 // a TMA reduce (cp.reduce.async.bulk.tensor ... .add: no per-thread atomics; <= 5 key tiles add into each element).
-//   TMEM (448 of 512 columns):  S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
+//   TMEM (all 512 columns):  S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ ping [384,448) pong [448,512)
 //   smem (194 KB):  K_j, V_j (16 KB each, loaded once) | Q_i, dO_i (2 stages x 16 KB each) | P, dS (32 KB each, bf16,
 //                   [query][key] in two 64-key column blocks) | dQ staging (8 x 4 KB)
 //   warp 0   TMA producer;  warp 1   MMA issuer (one elected thread);  warps 2-9  softmax / epilogue:
@@ -32,7 +32,7 @@ constexpr int BT_TILE = BT_M * BT_HD * 2; // 16 KB: one [128][64] bf16 operand t
 constexpr int BT_PS = 2 * BT_TILE;        // 32 KB: P or dS, two 64-key column blocks of [128 queries][128 B]
 constexpr int BT_THREADS = 320;
 constexpr int BT_SMEM = 1024 + 2 * BT_TILE + 4 * BT_TILE + 2 * BT_PS + 8 * 4096 + 256;
-constexpr uint32_t BT_S = 0, BT_DP = 128, BT_DV = 256, BT_DK = 320, BT_DQ = 384;
+constexpr uint32_t BT_S = 0, BT_DP = 128, BT_DV = 256, BT_DK = 320, BT_DQ = 384;   // dQ: two buffers, [384,448) and [448,512)
 
 struct AttnBwdTcParams {
   const float* lse;      // [B, H, N] natural log
@@ -143,8 +143,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       issue_sdp(0);
       for (int i = 0; i < n_t; ++i) {
         const int st = i & 1;
-        ptx::mbar_wait(pds_full, i & 1);            // P and dS of tile i are in shared memory; S / dP / dQ TMEM are free
+        ptx::mbar_wait(pds_full, i & 1);            // P and dS of tile i are in shared memory; S / dP TMEM have been read
         ptx::tc_fence_after();
+        // S / dP of the NEXT query tile first: the softmax warps work on them while the 24 MMAs below run
+        if (i + 1 < n_t) issue_sdp(i + 1);
         const uint32_t p_a = ptx::smem_u32(p_s), ds_a = ptx::smem_u32(ds_s);
         const uint32_t do_a = ptx::smem_u32(do_s + st * BT_TILE), q_a = ptx::smem_u32(q_s + st * BT_TILE), k_a = ptx::smem_u32(k_s);
         // K index = query row: 16 rows = two 8-row groups of 1024 B; the second 64-key block of P / dS is 16 KB further (LBO)
@@ -159,11 +161,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         // dQ = dS K_j: K index = key: dS K-major (64-key block ks / 4, 32 B per step), K_j MN-major (2048 B per 16 keys)
 #pragma unroll
         for (int ks = 0; ks < BT_M / 16; ++ks)
-          ptx::mma_f16_ss(tmem + BT_DQ, ptx::smem_desc_sw128(ds_a + (ks >> 2) * BT_TILE + (ks & 3) * 32, 16, 1024),
+          ptx::mma_f16_ss(tmem + BT_DQ + (uint32_t)(i & 1) * 64, ptx::smem_desc_sw128(ds_a + (ks >> 2) * BT_TILE + (ks & 3) * 32, 16, 1024),
                           ptx::smem_desc_sw128(k_a + ks * 2048, 16, 1024), idesc_q, ks != 0);
         ptx::tc_commit(&qdo_empty[st]);
-        ptx::tc_commit(dq_full);
-        if (i + 1 < n_t) issue_sdp(i + 1);
+        ptx::tc_commit(dq_full);                    // also: P / dS shared memory is free again
       }
       ptx::tc_commit(dkv_full);
     }
@@ -178,57 +179,79 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     uint8_t* my_stg = stg + (warp - 2) * 4096;
     const float c = p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
-    for (int i = 0; i < n_t; ++i) {
+    // Software pipeline over the query tiles: while the tensor core runs the 24 MMAs of tile i, these warps already
+    // turn S / dP of tile i + 1 into P / dS (kept in registers as bf16 pairs); the stores into the shared P / dS tile wait
+    // for dq_full(i) (= those MMAs have retired), and the dQ_i epilogue runs after the hand-off, next to MMAs(i + 1).
+    uint32_t pk_p[32], pk_ds[32];          // this thread's 64 keys of P and dS, packed bf16 pairs
+    auto compute = [&](int i) {
       const int row = i * BT_M + r_local;
       const bool row_ok = row < p.N;
       const float lse2 = row_ok ? __ldg(lse_bh + row) * LOG2E : 0.f;
       const float dlt = row_ok ? __ldg(delta_bh + row) : 0.f;
       ptx::mbar_wait(s_full, i & 1);
       ptx::tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int col0 = half * 64 + cc * 32;               // column of the 128-key tile
         uint32_t rs[32], rd[32];
         ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_S + col0, rs);
         ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DP + col0, rd);
         ptx::tmem_ld_wait();
-        float pv[32], dsv[32];
         const int key0 = jt * BT_M + col0;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const bool ok = row_ok && (key0 + t < p.N);
-          const float pr = ok ? ptx::ex2_ftz(fmaf(__uint_as_float(rs[t]), c, -lse2)) : 0.f;
-          pv[t] = pr;
-          dsv[t] = pr * (__uint_as_float(rd[t]) - dlt) * p.scale;
+        for (int t = 0; t < 32; t += 2) {
+          const bool ok0 = row_ok && (key0 + t < p.N), ok1 = row_ok && (key0 + t + 1 < p.N);
+          const float p0 = ok0 ? ptx::ex2_ftz(fmaf(__uint_as_float(rs[t]), c, -lse2)) : 0.f;
+          const float p1 = ok1 ? ptx::ex2_ftz(fmaf(__uint_as_float(rs[t + 1]), c, -lse2)) : 0.f;
+          pk_p[cc * 16 + (t >> 1)] = pack_bf16x2(p0, p1);
+          pk_ds[cc * 16 + (t >> 1)] = pack_bf16x2(p0 * (__uint_as_float(rd[t]) - dlt) * p.scale, p1 * (__uint_as_float(rd[t + 1]) - dlt) * p.scale);
         }
-        bt_store_row32(p_s + half * BT_TILE, r_local, cc * 4, pv);
-        bt_store_row32(ds_s + half * BT_TILE, r_local, cc * 4, dsv);
       }
       ptx::tc_fence_before();              // the TMEM reads above are complete
+    };
+    auto store_pds = [&]() {
+      uint8_t* prow = p_s + half * BT_TILE + r_local * 128;
+      uint8_t* drow = ds_s + half * BT_TILE + r_local * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {        // eight 16-byte pieces = this thread's 64 keys
+        const int sw = (g ^ (r_local & 7)) * 16;
+        *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pk_p[4 * g], pk_p[4 * g + 1], pk_p[4 * g + 2], pk_p[4 * g + 3]);
+        *reinterpret_cast<uint4*>(drow + sw) = make_uint4(pk_ds[4 * g], pk_ds[4 * g + 1], pk_ds[4 * g + 2], pk_ds[4 * g + 3]);
+      }
+    };
+    auto dq_epilogue = [&](int i) {        // dQ_i contribution of this key tile: TMEM -> swizzled fp32 staging -> TMA reduce-add
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DQ + (uint32_t)(i & 1) * 64 + half * 32, r);
+      ptx::tmem_ld_wait();
+      if (lane == 0) ptx::tma_store_wait_read<0>();          // the previous reduce has drained this staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<uint4*>(my_stg + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && i * BT_M + quarter * 32 < p.N) {
+        ptx::tma_reduce_add_3d(&tm_dq, my_stg, col_q + half * 32, i * BT_M + quarter * 32, b);   // rows >= N are dropped
+        ptx::tma_store_commit();
+      }
+    };
+    compute(0);
+    for (int i = 0; i < n_t; ++i) {
+      if (i > 0) {                         // MMAs(i - 1) have retired: P / dS shared memory is free, dQ(i - 1) is complete
+        ptx::mbar_wait(dq_full, (i - 1) & 1);
+        ptx::tc_fence_after();
+      }
+      store_pds();
       ptx::fence_proxy_async_smem();       // P / dS visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pds_full);
-      // ---- dQ_i contribution of this key tile: TMEM -> swizzled fp32 staging -> TMA reduce-add ----
-      ptx::mbar_wait(dq_full, i & 1);
-      ptx::tc_fence_after();
-      {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DQ + half * 32, r);
-        ptx::tmem_ld_wait();
-        if (lane == 0) ptx::tma_store_wait_read<0>();        // the previous reduce has drained this staging buffer
-        __syncwarp();
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          *reinterpret_cast<uint4*>(my_stg + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
-        ptx::tc_fence_before();
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && i * BT_M + quarter * 32 < p.N) {
-          ptx::tma_reduce_add_3d(&tm_dq, my_stg, col_q + half * 32, i * BT_M + quarter * 32, b);   // rows >= N are dropped
-          ptx::tma_store_commit();
-        }
-      }
+      if (i > 0) dq_epilogue(i - 1);
+      if (i + 1 < n_t) compute(i + 1);
     }
+    ptx::mbar_wait(dq_full, (n_t - 1) & 1);
+    ptx::tc_fence_after();
+    dq_epilogue(n_t - 1);
     // ---- dK_j, dV_j: TMEM -> bf16 -> the (dead) K / V tiles -> two TMA stores ----
     ptx::mbar_wait(dkv_full, 0);
     ptx::tc_fence_after();

@@ -159,24 +159,35 @@ row_bwd_kernel(const RowBwdParams p) {
   }
 }
 
-// partial column sums of x [M, C] (ld elements between rows): grid = slabs of rows, partials [grid][C]
+// partial column sums of x [M, C] (ld elements between rows): grid = (column blocks of 512, row slabs), partials
+// [slab][C].  128 column groups of 4 x 2 row phases per CTA, eight rows in flight per thread.
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, int ld, int M, int C, float* __restrict__ partials) {
+  __shared__ float4 red[128];
   pdl_trigger();
   pdl_wait();
-  const int per = (M + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * per, r1 = min(M, r0 + per);
-  for (int c4 = threadIdx.x; c4 < C / 4; c4 += blockDim.x) {
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    int r = r0;
-    for (; r + 1 < r1; r += 2) {
-      const float4 u = ld_row4<T>(x + (size_t)r * ld, c4), v = ld_row4<T>(x + (size_t)(r + 1) * ld, c4);
-      a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
-      a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+  const int cgp = threadIdx.x & 127, ph = threadIdx.x >> 7;
+  const int c4 = blockIdx.x * 128 + cgp;
+  const int per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(M, r0 + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < C / 4) {
+    int r = r0 + ph;
+    for (; r + 14 < r1; r += 16) {
+      float4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = ld_row4<T>(x + (size_t)(r + 2 * k) * ld, c4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc.x += u[k].x; acc.y += u[k].y; acc.z += u[k].z; acc.w += u[k].w; }
     }
-    if (r < r1) { const float4 u = ld_row4<T>(x + (size_t)r * ld, c4); a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w; }
-    reinterpret_cast<float4*>(partials + (size_t)blockIdx.x * C)[c4] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    for (; r < r1; r += 2) { const float4 u = ld_row4<T>(x + (size_t)r * ld, c4); acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w; }
+  }
+  if (ph == 1) red[cgp] = acc;
+  __syncthreads();
+  if (ph == 0 && c4 < C / 4) {
+    const float4 o = red[cgp];
+    reinterpret_cast<float4*>(partials + (size_t)blockIdx.y * C)[c4] = make_float4(acc.x + o.x, acc.y + o.y, acc.z + o.z, acc.w + o.w);
   }
 }
 
@@ -395,11 +406,13 @@ extern "C" int tpat_colsum(const void* x, int dtype, int ld, int M, int C, float
   TPAT_CHECK(x && partials_ws && dst, "tpat_colsum: null pointer");
   TPAT_CHECK(M >= 0 && C > 0 && C % 4 == 0 && C <= 4096 && ld >= C && aligned16(x) && (ld * dtype_size(dtype)) % 8 == 0, "tpat_colsum: need C %% 4 == 0, C <= 4096, aligned rows");
   if (M == 0) return 0;
-  int grid = (M + 31) / 32;
-  if (grid > 2 * sm_count()) grid = 2 * sm_count();
+  const int cblocks = (C / 4 + 127) / 128;
+  int grid = (M + 63) / 64;                                 // row slabs
+  const int max_slabs = (2 * sm_count()) / cblocks > 0 ? (2 * sm_count()) / cblocks : 1;
+  if (grid > max_slabs) grid = max_slabs;
   cudaStream_t st = as_stream(stream);
-  if (dtype == TPAT_F32) TPAT_CUDA(launch_kernel(colsum_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)x, ld, M, C, partials_ws));
-  else TPAT_CUDA(launch_kernel(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)x, ld, M, C, partials_ws));
+  if (dtype == TPAT_F32) TPAT_CUDA(launch_kernel(colsum_kernel<float>, dim3(cblocks, grid), dim3(256), 0, st, (const float*)x, ld, M, C, partials_ws));
+  else TPAT_CUDA(launch_kernel(colsum_kernel<__nv_bfloat16>, dim3(cblocks, grid), dim3(256), 0, st, (const __nv_bfloat16*)x, ld, M, C, partials_ws));
   TPAT_LAUNCH_CHECK();
   return finish_partials(partials_ws, grid, 1, C, dst, nullptr, nullptr, nullptr, st);
 }
