@@ -44,7 +44,7 @@ enum {
   TPAT_EPI_BIAS_GELU = 1,     /* C = gelu_erf(A W^T + b)                     */
   TPAT_EPI_BIAS_RESIDUAL = 2, /* C = R + A W^T + b   (C may alias R)         */
   TPAT_EPI_BIAS_POS = 3,      /* patch-embed: C[b, extra+p] = A W^T + b + pos[extra+p] */
-  TPAT_EPI_DGELU = 4          /* training (tpat_gemm_train): C = (A W^T) * gelu'(aux)      */
+  TPAT_EPI_DGELU = 4          /* training (tpat_gemm_train): C = (A W^T) * aux, aux = saved gelu'(h) */
 };
 /* GEMM / attention implementation */
 enum {
@@ -325,8 +325,8 @@ int tpat_forward_launch_count(const tpat_forward_args* args);
 
 /* extras of tpat_gemm_train: all optional */
 typedef struct tpat_gemm_extra {
-  void* pre_out; int ld_pre;                     /* TPAT_EPI_BIAS_GELU: also store acc + bias (dtype of C): the GELU backward needs it */
-  const void* aux; int ld_aux;                   /* TPAT_EPI_DGELU: pre-activation h (dtype of C); C = (A W^T) * gelu'(h)            */
+  void* dact_out; int ld_dact;                   /* TPAT_EPI_BIAS_GELU: also store gelu'(A W^T + b) (dtype of C) for the backward    */
+  const void* aux; int ld_aux;                   /* TPAT_EPI_DGELU: that saved derivative (dtype of C); C = (A W^T) * aux           */
   const float* row_scale; int rows_per_clip;     /* TPAT_EPI_BIAS_RESIDUAL: C = R + row_scale[m / rows_per_clip] * (A W^T + b):
                                                     timm DropPath's per-sample scale 0 | 1 / keep_prob (models_vit.py:149,198,205)   */
 } tpat_gemm_extra;

@@ -168,17 +168,20 @@ def test_gemm_train_epilogues(impl_name):
     a = torch.randn(M, D, device=dev()).to(dt)
     w1 = (torch.randn(Dh, D, device=dev()) * 0.03).to(dt)
     b1 = torch.randn(Dh, device=dev()) * 0.1
-    act, pre = ops.gemm_train(a, w1, b1, dt, _lib.EPI_BIAS_GELU, impl, want_pre=True)
-    pre_ref = a.double() @ w1.double().T + b1.double()
-    assert rel_err(pre.float(), pre_ref) < tol and rel_err(act.float(), F.gelu(pre_ref)) < tol
-    # dgrad with GELU': dh = (g W2) * gelu'(pre)
+    act, dact = ops.gemm_train(a, w1, b1, dt, _lib.EPI_BIAS_GELU, impl, want_dact=True)
+    pre_ref = (a.double() @ w1.double().T + b1.double()).requires_grad_(True)
+    act_ref = F.gelu(pre_ref)
+    act_ref.sum().backward()                                              # pre_ref.grad = gelu'(pre)
+    assert rel_err(act.float(), act_ref.detach()) < tol and rel_err(dact.float(), pre_ref.grad) < tol
+    plain = ops.gemm_train(a, w1, b1, dt, _lib.EPI_BIAS_GELU, impl)
+    assert torch.equal(plain, act)                                        # keeping the derivative does not change the forward
+    # dgrad with the saved derivative: dh = (g W2) * gelu'(pre)
     g = torch.randn(M, D, device=dev()).to(dt)
     w2 = (torch.randn(D, Dh, device=dev()) * 0.03).to(dt)              # fc2.weight [out=D, in=Dh]; B operand = its [in, out] copy
     w2t = w2.T.contiguous()
-    dh = ops.gemm_train(g, w2t, None, dt, _lib.EPI_DGELU, impl, aux=pre)
-    hp = pre.double().requires_grad_(True)
-    F.gelu(hp).backward(g.double() @ w2.double())
-    assert nerr(dh.float(), hp.grad) < (2e-5 if impl_name == "simt" else 1.5e-2)
+    dh = ops.gemm_train(g, w2t, None, dt, _lib.EPI_DGELU, impl, aux=dact)
+    want_dh = (g.double() @ w2.double()) * pre_ref.grad
+    assert nerr(dh.float(), want_dh) < (2e-5 if impl_name == "simt" else 1.5e-2)
     # residual with per-clip scale
     res = torch.randn(M, D, device=dev())
     scale = torch.tensor([0.0, 1.0 / 0.9, 1.0 / 0.9], device=dev())

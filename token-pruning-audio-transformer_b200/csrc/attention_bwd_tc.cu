@@ -34,7 +34,14 @@ constexpr int BT_THREADS = 320;
 constexpr int BT_SMEM = 1024 + 2 * BT_TILE + 4 * BT_TILE + 2 * BT_PS + 8 * 4096 + 256;
 constexpr uint32_t BT_S = 0, BT_DP = 128, BT_DV = 256, BT_DK = 320, BT_DQ = 384;   // dQ: two buffers, [384,448) and [448,512)
 
+#ifdef TPAT_ATTN_BWD_TRACE
+#define BWD_TRACE(slot) do { if (tracing && tn < 250) p.trace[tn++] = (clock64() & 0xFFFFFFFFFFFFll) | ((long long)(slot) << 48); } while (0)
+#else
+#define BWD_TRACE(slot) do { } while (0)
+#endif
+
 struct AttnBwdTcParams {
+  long long* trace;      // debug builds (TPAT_ATTN_BWD_TRACE): clock stamps of one softmax thread and of the MMA thread
   const float* lse;      // [B, H, N] natural log
   const float* delta;    // [B, H, N]
   int N, H, n_t;
@@ -120,6 +127,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (ptx::elect_one()) {
+#ifdef TPAT_ATTN_BWD_TRACE
+      const bool tracing = p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == (gridDim.z >> 1);
+      int tn = 256;
+#define BWD_TRACE_M(slot) do { if (tracing && tn < 500) p.trace[tn++] = (clock64() & 0xFFFFFFFFFFFFll) | ((long long)(slot) << 48); } while (0)
+#else
+#define BWD_TRACE_M(slot) do { } while (0)
+#endif
       constexpr uint32_t idesc_s = ptx::idesc_bf16_f32(128, 128, 0, 0);    // Q / dO (K-major) x K / V (K-major)
       constexpr uint32_t idesc_kv = ptx::idesc_bf16_f32(128, 64, 1, 1);    // P^T / dS^T (MN-major) x dO / Q (MN-major)
       constexpr uint32_t idesc_q = ptx::idesc_bf16_f32(128, 64, 0, 1);     // dS (K-major) x K (MN-major)
@@ -143,8 +157,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       issue_sdp(0);
       for (int i = 0; i < n_t; ++i) {
         const int st = i & 1;
+        BWD_TRACE_M(20);
         ptx::mbar_wait(pds_full, i & 1);            // P and dS of tile i are in shared memory; S / dP TMEM have been read
         ptx::tc_fence_after();
+        BWD_TRACE_M(21);
         // S / dP of the NEXT query tile first: the softmax warps work on them while the 24 MMAs below run
         if (i + 1 < n_t) issue_sdp(i + 1);
         const uint32_t p_a = ptx::smem_u32(p_s), ds_a = ptx::smem_u32(ds_s);
@@ -165,7 +181,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
                           ptx::smem_desc_sw128(k_a + ks * 2048, 16, 1024), idesc_q, ks != 0);
         ptx::tc_commit(&qdo_empty[st]);
         ptx::tc_commit(dq_full);                    // also: P / dS shared memory is free again
+        BWD_TRACE_M(22);
       }
+#ifdef TPAT_ATTN_BWD_TRACE
+      if (tracing) p.trace[511] = tn;
+#endif
       ptx::tc_commit(dkv_full);
     }
   } else {
@@ -182,14 +202,21 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     // Software pipeline over the query tiles: while the tensor core runs the 24 MMAs of tile i, these warps already
     // turn S / dP of tile i + 1 into P / dS (kept in registers as bf16 pairs); the stores into the shared P / dS tile wait
     // for dq_full(i) (= those MMAs have retired), and the dQ_i epilogue runs after the hand-off, next to MMAs(i + 1).
+#ifdef TPAT_ATTN_BWD_TRACE
+    const bool tracing = p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == (gridDim.z >> 1) && threadIdx.x == 64;
+    int tn = 0;
+    BWD_TRACE(0);
+#endif
     uint32_t pk_p[32], pk_ds[32];          // this thread's 64 keys of P and dS, packed bf16 pairs
     auto compute = [&](int i) {
       const int row = i * BT_M + r_local;
       const bool row_ok = row < p.N;
       const float lse2 = row_ok ? __ldg(lse_bh + row) * LOG2E : 0.f;
       const float dlt = row_ok ? __ldg(delta_bh + row) : 0.f;
+      BWD_TRACE(1);
       ptx::mbar_wait(s_full, i & 1);
       ptx::tc_fence_after();
+      BWD_TRACE(2);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int col0 = half * 64 + cc * 32;               // column of the 128-key tile
@@ -208,6 +235,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
       }
       ptx::tc_fence_before();              // the TMEM reads above are complete
+      BWD_TRACE(3);
     };
     auto store_pds = [&]() {
       uint8_t* prow = p_s + half * BT_TILE + r_local * 128;
@@ -239,19 +267,27 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     compute(0);
     for (int i = 0; i < n_t; ++i) {
       if (i > 0) {                         // MMAs(i - 1) have retired: P / dS shared memory is free, dQ(i - 1) is complete
+        BWD_TRACE(4);
         ptx::mbar_wait(dq_full, (i - 1) & 1);
         ptx::tc_fence_after();
+        BWD_TRACE(5);
       }
       store_pds();
       ptx::fence_proxy_async_smem();       // P / dS visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pds_full);
+      BWD_TRACE(6);
       if (i > 0) dq_epilogue(i - 1);
+      BWD_TRACE(7);
       if (i + 1 < n_t) compute(i + 1);
     }
     ptx::mbar_wait(dq_full, (n_t - 1) & 1);
     ptx::tc_fence_after();
     dq_epilogue(n_t - 1);
+    BWD_TRACE(8);
+#ifdef TPAT_ATTN_BWD_TRACE
+    if (tracing) p.trace[254] = tn;
+#endif
     // ---- dK_j, dV_j: TMEM -> bf16 -> the (dead) K / V tiles -> two TMA stores ----
     ptx::mbar_wait(dkv_full, 0);
     ptx::tc_fence_after();
@@ -319,6 +355,11 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const 
   if (int rc = encode_tmap_3d(&tm_dq, dq_acc, 4, B, N, H * BT_HD, 32, 32)) return rc;
   if (int rc = encode_tmap_3d(&tm_dkv, dqkv, 2, B, N, 3 * H * BT_HD, BT_M, 64)) return rc;
   AttnBwdTcParams p;
+  p.trace = nullptr;
+#ifdef TPAT_ATTN_BWD_TRACE
+  { static long long* dbg = nullptr; if (!dbg) cudaMalloc(&dbg, 512 * sizeof(long long)); cudaMemsetAsync(dbg, 0, 512 * sizeof(long long), st);
+    p.trace = dbg; extern long long* g_attn_bwd_trace_buf; g_attn_bwd_trace_buf = dbg; }
+#endif
   p.lse = lse; p.delta = delta; p.N = N; p.H = H; p.n_t = (N + BT_M - 1) / BT_M;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   static DeviceOnce once;
@@ -336,6 +377,14 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const 
 }
 
 }  // namespace tpat
+
+#ifdef TPAT_ATTN_BWD_TRACE
+namespace tpat { long long* g_attn_bwd_trace_buf = nullptr; }
+extern "C" int tpat_debug_attn_bwd_trace(long long* host_out) {   // debug builds only: copy the 512 stamps to the host
+  if (!tpat::g_attn_bwd_trace_buf) return 1;
+  return cudaMemcpy(host_out, tpat::g_attn_bwd_trace_buf, 512 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
+#endif
 
 extern "C" size_t tpat_attention_bwd_ws_floats(int B, int N, int H, int hd) {
   return ((size_t)B * H * N + 63) / 64 * 64 + (size_t)B * N * H * hd;

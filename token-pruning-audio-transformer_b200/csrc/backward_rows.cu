@@ -408,7 +408,10 @@ extern "C" int tpat_colsum(const void* x, int dtype, int ld, int M, int C, float
   if (M == 0) return 0;
   const int cblocks = (C / 4 + 127) / 128;
   int grid = (M + 63) / 64;                                 // row slabs
-  const int max_slabs = (2 * sm_count()) / cblocks > 0 ? (2 * sm_count()) / cblocks : 1;
+  // up to ~8 CTAs per SM in flight (this kernel is pure streaming: occupancy = bytes in flight); the partials buffer holds
+  // tpat_bwd_partials_floats / C >= 1184 * 4096 / C slabs
+  int max_slabs = (8 * sm_count()) / cblocks > 0 ? (8 * sm_count()) / cblocks : 1;
+  if ((size_t)max_slabs * C > (size_t)2 * 148 * 4 * 4096) max_slabs = (int)((size_t)2 * 148 * 4 * 4096 / C);
   if (grid > max_slabs) grid = max_slabs;
   cudaStream_t st = as_stream(stream);
   if (dtype == TPAT_F32) TPAT_CUDA(launch_kernel(colsum_kernel<float>, dim3(cblocks, grid), dim3(256), 0, st, (const float*)x, ld, M, C, partials_ws));

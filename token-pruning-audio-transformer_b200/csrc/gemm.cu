@@ -47,10 +47,10 @@ static int gemm_entry(const void* A, int a_dtype, int lda, const void* W, int w_
   if (M == 0) return 0;
   EpiParams ep{bias, residual, ldr, pos, P, num_extra, epilogue};
   if (extra != nullptr) {
-    if (extra->pre_out != nullptr) {
-      TPAT_CHECK(epilogue == TPAT_EPI_BIAS_GELU && extra->ld_pre >= N && aligned16(extra->pre_out) && (extra->ld_pre * dtype_size(c_dtype)) % 16 == 0,
-                 "tpat_gemm_train: pre_out needs the bias+GELU epilogue and 16-byte aligned rows");
-      ep.pre_out = extra->pre_out; ep.ld_pre = extra->ld_pre;
+    if (extra->dact_out != nullptr) {
+      TPAT_CHECK(epilogue == TPAT_EPI_BIAS_GELU && extra->ld_dact >= N && aligned16(extra->dact_out) && (extra->ld_dact * dtype_size(c_dtype)) % 16 == 0,
+                 "tpat_gemm_train: dact_out needs the bias+GELU epilogue and 16-byte aligned rows");
+      ep.dact_out = extra->dact_out; ep.ld_dact = extra->ld_dact;
     }
     if (epilogue == TPAT_EPI_DGELU) { ep.aux = extra->aux; ep.ld_aux = extra->ld_aux; }
     if (extra->row_scale != nullptr) {

@@ -16,8 +16,8 @@ struct EpiParams {
   const float* ln_colsum = nullptr;
   float ln_eps = 0.f;
   // training extras (tpat_gemm_train): all optional
-  void* pre_out = nullptr; int ld_pre = 0;            // BIAS_GELU: also store the pre-activation (acc + bias), dtype of C
-  const void* aux = nullptr; int ld_aux = 0;          // DGELU: pre-activation h (dtype of C): C = acc * gelu'(h)
+  void* dact_out = nullptr; int ld_dact = 0;            // BIAS_GELU: also store gelu'(acc + bias), dtype of C
+  const void* aux = nullptr; int ld_aux = 0;          // DGELU: the saved gelu'(h) (dtype of C): C = acc * aux
   const float* row_scale = nullptr; int rows_per_clip = 0;   // BIAS_RESIDUAL: C = R + row_scale[m / rows_per_clip] * (acc + bias)  (DropPath)
 };
 

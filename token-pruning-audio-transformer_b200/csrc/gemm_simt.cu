@@ -33,12 +33,12 @@ __device__ __forceinline__ void epi_store(OutT* C, int ldc, int m, int n, float 
   float v = acc + (ep.bias ? __ldg(ep.bias + n) : 0.f);
   size_t orow = (size_t)m;
   if (ep.epilogue == TPAT_EPI_BIAS_GELU) {
-    if (ep.pre_out) reinterpret_cast<OutT*>(ep.pre_out)[(size_t)m * ep.ld_pre + n] = from_f32<OutT>(v);
+    if (ep.dact_out)   // training: keep the exact erf-GELU derivative Phi(h) + h phi(h) for the backward
+      reinterpret_cast<OutT*>(ep.dact_out)[(size_t)m * ep.ld_dact + n] =
+          from_f32<OutT>(0.5f * (1.0f + erff(v * 0.70710678118654752440f)) + v * 0.39894228040143267794f * expf(-0.5f * v * v));
     v = gelu_erf(v);
   } else if (ep.epilogue == TPAT_EPI_DGELU) {
-    // exact erf-GELU derivative: Phi(h) + h phi(h)
-    const float h = to_f32<OutT>(reinterpret_cast<const OutT*>(ep.aux)[(size_t)m * ep.ld_aux + n]);
-    v *= 0.5f * (1.0f + erff(h * 0.70710678118654752440f)) + h * 0.39894228040143267794f * expf(-0.5f * h * h);
+    v *= to_f32<OutT>(reinterpret_cast<const OutT*>(ep.aux)[(size_t)m * ep.ld_aux + n]);
   } else if (ep.epilogue == TPAT_EPI_BIAS_RESIDUAL) {
     if (ep.row_scale) v *= __ldg(ep.row_scale + m / ep.rows_per_clip);
     v = ep.residual[(size_t)m * ep.ldr + n] + v;  // plain load: C may alias the residual

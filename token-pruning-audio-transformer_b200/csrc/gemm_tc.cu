@@ -319,7 +319,7 @@ int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc
   TcGemmParams p{};
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
-  p.pre_out = ep.pre_out; p.ld_pre = ep.ld_pre; p.aux = ep.aux; p.ld_aux = ep.ld_aux; p.row_scale = ep.row_scale; p.rows_per_clip = ep.rows_per_clip;
+  p.dact_out = ep.dact_out; p.ld_dact = ep.ld_dact; p.aux = ep.aux; p.ld_aux = ep.ld_aux; p.row_scale = ep.row_scale; p.rows_per_clip = ep.rows_per_clip;
   p.bn = bn;
   p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + bn - 1) / bn;
   p.desc = g_walk_desc;

@@ -320,7 +320,7 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.xb = (__nv_bfloat16*)ep.xb; p.ldxb = ep.ldxb; p.part_out = reinterpret_cast<float2*>(ep.part_out); p.part_ld = ep.part_ld;
   p.ln_part = reinterpret_cast<const float2*>(ep.ln_part); p.ln_chunks = ep.ln_chunks; p.ln_colsum = ep.ln_colsum; p.ln_eps = ep.ln_eps;
-  p.pre_out = ep.pre_out; p.ld_pre = ep.ld_pre; p.aux = ep.aux; p.ld_aux = ep.ld_aux; p.row_scale = ep.row_scale; p.rows_per_clip = ep.rows_per_clip;
+  p.dact_out = ep.dact_out; p.ld_dact = ep.ld_dact; p.aux = ep.aux; p.ld_aux = ep.ld_aux; p.row_scale = ep.row_scale; p.rows_per_clip = ep.rows_per_clip;
   p.tiles_m = (M + 255) / 256; p.tiles_n = (N + TG_BN - 1) / TG_BN;
   p.bn = TG_BN;
   p.desc = g_walk_desc;

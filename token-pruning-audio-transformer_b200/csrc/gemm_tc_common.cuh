@@ -35,7 +35,7 @@ struct TcGemmParams {
   const float* ln_colsum;
   float ln_eps;
   // training extras (see EpiParams)
-  void* pre_out; int ld_pre;
+  void* dact_out; int ld_dact;
   const void* aux; int ld_aux;
   const float* row_scale; int rows_per_clip;
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
@@ -64,17 +64,22 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
-// d/dx of gelu_erf_fast (same fitted form, one MUFU): 0.5 (1 + t) + 0.5 x (1 - t^2) u'(x), u = x (a0 + a1 x^2 + a2 x^4)
-__device__ __forceinline__ float gelu_erf_fast_grad(float x) {
+// gelu_erf_fast and its derivative from ONE tanh: d/dx = 0.5 (1 + t) + 0.5 x (1 - t^2) u'(x), u = x (a0 + a1 x^2 + a2 x^4).
+// The training forward stores the derivative (bf16, |gelu'| <= 1.13) instead of the pre-activation, so that the GELU
+// backward inside the data-gradient GEMM's epilogue is one multiply (measured: the recompute-in-the-backward form ran
+// that GEMM at 704 TF/s against 1316 TF/s without it).
+__device__ __forceinline__ void gelu_erf_fast_both(float x, float& y, float& dy) {
   const float x2 = fminf(x * x, 81.0f);
   float h = fmaf(x2, -2.8633e-4f, 0.036609f);
   h = fmaf(h, x2, 0.797786f);
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h * x));
+  const float hx = 0.5f * x;
+  y = fmaf(hx, t, hx);
   float du = fmaf(x2, 5.0f * -2.8633e-4f, 3.0f * 0.036609f);
   du = fmaf(du, x2, 0.797786f);
   const float s = fmaf(-t, t, 1.0f);                 // 1 - t^2
-  return fmaf(0.5f * x * s, du, fmaf(0.5f, t, 0.5f));
+  dy = fmaf(hx * s, du, fmaf(0.5f, t, 0.5f));
 }
 
 // (mean, rstd) of one row from the partial moments of its 32-element chunks (Chan's pairwise update, fixed order)
@@ -135,6 +140,24 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
   constexpr int NCH = TcEpiPrefetch<EW>::NCH, CSTRIDE = TcEpiPrefetch<EW>::CSTRIDE;
   const int jl = lane & 7, rl = lane >> 3;   // coalesced phase: lane -> (16 B piece, row within a group of 4)
   bool released = false;
+  // DGELU (bf16): the saved GELU derivatives of chunk ci + 1 are requested while chunk ci is processed (packed bf16,
+  // two register buffers): with K = 768 the epilogue has ~7000 cycles per tile and three chunks per warp, each of which
+  // would otherwise expose a full L2 / HBM round trip (measured: 704 TF/s before, see profiles/r02_ncu_full_summary.txt)
+  constexpr bool kAuxQ = EPI == TPAT_EPI_DGELU && sizeof(OutT) == 2;
+  uint2 auxq[2][8];
+  auto load_aux = [&](int ci_, uint2 (&dst)[8]) {
+    const int c_ = cg + CSTRIDE * ci_;
+    const int n_ = n0 + c_ * 32;
+    if (c_ < p.bn / 32 && n_ < p.N) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int m = m0 + it * 4 + rl;
+        dst[it] = m < p.M ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + (size_t)m * p.ld_aux + n_ + jl * 4))
+                          : make_uint2(0u, 0u);
+      }
+    }
+  };
+  if constexpr (kAuxQ) load_aux(0, auxq[0]);
 #pragma unroll
   for (int ci = 0; ci < NCH; ++ci) {
     const int c = cg + CSTRIDE * ci;
@@ -142,6 +165,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
     const bool live = c < p.bn / 32 && n < p.N;      // warp-uniform
     const int ncol = n + jl * 4;
     float4 extra[8];
+    if constexpr (kAuxQ) { if (ci + 1 < NCH) load_aux(ci + 1, auxq[(ci + 1) & 1]); }
     if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL) {
       if (live) {
 #pragma unroll
@@ -150,8 +174,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
           extra[it] = m < p.M ? *reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + ncol) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-    } else if constexpr (EPI == TPAT_EPI_DGELU) {
-      if (live) {   // the saved pre-activations are requested before the TMEM read: their latency overlaps it
+    } else if constexpr (EPI == TPAT_EPI_DGELU && !kAuxQ) {
+      if (live) {   // the saved GELU derivatives are requested before the TMEM read: their latency overlaps it
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int m = m0 + it * 4 + rl;
@@ -209,26 +233,35 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
     }
     __syncwarp();   // all lanes have read the transpose buffer: the next chunk may overwrite it
     if constexpr (EPI == TPAT_EPI_BIAS_GELU) {
-      if (p.pre_out != nullptr) {            // training: keep the pre-activation for the GELU backward
+      if (p.dact_out != nullptr) {            // training: GELU and its derivative from one tanh; the derivative is kept
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
+          float4 d;
+          gelu_erf_fast_both(v[it].x, v[it].x, d.x); gelu_erf_fast_both(v[it].y, v[it].y, d.y);
+          gelu_erf_fast_both(v[it].z, v[it].z, d.z); gelu_erf_fast_both(v[it].w, v[it].w, d.w);
           const int m = m0 + it * 4 + rl;
           if (m >= p.M) continue;
-          if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.pre_out) + (size_t)m * p.ld_pre + ncol) = v[it];
-          else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.pre_out) + (size_t)m * p.ld_pre + ncol) =
-                   make_uint2(pack_bf16x2(v[it].x, v[it].y), pack_bf16x2(v[it].z, v[it].w));
+          if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dact_out) + (size_t)m * p.ld_dact + ncol) = d;
+          else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.dact_out) + (size_t)m * p.ld_dact + ncol) =
+                   make_uint2(pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
         }
-      }
+      } else {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        v[it].x = gelu_erf_fast(v[it].x); v[it].y = gelu_erf_fast(v[it].y);
-        v[it].z = gelu_erf_fast(v[it].z); v[it].w = gelu_erf_fast(v[it].w);
+        for (int it = 0; it < 8; ++it) {
+          v[it].x = gelu_erf_fast(v[it].x); v[it].y = gelu_erf_fast(v[it].y);
+          v[it].z = gelu_erf_fast(v[it].z); v[it].w = gelu_erf_fast(v[it].w);
+        }
       }
     } else if constexpr (EPI == TPAT_EPI_DGELU) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        v[it].x *= gelu_erf_fast_grad(extra[it].x); v[it].y *= gelu_erf_fast_grad(extra[it].y);
-        v[it].z *= gelu_erf_fast_grad(extra[it].z); v[it].w *= gelu_erf_fast_grad(extra[it].w);
+        if constexpr (kAuxQ) {
+          const uint2 hh = auxq[ci & 1][it];
+          const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162*>(&hh.x), hb = *reinterpret_cast<const __nv_bfloat162*>(&hh.y);
+          v[it].x *= __low2float(ha); v[it].y *= __high2float(ha); v[it].z *= __low2float(hb); v[it].w *= __high2float(hb);
+        } else {
+          v[it].x *= extra[it].x; v[it].y *= extra[it].y; v[it].z *= extra[it].z; v[it].w *= extra[it].w;
+        }
       }
     } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS) {
       if (EPI == TPAT_EPI_BIAS_RESIDUAL && p.row_scale != nullptr) {     // DropPath: per-clip scale of the branch

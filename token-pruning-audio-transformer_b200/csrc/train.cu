@@ -220,7 +220,7 @@ extern "C" int tpat_train_forward(const tpat_train_args* t, tpat_stream_t stream
     }
     {
       tpat_gemm_extra ex{};
-      ex.pre_out = k.h; ex.ld_pre = Dh;
+      ex.dact_out = k.h; ex.ld_dact = Dh;
       if (int rc = tpat_gemm_train(k.y2, act, D, bw.fc1_w, act, bw.fc1_b, k.a, act, Dh, nullptr, 0, M2, Dh, D, TPAT_EPI_BIAS_GELU,
                                    impl, &ex, stream)) return rc;
     }

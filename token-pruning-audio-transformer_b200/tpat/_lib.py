@@ -54,7 +54,7 @@ class ForwardArgs(Structure):
 
 class GemmExtra(Structure):
     """tpat_gemm_extra (include/tpat.h)."""
-    _fields_ = [("pre_out", c_void_p), ("ld_pre", c_int), ("aux", c_void_p), ("ld_aux", c_int), ("row_scale", c_void_p),
+    _fields_ = [("dact_out", c_void_p), ("ld_dact", c_int), ("aux", c_void_p), ("ld_aux", c_int), ("row_scale", c_void_p),
                 ("rows_per_clip", c_int)]
 
 

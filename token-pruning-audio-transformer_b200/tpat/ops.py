@@ -328,9 +328,9 @@ def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, lse
 
 
 def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dtype: torch.dtype, epilogue: int, impl: int,
-               residual: Optional[torch.Tensor] = None, want_pre: bool = False, aux: Optional[torch.Tensor] = None,
+               residual: Optional[torch.Tensor] = None, want_dact: bool = False, aux: Optional[torch.Tensor] = None,
                row_scale: Optional[torch.Tensor] = None, rows_per_clip: int = 0):
-    """tpat_gemm_train: out = epilogue(a @ w.T + bias) with the training extras (pre-activation output, GELU-backward
+    """tpat_gemm_train: out = epilogue(a @ w.T + bias) with the training extras (GELU-derivative output, GELU-backward
     epilogue, DropPath row scale)."""
     import ctypes
     _req(a, name="a"); _req(w, a.dtype, "w")
@@ -339,9 +339,9 @@ def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], o
     out = torch.empty(M, N, device=a.device, dtype=out_dtype)
     ex = _lib.GemmExtra()
     pre = None
-    if want_pre:
+    if want_dact:
         pre = torch.empty(M, N, device=a.device, dtype=out_dtype)
-        ex.pre_out, ex.ld_pre = pre.data_ptr(), N
+        ex.dact_out, ex.ld_dact = pre.data_ptr(), N
     if aux is not None:
         _req(aux, out_dtype, "aux")
         ex.aux, ex.ld_aux = aux.data_ptr(), N
@@ -350,7 +350,7 @@ def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], o
     check(lib.tpat_gemm_train(a.data_ptr(), _DT[a.dtype], K, w.data_ptr(), _DT[w.dtype], _ptr(bias), out.data_ptr(), _DT[out_dtype], N,
                               _ptr(residual), N if residual is not None else 0, M, N, K, epilogue, impl, ctypes.byref(ex), _stream()),
           "tpat_gemm_train")
-    return (out, pre) if want_pre else out
+    return (out, pre) if want_dact else out
 
 
 def adamw(p, g, m, v, p_bf16, chunks, groups, lr, beta1, beta2, eps, step, grad_scale=1.0):
