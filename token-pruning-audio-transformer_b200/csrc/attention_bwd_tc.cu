@@ -78,7 +78,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   uint64_t* pds_full = bars + 6;           // [1] 8 arrivals
   uint64_t* dq_full = bars + 7;            // [1]
   uint64_t* dkv_full = bars + 8;           // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* sdp_free = bars + 9;           // [1] 8 arrivals: S / dP of the current tile are in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,6 +97,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     ptx::mbar_init(pds_full, 8);
     ptx::mbar_init(dq_full, 1);
     ptx::mbar_init(dkv_full, 1);
+    ptx::mbar_init(sdp_free, 8);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -157,12 +159,15 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       issue_sdp(0);
       for (int i = 0; i < n_t; ++i) {
         const int st = i & 1;
+        // S / dP of the NEXT query tile as soon as the softmax warps hold tile i's in registers (about half way through
+        // their exponentials): the results are ready long before the softmax warps come back for them
+        ptx::mbar_wait(sdp_free, i & 1);
+        ptx::tc_fence_after();
+        if (i + 1 < n_t) issue_sdp(i + 1);
         BWD_TRACE_M(20);
-        ptx::mbar_wait(pds_full, i & 1);            // P and dS of tile i are in shared memory; S / dP TMEM have been read
+        ptx::mbar_wait(pds_full, i & 1);            // P and dS of tile i are in shared memory
         ptx::tc_fence_after();
         BWD_TRACE_M(21);
-        // S / dP of the NEXT query tile first: the softmax warps work on them while the 24 MMAs below run
-        if (i + 1 < n_t) issue_sdp(i + 1);
         const uint32_t p_a = ptx::smem_u32(p_s), ds_a = ptx::smem_u32(ds_s);
         const uint32_t do_a = ptx::smem_u32(do_s + st * BT_TILE), q_a = ptx::smem_u32(q_s + st * BT_TILE), k_a = ptx::smem_u32(k_s);
         // K index = query row: 16 rows = two 8-row groups of 1024 B; the second 64-key block of P / dS is 16 KB further (LBO)
@@ -208,15 +213,27 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     BWD_TRACE(0);
 #endif
     uint32_t pk_p[32], pk_ds[32];          // this thread's 64 keys of P and dS, packed bf16 pairs
-    auto compute = [&](int i) {
+    // log-sum-exp and delta of this thread's row of tile i are requested one tile ahead (their global-load latency was
+    // ~850 cycles per tile pair on the critical path, profiles/r02m_attn_bwd_trace_v3.txt)
+    float lse_nx = 0.f, dlt_nx = 0.f;
+    auto prefetch_row = [&](int i) {
+      const int row = i * BT_M + r_local;
+      const bool ok = i < n_t && row < p.N;
+      lse_nx = ok ? __ldg(lse_bh + row) : 0.f;
+      dlt_nx = ok ? __ldg(delta_bh + row) : 0.f;
+    };
+    auto compute = [&](int i, float lse_row, float dlt) {
       const int row = i * BT_M + r_local;
       const bool row_ok = row < p.N;
-      const float lse2 = row_ok ? __ldg(lse_bh + row) * LOG2E : 0.f;
-      const float dlt = row_ok ? __ldg(delta_bh + row) : 0.f;
+      const float lse2 = lse_row * LOG2E;
       BWD_TRACE(1);
       ptx::mbar_wait(s_full, i & 1);
       ptx::tc_fence_after();
       BWD_TRACE(2);
+      // dS = P (dP - delta) scale = P * fma(dP, scale, -delta * scale).  Fully valid tile pairs (the common case) skip the
+      // per-element bounds tests.
+      const float nds = -dlt * p.scale;
+      const bool all_ok = (i * BT_M + BT_M <= p.N) && (jt * BT_M + BT_M <= p.N);     // CTA-uniform
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int col0 = half * 64 + cc * 32;               // column of the 128-key tile
@@ -224,14 +241,29 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_S + col0, rs);
         ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DP + col0, rd);
         ptx::tmem_ld_wait();
-        const int key0 = jt * BT_M + col0;
+        if (cc == 1) {                       // both chunks are out of tensor memory: S / dP may be overwritten
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(sdp_free);
+        }
+        if (all_ok) {
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          const bool ok0 = row_ok && (key0 + t < p.N), ok1 = row_ok && (key0 + t + 1 < p.N);
-          const float p0 = ok0 ? ptx::ex2_ftz(fmaf(__uint_as_float(rs[t]), c, -lse2)) : 0.f;
-          const float p1 = ok1 ? ptx::ex2_ftz(fmaf(__uint_as_float(rs[t + 1]), c, -lse2)) : 0.f;
-          pk_p[cc * 16 + (t >> 1)] = pack_bf16x2(p0, p1);
-          pk_ds[cc * 16 + (t >> 1)] = pack_bf16x2(p0 * (__uint_as_float(rd[t]) - dlt) * p.scale, p1 * (__uint_as_float(rd[t + 1]) - dlt) * p.scale);
+          for (int t = 0; t < 32; t += 2) {
+            const float p0 = ptx::ex2_ftz(fmaf(__uint_as_float(rs[t]), c, -lse2));
+            const float p1 = ptx::ex2_ftz(fmaf(__uint_as_float(rs[t + 1]), c, -lse2));
+            pk_p[cc * 16 + (t >> 1)] = pack_bf16x2(p0, p1);
+            pk_ds[cc * 16 + (t >> 1)] = pack_bf16x2(p0 * fmaf(__uint_as_float(rd[t]), p.scale, nds), p1 * fmaf(__uint_as_float(rd[t + 1]), p.scale, nds));
+          }
+        } else {
+          const int key0 = jt * BT_M + col0;
+#pragma unroll
+          for (int t = 0; t < 32; t += 2) {
+            const bool ok0 = row_ok && (key0 + t < p.N), ok1 = row_ok && (key0 + t + 1 < p.N);
+            const float p0 = ok0 ? ptx::ex2_ftz(fmaf(__uint_as_float(rs[t]), c, -lse2)) : 0.f;
+            const float p1 = ok1 ? ptx::ex2_ftz(fmaf(__uint_as_float(rs[t + 1]), c, -lse2)) : 0.f;
+            pk_p[cc * 16 + (t >> 1)] = pack_bf16x2(p0, p1);
+            pk_ds[cc * 16 + (t >> 1)] = pack_bf16x2(p0 * fmaf(__uint_as_float(rd[t]), p.scale, nds), p1 * fmaf(__uint_as_float(rd[t + 1]), p.scale, nds));
+          }
         }
       }
       ptx::tc_fence_before();              // the TMEM reads above are complete
@@ -264,8 +296,12 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         ptx::tma_store_commit();
       }
     };
-    compute(0);
+    prefetch_row(0);
+    compute(0, lse_nx, dlt_nx);
+    prefetch_row(1);
     for (int i = 0; i < n_t; ++i) {
+      const float lse_i1 = lse_nx, dlt_i1 = dlt_nx;      // tile i + 1's values (requested a whole iteration ago)
+      prefetch_row(i + 2);
       if (i > 0) {                         // MMAs(i - 1) have retired: P / dS shared memory is free, dQ(i - 1) is complete
         BWD_TRACE(4);
         ptx::mbar_wait(dq_full, (i - 1) & 1);
@@ -279,7 +315,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       BWD_TRACE(6);
       if (i > 0) dq_epilogue(i - 1);
       BWD_TRACE(7);
-      if (i + 1 < n_t) compute(i + 1);
+      if (i + 1 < n_t) compute(i + 1, lse_i1, dlt_i1);
     }
     ptx::mbar_wait(dq_full, (n_t - 1) & 1);
     ptx::tc_fence_after();
