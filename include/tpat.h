@@ -1,6 +1,6 @@
 /*
  * tpat.h -- C-ABI of libtpat.so: the B200 (sm_100a) kernels behind the token-pruned ViT-B/16
- * forward of andylee-24/token-pruning-audio-transformer.
+ * forward AND fine-tune step (backward, optimizer) of andylee-24/token-pruning-audio-transformer.
  *
  * The reference has no native layer and no FFI (it is 100 % PyTorch); its "plugin
  * interface" for this path is the Python model API (audiomae/models_vit.py:502-527,

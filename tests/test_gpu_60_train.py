@@ -371,3 +371,63 @@ def test_fused_adamw_training_loop_decreases_loss_and_matches_torch_adamw():
         assert abs(a - b) < 2e-5
     for k, v in runs["torch"][1].items():
         assert nerr(runs["fused"][1][k], v) < 1e-4, k
+
+
+def test_eval_after_fused_adamw_steps_sees_the_new_weights_and_grads_accumulate():
+    """(1) FusedAdamW writes the flat parameter buffer from a kernel (no tensor version bump): the inference engine must
+    still repack -- an eval forward after training equals a fresh model loaded with the trained state-dict.
+    (2) autograd's contract: a second backward without zero_grad ACCUMULATES into p.grad."""
+    from tpat.optim import FusedAdamW
+    cfg = dict(GRAD_CONFIGS["audiomae_256_b2_train"])
+    sd, x, y = case_inputs(cfg)
+    model = build_train_model(cfg, sd, "fp32", drop_path_rate=0.0)
+    xd, yd = x.to(dev()), y.to(dev())
+    with torch.no_grad():
+        model.eval()
+        before = model(xd).clone()
+        model.train()
+    opt = FusedAdamW([{"params": [p for p in model.parameters() if p.requires_grad]}], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0,
+                     model=model)
+    F.binary_cross_entropy_with_logits(model(xd), yd).backward()
+    g1 = model.head.weight.grad.clone()
+    F.binary_cross_entropy_with_logits(model(xd), yd).backward()          # no zero_grad: accumulate
+    assert nerr(model.head.weight.grad, 2.0 * g1) < 1e-6
+    opt.zero_grad()
+    assert float(model.head.weight.grad.abs().max()) == 0.0
+    for _ in range(2):
+        loss = F.binary_cross_entropy_with_logits(model(xd), yd)
+        opt.zero_grad(); loss.backward(); opt.step()
+    model.eval()
+    with torch.no_grad():
+        after = model(xd)
+        fresh = build_train_model(cfg, {k: v.detach().cpu() for k, v in model.state_dict().items()}, "fp32").eval()
+        want = fresh(xd)
+    assert not torch.equal(after, before)
+    assert torch.equal(after, want)
+
+
+def test_training_other_sizes_and_fallback_paths():
+    """ViT-S (D = 384: the tcgen05 weight-gradient kernel does not cover 384-wide outputs -> transpose route) and a
+    batch of one clip, bf16 and fp32, against the oracle's autograd."""
+    from tpat import models_vit
+    T, C, dim, depth, heads = 128, 12, 384, 12, 6
+    sd = weights.make_audiomae_state_dict(C, T, seed=21, flavour="perturbed", depth=depth, dim=dim)
+    for B in (1, 3):
+        x = weights.make_spectrogram("audiomae", B, T, seed=22 + B)
+        y = (torch.rand(B, C, generator=torch.Generator().manual_seed(5)) < 0.2).float()
+        for precision, tol in (("fp32", 2e-5), ("bf16", 2.5e-2)):
+            m = models_vit.vit_small_patch16(num_classes=C, drop_path_rate=0.0, mean_pooling=True, mask_2d=True, target_length=T,
+                                             drop_loc=(2, 5), base_keep_rate=0.6, precision=precision)
+            m.patch_embed = models_vit.PatchEmbed((T, 128), 16, 1, dim)
+            m.pos_embed = nn.Parameter(torch.zeros(1, m.patch_embed.num_patches + 1, dim), requires_grad=False)
+            m.load_state_dict(sd, strict=True)
+            m = m.to(dev()).train()
+            F.binary_cross_entropy_with_logits(m(x.to(dev())), y.to(dev())).backward()
+            forced = {i: t.cpu() for i, t in enumerate(m.last_topk_idx) if t is not None}
+            _, _, o_grads = vo.loss_and_grads("audiomae", sd, x, y, None, (2, 5), 0.6, num_heads=heads, dtype=torch.float64,
+                                              forced_idx=forced if precision == "bf16" else None)
+            named = dict(m.named_parameters())
+            errs = {k: nerr(named[k].grad, v) for k, v in o_grads.items()}
+            k = max(errs, key=errs.get)
+            print(f"[train grads {precision}] vit_small B={B}: worst rel err {errs[k]:.2e} ({k})")
+            assert errs[k] < tol, (k, errs[k])

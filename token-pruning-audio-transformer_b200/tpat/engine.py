@@ -94,10 +94,15 @@ class EnginePool:
                 e = self._train[idx] = TrainEngine(*self._args)
             return e
 
-    def invalidate(self) -> None:
+    def invalidate_inference(self) -> None:
+        """Drop the inference engines' packed weights / bf16 copies / graphs (the weights changed without a version bump)."""
         with self._lock:
             for e in self._engines.values():
                 e.invalidate()
+
+    def invalidate(self) -> None:
+        self.invalidate_inference()
+        with self._lock:
             for e in self._train.values():
                 e.mark_updated()
 

@@ -81,6 +81,7 @@ class FusedAdamW(torch.optim.Optimizer):
               "tpat_adamw")
         engine.pending_grad_scale = 1.0
         engine.mark_updated(bf16_fresh=pb is not None)
+        self.model._engines.invalidate_inference()     # the kernel wrote the weights without bumping tensor versions
         return loss
 
     def zero_grad(self, set_to_none: bool = True):
