@@ -99,6 +99,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128;
         const int n0 = (tile % p.tiles_n) * TG_BN + (int)rank * 128;
+        // epilogue operand read with plain loads (fp32 residual of fc2, saved GELU derivative of the data-gradient GEMM): pull
+        // this CTA's 128 x 256 block into L2 now; the epilogue gets to it a whole main loop later (measured on the DGELU
+        // GEMM: 60 us of 160 were exposed HBM latency of those loads, tools/probes/epilogue_probe.py)
+        if (p.pf_l2) ptx::tma_prefetch_l2_2d(&tmap_r, (tile % p.tiles_n) * TG_BN, m0);
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full_leader = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
@@ -336,14 +340,29 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
       if (p.ln_part != nullptr && c_dtype == TPAT_BF16) return launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16, false, true>(ta, tw, ta, ta, p, st);
       TPAT_CHECK(p.ln_part == nullptr, "tpat_gemm_ln: the folded GEMM writes bf16");
       return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_BIAS_GELU, __nv_bfloat16>(ta, tw, ta, ta, p, st) : launch_tc2<TPAT_EPI_BIAS_GELU, float>(ta, tw, ta, ta, p, st);
-    case TPAT_EPI_DGELU:
-      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_DGELU, __nv_bfloat16>(ta, tw, ta, ta, p, st) : launch_tc2<TPAT_EPI_DGELU, float>(ta, tw, ta, ta, p, st);
+    case TPAT_EPI_DGELU: {
+      CUtensorMap tx = ta;
+      static const bool no_pf = getenv("TPAT_GEMM_NO_L2_PREFETCH") != nullptr;
+      if (!no_pf && N % 256 == 0 && (ep.ld_aux * dtype_size(c_dtype)) % 16 == 0) {
+        if (int rc = encode_tmap_2d(&tx, ep.aux, (int)dtype_size(c_dtype), (uint64_t)M, (uint64_t)N, (uint64_t)ep.ld_aux * dtype_size(c_dtype), 128, 256, false)) return rc;
+        p.pf_l2 = 1;
+      }
+      return c_dtype == TPAT_BF16 ? launch_tc2<TPAT_EPI_DGELU, __nv_bfloat16>(ta, tw, tx, ta, p, st) : launch_tc2<TPAT_EPI_DGELU, float>(ta, tw, tx, ta, p, st);
+    }
     case TPAT_EPI_BIAS_RESIDUAL: {
       // Long-K GEMMs (fc2, K = 3072) hide the register-path epilogue behind the main loop and prefer the fifth
       // pipeline stage; short-K ones (proj, K = 768) are bound by the residual read-modify-write and use the
       // TMA-fed epilogue (measured r01: proj 0.081 -> 0.064 ms, fc2 0.129 -> 0.140 ms with it).
-      if (K > 1536) return p.xb ? launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, false, true>(ta, tw, ta, ta, p, st)
-                                : launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, false>(ta, tw, ta, ta, p, st);
+      if (K > 1536) {
+        CUtensorMap tx = ta;
+        static const bool pf_res = getenv("TPAT_GEMM_RES_L2_PREFETCH") != nullptr;     // (A/B switch)
+        if (pf_res && N % 256 == 0) {
+          if (int rc = encode_tmap_2d(&tx, ep.residual, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldr * 4, 128, 256, false)) return rc;
+          p.pf_l2 = 1;
+        }
+        return p.xb ? launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, false, true>(ta, tw, tx, ta, p, st)
+                    : launch_tc2<TPAT_EPI_BIAS_RESIDUAL, float, false>(ta, tw, tx, ta, p, st);
+      }
       // fp32 residual in / C out as 32 x 32 blocks (128 B rows, 128B swizzle)
       CUtensorMap tr, tc;
       if (int rc = encode_tmap_2d(&tr, ep.residual, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldr * 4, 32, 32, true)) return rc;

@@ -38,6 +38,8 @@ struct TcGemmParams {
   void* dact_out; int ld_dact;
   const void* aux; int ld_aux;
   const float* row_scale; int rows_per_clip;
+  int pf_l2;        // 1: tmap_r covers the tensor the epilogue reads with plain loads (residual / saved GELU derivative);
+                    //    the TMA warp prefetches each tile's 128 x 256 block into L2 when it starts loading the tile
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
 };
 
@@ -112,18 +114,6 @@ template <int EW> struct TcEpiPrefetch {
   float4 colsum[NCH];   // consumer side of the LayerNorm fold
 };
 
-template <int EW>
-__device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmParams& p, int n0, int cg, int lane, TcEpiPrefetch<EW>& pf) {
-  const int jl = lane & 7;
-#pragma unroll
-  for (int ci = 0; ci < TcEpiPrefetch<EW>::NCH; ++ci) {
-    const int c = cg + TcEpiPrefetch<EW>::CSTRIDE * ci;
-    const int ncol = n0 + c * 32 + jl * 4;
-    pf.bias[ci] = (p.bias != nullptr && c < p.bn / 32 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    pf.colsum[ci] = (p.ln_colsum != nullptr && c < p.bn / 32 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
 // Epilogue of one accumulator for one epilogue warp.
 //   taddr_row : TMEM address of this warp's lane quarter at column 0 of the accumulator
 //   m0        : global row of this warp's first TMEM lane;  n0 : first global column of the tile
@@ -141,14 +131,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
   const int jl = lane & 7, rl = lane >> 3;   // coalesced phase: lane -> (16 B piece, row within a group of 4)
   bool released = false;
   // DGELU (bf16): the saved GELU derivatives of chunk ci + 1 are requested while chunk ci is processed (packed bf16,
-  // two register buffers): with K = 768 the epilogue has ~7000 cycles per tile and three chunks per warp, each of which
-  // would otherwise expose a full L2 / HBM round trip (measured: 704 TF/s before, see profiles/r02_ncu_full_summary.txt)
+  // two register buffers), and the TMA warp pulls the tile's block into L2 when it starts on the tile (pf_l2).  Measured
+  // (tools/probes/epilogue_probe.py, M = 32 832): loads inside the chunk 0.160 ms; this form 0.144 ms; all three chunks
+  // requested before the accumulator wait 0.166 ms (register pressure: spills); no loads at all 0.100 ms.
   constexpr bool kAuxQ = EPI == TPAT_EPI_DGELU && sizeof(OutT) == 2;
   uint2 auxq[2][8];
   auto load_aux = [&](int ci_, uint2 (&dst)[8]) {
     const int c_ = cg + CSTRIDE * ci_;
     const int n_ = n0 + c_ * 32;
+#ifdef TPAT_DBG_DGELU_NOAUX
+    if (false) {
+#else
     if (c_ < p.bn / 32 && n_ < p.N) {
+#endif
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int m = m0 + it * 4 + rl;
@@ -302,6 +297,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
         const int b = m / p.P, pp = m - b * p.P;
         orow = (size_t)b * (p.num_extra + p.P) + p.num_extra + pp;
       }
+#ifdef TPAT_DBG_EPI_NOSTORE
+      if (v[it].x == 123456.789f)      // (timing experiment: the stores are compiled in but never executed)
+#endif
       if constexpr (sizeof(OutT) == 4) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + ncol) = v[it];
       } else {

@@ -257,6 +257,10 @@ extern "C" int tpat_train_backward(const tpat_train_args* t, int stage_hi, int s
   // of the stage number: the head stage writes g[0], every block flips twice, so blocks always start and end on g[0].
   float* g = w.g[0];
   float* g_alt = w.g[1];
+  // gradients w.r.t. the LayerNorm outputs (dy) travel in the operand dtype on the tcgen05 path: half the bytes written by
+  // the two data-gradient GEMMs and read by the LayerNorm backward; TPAT_TRAIN_DY_FP32=1 keeps them fp32
+  static const bool dy_fp32 = getenv("TPAT_TRAIN_DY_FP32") != nullptr;
+  const int dyt = (impl == TPAT_IMPL_TC && !dy_fp32) ? TPAT_BF16 : TPAT_F32;
 
   for (int stage = stage_hi; stage >= stage_lo; --stage) {
     if (stage == a->depth + 1) {
@@ -285,10 +289,10 @@ extern "C" int tpat_train_backward(const tpat_train_args* t, int stage_hi, int s
       // fc1
       if (gr.fc1_b) if (int rc = tpat_colsum(w.dh, act, Dh, M2, Dh, w.parts, gr.fc1_b, stream)) return rc;
       if (int rc = wgrad(w.dh, k.y2, gr.fc1_w, M2, Dh, D, act, impl, w, stream)) return rc;
-      if (int rc = dgrad(w.dh, act, M2, Dh, D, wt.fc1_wt, w.dy, TPAT_F32, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
+      if (int rc = dgrad(w.dh, act, M2, Dh, D, wt.fc1_wt, w.dy, dyt, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
       // norm2 backward + residual (+ scatter): g [M2] -> g_alt [M]
       if (prune) if (int rc = tpat_inverse_index(a->topk_idx[i], w.inv, B, N - extra, a->keep[i], stream)) return rc;
-      if (int rc = tpat_row_bwd(w.dy, TPAT_F32, k.x_g, bw.ln2_g, g, g_alt, w.gb, act, t->drop_scale[i][0], prune ? w.inv : nullptr, w.parts,
+      if (int rc = tpat_row_bwd(w.dy, dyt, k.x_g, bw.ln2_g, g, g_alt, w.gb, act, t->drop_scale[i][0], prune ? w.inv : nullptr, w.parts,
                                 gr.ln2_g, gr.ln2_b, gr.proj_b, B, N2, N, extra, 0, D, a->ln_eps, stream)) return rc;
       { float* tmp = g; g = g_alt; g_alt = tmp; }
       // proj
@@ -299,9 +303,9 @@ extern "C" int tpat_train_backward(const tpat_train_args* t, int stage_hi, int s
       // qkv
       if (gr.qkv_b) if (int rc = tpat_colsum(w.dqkv, act, 3 * D, M, 3 * D, w.parts, gr.qkv_b, stream)) return rc;
       if (int rc = wgrad(w.dqkv, k.y1, gr.qkv_w, M, 3 * D, D, act, impl, w, stream)) return rc;
-      if (int rc = dgrad(w.dqkv, act, M, 3 * D, D, wt.qkv_wt, w.dy, TPAT_F32, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
+      if (int rc = dgrad(w.dqkv, act, M, 3 * D, D, wt.qkv_wt, w.dy, dyt, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
       // norm1 backward + residual: g [M] -> g_alt [M]; operand copy scaled for the previous block's fc2 (+ its bias gradient)
-      if (int rc = tpat_row_bwd(w.dy, TPAT_F32, k.x_in, bw.ln1_g, g, g_alt, i > 0 ? w.gb : nullptr, act, i > 0 ? t->drop_scale[i - 1][1] : nullptr,
+      if (int rc = tpat_row_bwd(w.dy, dyt, k.x_in, bw.ln1_g, g, g_alt, i > 0 ? w.gb : nullptr, act, i > 0 ? t->drop_scale[i - 1][1] : nullptr,
                                 nullptr, w.parts, gr.ln1_g, gr.ln1_b, i > 0 ? t->grads[i - 1].fc2_b : nullptr, B, N, N, extra, 0, D, a->ln_eps, stream)) return rc;
       { float* tmp = g; g = g_alt; g_alt = tmp; }
     } else {

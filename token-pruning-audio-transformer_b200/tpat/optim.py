@@ -85,9 +85,10 @@ class FusedAdamW(torch.optim.Optimizer):
         return loss
 
     def zero_grad(self, set_to_none: bool = True):
-        """One memset of the flat gradient buffer (the views stay attached)."""
-        if self._engine is not None and self._engine.flat_g is not None:
-            self._engine.flat_g.zero_()
+        """One memset of the flat gradient buffer (the ``p.grad`` views stay attached)."""
+        engine = self._engine or self.model._engines.get_train(self.model._device_of_params())
+        if engine.flat_g is not None:
+            engine.flat_g.zero_()
         else:
             super().zero_grad(set_to_none=set_to_none)
 
