@@ -114,6 +114,18 @@ template <int EW> struct TcEpiPrefetch {
   float4 colsum[NCH];   // consumer side of the LayerNorm fold
 };
 
+template <int EW>
+__device__ __forceinline__ void tc_epilogue_prefetch(const TcGemmParams& p, int n0, int cg, int lane, TcEpiPrefetch<EW>& pf) {
+  const int jl = lane & 7;
+#pragma unroll
+  for (int ci = 0; ci < TcEpiPrefetch<EW>::NCH; ++ci) {
+    const int c = cg + TcEpiPrefetch<EW>::CSTRIDE * ci;
+    const int ncol = n0 + c * 32 + jl * 4;
+    pf.bias[ci] = (p.bias != nullptr && c < p.bn / 32 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pf.colsum[ci] = (p.ln_colsum != nullptr && c < p.bn / 32 && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_colsum + ncol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // Epilogue of one accumulator for one epilogue warp.
 //   taddr_row : TMEM address of this warp's lane quarter at column 0 of the accumulator
 //   m0        : global row of this warp's first TMEM lane;  n0 : first global column of the tile
