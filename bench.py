@@ -332,12 +332,27 @@ def run_train(args, rank, world, local_rank):
     dev_x = [t.to(device) for t in host_x]
     dev_y = [t.to(device) for t in host_y]
 
-    def step(x, y):
+    def eager_step(x, y):
         loss = F.binary_cross_entropy_with_logits(model(x), y)
         opt.zero_grad()
         loss.backward()
         opt.step()
         return loss
+
+    graphed = None
+    if args.graph and world == 1:     # (capturing the NCCL buckets hung on this stack -- torch 2.11 / NCCL 2.28 --: eager when N > 1)
+        # the whole step (forward, loss, backward incl. its NCCL buckets, FusedAdamW) as one CUDA graph; inputs are
+        # copied into the graph's static buffers inside the timed region (device-to-device for `value`, H2D for `e2e`)
+        from tpat.train import GraphedTrainStep
+        try:
+            graphed = GraphedTrainStep(model, opt, lambda lg, t: F.binary_cross_entropy_with_logits(lg, t), dev_x[0], dev_y[0])
+        except Exception as exc:        # e.g. a collective that cannot be captured on this stack: report, run eagerly
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture of the train step failed ({type(exc).__name__}: {exc}); eager launches", file=sys.stderr)
+            graphed = None
+
+    def step(x, y):
+        return graphed(x, y) if graphed is not None else eager_step(x, y)
 
     def barrier():
         if world > 1:
@@ -364,11 +379,11 @@ def run_train(args, rank, world, local_rank):
         eng = model._engines.get_train(device)
         eng.grad_sync = False
         for i in range(2):
-            step(dev_x[i % NROT], dev_y[i % NROT])
+            eager_step(dev_x[i % NROT], dev_y[i % NROT])
         barrier()
         e0.record()
         for i in range(args.steps):
-            step(dev_x[i % NROT], dev_y[i % NROT])
+            eager_step(dev_x[i % NROT], dev_y[i % NROT])
         e1.record()
         barrier()
         ms_nocomm = e0.elapsed_time(e1)
@@ -379,9 +394,15 @@ def run_train(args, rank, world, local_rank):
 
     def e2e_loop(n):
         for i in range(n):
-            sx.copy_(host_x[i % NROT], non_blocking=True)
-            sy.copy_(host_y[i % NROT], non_blocking=True)
-            out_loss.copy_(step(sx, sy).detach().reshape(1), non_blocking=True)
+            if graphed is not None:          # H2D straight into the graph's static input buffers
+                graphed.x.copy_(host_x[i % NROT], non_blocking=True)
+                graphed.y.copy_(host_y[i % NROT], non_blocking=True)
+                loss_i = graphed(None, None, copy=False)
+            else:
+                sx.copy_(host_x[i % NROT], non_blocking=True)
+                sy.copy_(host_y[i % NROT], non_blocking=True)
+                loss_i = eager_step(sx, sy)
+            out_loss.copy_(loss_i.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     e2e_s = float("nan")
@@ -417,7 +438,7 @@ def run_train(args, rank, world, local_rank):
                        "l2": f"inputs rotate over {NROT} batches; ~8 GB of saved activations are rewritten every step (> 126 MB L2)"},
             "e2e": {"value": round(total_clips / e2e_s, 1), "unit": UNIT,
                     "h2d_bytes_per_step": B * T_FRAMES * F_BINS * 4 + B * NUM_CLASSES * 4, "d2h_bytes_per_step": 4},
-            "loss_last_step": last_loss, "clocks": clocks,
+            "loss_last_step": last_loss, "clocks": clocks, "cuda_graph": graphed is not None,
             "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(tf / peak, 4),
                          "traffic": None, "kernel": "whole fine-tune step: 3 x %.2f GFLOP/clip algorithmic (forward, dX, dW)" % (fl / 3e9),
                          "peak_source": f"{peaks['source']} {'burst' if burst else 'sustained'} bf16 peak"},

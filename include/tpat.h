@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 8
+#define TPAT_VERSION 9
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -391,10 +391,13 @@ int tpat_pool_norm_bwd(const float* x, const float* dpooled, float* dx, const fl
  * groups of util/lr_decay.py:15-75): p *= 1 - lr_g wd_g; m, v moments; p -= lr_g / bc1 * m / (sqrt(v) / sqrt(bc2) + eps),
  * g = grad * grad_scale (1 / world size after a SUM all-reduce).  chunks [n_chunks][4] int32 = (offset, length, group, 0),
  * groups [n_groups][2] fp32 = (lr scale, weight decay).  p_bf16 (optional): bf16 copy of p refreshed in the same pass.
+ * step_dev (optional): the step count t of the bias corrections 1 - beta^t lives in device memory (tpat_counter_inc
+ * advances it), so that a CUDA graph of the whole step can be replayed; NULL: `step` (>= 1) is used.
  */
 int tpat_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunks, int n_chunks,
-               const float* groups, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-               tpat_stream_t stream);
+               const float* groups, float lr, float beta1, float beta2, float eps, int step, const int32_t* step_dev,
+               float grad_scale, tpat_stream_t stream);
+int tpat_counter_inc(int32_t* counter, tpat_stream_t stream);
 
 typedef struct {
   float* ln1_g; float* ln1_b; float* qkv_w; float* qkv_b; float* proj_w; float* proj_b;

@@ -431,3 +431,42 @@ def test_training_other_sizes_and_fallback_paths():
             k = max(errs, key=errs.get)
             print(f"[train grads {precision}] vit_small B={B}: worst rel err {errs[k]:.2e} ({k})")
             assert errs[k] < tol, (k, errs[k])
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """GraphedTrainStep: the captured step (forward + loss + backward + FusedAdamW, device-side step counter) replays to the
+    same losses and weights as the eager loop (fp32 mode, no DropPath -> deterministic)."""
+    from tpat.lr_decay import param_groups_lrd
+    from tpat.optim import FusedAdamW
+    from tpat.train import GraphedTrainStep
+    cfg = dict(GRAD_CONFIGS["audiomae_256_b2_train"])
+    sd, x, y = case_inputs(cfg)
+    xs = [x.to(dev()), (x * 0.9 + 0.05).to(dev()), (x * 1.1).to(dev())]
+    yd = y.to(dev())
+    crit = lambda lg, t: F.binary_cross_entropy_with_logits(lg, t)
+    runs = {}
+    for kind in ("eager", "graph"):
+        model = build_train_model(cfg, sd, "fp32", drop_path_rate=0.0)
+        groups = param_groups_lrd(model, 0.05, no_weight_decay_list=model.no_weight_decay(), layer_decay=0.75)
+        opt = FusedAdamW(groups, lr=1e-3, betas=(0.9, 0.95), model=model)
+        for gq in opt.param_groups:
+            gq["lr"] = 1e-3 * gq["lr_scale"]
+        losses = []
+        if kind == "eager":
+            for i in range(3 + 3):                       # the graph run spends 3 eager warm-up steps on xs[0]; the capture
+                xi = xs[0] if i < 3 else xs[(i - 3) % 3]  # pass itself executes nothing
+                loss = crit(model(xi), yd)
+                opt.zero_grad(); loss.backward(); opt.step()
+                losses.append(loss.item())
+            losses = losses[3:]
+        else:
+            step = GraphedTrainStep(model, opt, crit, xs[0], yd, warmup=3)
+            for i in range(3):
+                losses.append(step(xs[i % 3], yd).item())
+            assert opt.state_dict()["step"] == 6     # device-side counter: 3 warm-up steps + 3 replays
+        runs[kind] = (losses, {k: v.detach().clone() for k, v in model.named_parameters()})
+    print(f"[graphed step] losses eager {runs['eager'][0]} graph {runs['graph'][0]}")
+    for a, b in zip(runs["eager"][0], runs["graph"][0]):
+        assert abs(a - b) < 1e-5
+    for k, v in runs["eager"][1].items():
+        assert nerr(runs["graph"][1][k], v) < 1e-5, k

@@ -38,6 +38,7 @@ struct AdamWParams {
   const int4* chunks;        // (offset, length, group, unused)
   const float2* groups;      // (lr scale, weight decay)
   float lr, beta1, beta2, eps, bc1, bc2, grad_scale;
+  const int* step_dev;       // optional: step counter in device memory (CUDA-graph replays: the host cannot pass a new step)
 };
 
 __global__ void __launch_bounds__(256)
@@ -45,7 +46,13 @@ adamw_kernel(const AdamWParams a) {
   const int4 ch = __ldg(a.chunks + blockIdx.x);
   const float2 gr = __ldg(a.groups + ch.z);
   const float lr = a.lr * gr.x, wd = gr.y;
-  const float step = lr / a.bc1, inv_sqrt_bc2 = rsqrtf(a.bc2);
+  float bc1 = a.bc1, bc2 = a.bc2;
+  if (a.step_dev != nullptr) {
+    const float t = (float)__ldg(a.step_dev);
+    bc1 = 1.0f - powf(a.beta1, t);
+    bc2 = 1.0f - powf(a.beta2, t);
+  }
+  const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
   const size_t base = (size_t)(unsigned)ch.x;
   for (int i = threadIdx.x; i < ch.y; i += blockDim.x) {
     const size_t k = base + i;
@@ -59,6 +66,8 @@ adamw_kernel(const AdamWParams a) {
     if (a.p_bf16) a.p_bf16[k] = __float2bfloat16_rn(p);
   }
 }
+
+__global__ void counter_inc_kernel(int* ctr) { *ctr += 1; }
 
 // out[i] (+)= sum_b x[b * n + i]  (gradient of a parameter broadcast over the clips: cls / dist token, pos_embed)
 __global__ void __launch_bounds__(256)
@@ -91,14 +100,23 @@ extern "C" int tpat_transpose(const void* src, int src_dtype, int ld_src, void* 
   return 0;
 }
 
-extern "C" int tpat_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunks, int n_chunks,
-                          const float* groups, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
-                          tpat_stream_t stream) {
+extern "C" int tpat_counter_inc(int32_t* counter, tpat_stream_t stream) {
   using namespace tpat;
-  TPAT_CHECK(p && g && m && v && chunks && groups && n_chunks >= 0 && step >= 1, "tpat_adamw: bad arguments");
+  TPAT_CHECK(counter != nullptr, "tpat_counter_inc: null pointer");
+  TPAT_CUDA(launch_kernel(counter_inc_kernel, dim3(1), dim3(1), 0, as_stream(stream), counter));
+  TPAT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tpat_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int32_t* chunks, int n_chunks,
+                          const float* groups, float lr, float beta1, float beta2, float eps, int step, const int32_t* step_dev,
+                          float grad_scale, tpat_stream_t stream) {
+  using namespace tpat;
+  TPAT_CHECK(p && g && m && v && chunks && groups && n_chunks >= 0 && (step >= 1 || step_dev != nullptr), "tpat_adamw: bad arguments");
   if (n_chunks == 0) return 0;
+  const float st = (float)(step >= 1 ? step : 1);
   AdamWParams a{p, g, m, v, (__nv_bfloat16*)p_bf16, reinterpret_cast<const int4*>(chunks), reinterpret_cast<const float2*>(groups),
-                lr, beta1, beta2, eps, 1.0f - powf(beta1, (float)step), 1.0f - powf(beta2, (float)step), grad_scale};
+                lr, beta1, beta2, eps, 1.0f - powf(beta1, st), 1.0f - powf(beta2, st), grad_scale, step_dev};
   TPAT_CUDA(launch_kernel(adamw_kernel, dim3(n_chunks), dim3(256), 0, as_stream(stream), a));
   TPAT_LAUNCH_CHECK();
   return 0;

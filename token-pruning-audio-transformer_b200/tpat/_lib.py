@@ -13,7 +13,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("TPAT_LIB_PATH") or os.path.join(_PKG_ROOT, "lib", "libtpat.so")   # override: kernel experiments
 
 TPAT_MAX_DEPTH = 32
-TPAT_VERSION = 8          # must equal TPAT_VERSION in include/tpat.h (checked at load)
+TPAT_VERSION = 9          # must equal TPAT_VERSION in include/tpat.h (checked at load)
 F32, BF16, BF16_SPLIT3 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_POS, EPI_DGELU = 0, 1, 2, 3, 4
 IMPL_SIMT, IMPL_TC = 0, 1
@@ -135,7 +135,8 @@ SIGNATURES = {
     "tpat_pool_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tpat_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_float,
-                           c_float, c_float, c_int, c_float, c_void_p]),
+                           c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
+    "tpat_counter_inc": (c_int, [c_void_p, c_void_p]),
     "tpat_sizeof_train_args": (c_size_t, []),
     "tpat_train_saved_bytes": (c_size_t, [POINTER(TrainArgs)]),
     "tpat_train_bwd_workspace_bytes": (c_size_t, [POINTER(TrainArgs)]),

@@ -353,10 +353,10 @@ def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], o
     return (out, pre) if want_dact else out
 
 
-def adamw(p, g, m, v, p_bf16, chunks, groups, lr, beta1, beta2, eps, step, grad_scale=1.0):
+def adamw(p, g, m, v, p_bf16, chunks, groups, lr, beta1, beta2, eps, step, grad_scale=1.0, step_dev=None):
     check(lib.tpat_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_bf16), chunks.data_ptr(), chunks.shape[0],
-                         groups.data_ptr(), float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_scale), _stream()),
-          "tpat_adamw")
+                         groups.data_ptr(), float(lr), float(beta1), float(beta2), float(eps), int(step), _ptr(step_dev),
+                         float(grad_scale), _stream()), "tpat_adamw")
 
 
 def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -24,6 +24,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.model = model
         self._engine = None
         self._step = 0
+        self._step_dev = None            # device-side step counter (CUDA-graph replays of the whole step)
         self._m = self._v = None
         self._chunks = self._groups_dev = self._groups_host = None
         self._n_chunks = 0
@@ -60,8 +61,18 @@ class FusedAdamW(torch.optim.Optimizer):
             self._v = torch.zeros_like(engine.flat_p)
             self._step = 0
         self._engine, self._flat_ptr = engine, engine.flat_p.data_ptr()
+        self._step_dev = torch.full((1,), self._step, dtype=torch.int32, device=dev)
         engine.fused_grad_scale = True
         return engine
+
+    def sync_hyperparams(self) -> None:
+        """param_groups -> the pinned (lr, weight decay) table the kernel's group table is copied from.  A CUDA graph of the
+        step replays that copy, so a scheduler's new ``group["lr"]`` takes effect if this is called before the replay."""
+        if self._groups_host is None:
+            self._bind()
+        for gi, g in enumerate(self.param_groups):                 # absolute per-group lr (what lr schedulers write)
+            self._groups_host[gi, 0] = float(g["lr"])
+            self._groups_host[gi, 1] = float(g["weight_decay"])
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -70,15 +81,15 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step += 1
         beta1, beta2 = self.param_groups[0]["betas"]
         eps = self.param_groups[0]["eps"]
-        for gi, g in enumerate(self.param_groups):                 # absolute per-group lr (what lr schedulers write)
-            self._groups_host[gi, 0] = float(g["lr"])
-            self._groups_host[gi, 1] = float(g["weight_decay"])
+        self.sync_hyperparams()
         self._groups_dev.copy_(self._groups_host, non_blocking=True)
         pb = engine.flat_pb.data_ptr() if engine.flat_pb is not None else None
+        stream = torch.cuda.current_stream().cuda_stream
+        # the step count of the bias corrections lives on the device (one-thread kernel), so that a captured step replays
+        check(lib.tpat_counter_inc(self._step_dev.data_ptr(), stream), "tpat_counter_inc")
         check(lib.tpat_adamw(engine.flat_p.data_ptr(), engine.flat_g.data_ptr(), self._m.data_ptr(), self._v.data_ptr(), pb,
                              self._chunks.data_ptr(), self._n_chunks, self._groups_dev.data_ptr(), 1.0, float(beta1), float(beta2),
-                             float(eps), self._step, float(engine.pending_grad_scale), torch.cuda.current_stream().cuda_stream),
-              "tpat_adamw")
+                             float(eps), 0, self._step_dev.data_ptr(), float(engine.pending_grad_scale), stream), "tpat_adamw")
         engine.pending_grad_scale = 1.0
         engine.mark_updated(bf16_fresh=pb is not None)
         self.model._engines.invalidate_inference()     # the kernel wrote the weights without bumping tensor versions
@@ -93,12 +104,14 @@ class FusedAdamW(torch.optim.Optimizer):
             super().zero_grad(set_to_none=set_to_none)
 
     def state_dict(self):
-        return {"step": self._step, "m": self._m, "v": self._v,
+        step = int(self._step_dev.item()) if self._step_dev is not None else self._step
+        return {"step": step, "m": self._m, "v": self._v,
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, sd):
         self._bind()
         self._step = int(sd["step"])
+        self._step_dev.fill_(self._step)
         self._m.copy_(sd["m"]); self._v.copy_(sd["v"])
         for g, s in zip(self.param_groups, sd["param_groups"]):
             g.update(s)

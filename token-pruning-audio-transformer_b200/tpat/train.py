@@ -349,3 +349,59 @@ def drop_path_scales(rates: Sequence[float], B: int, device, timm_04_style: bool
             pair.append(t.reshape(B).contiguous())
         out.append(tuple(pair))
     return out
+
+
+class GraphedTrainStep:
+    """The whole fine-tune step -- forward, loss, backward (with its NCCL gradient buckets), FusedAdamW -- as ONE CUDA
+    graph: ~440 kernel launches and all the Python in between become a single ``replay()``.
+
+        step = GraphedTrainStep(model, optimizer, criterion, sample_x, sample_y, keep_rate_list=None)
+        for x, y in loader:
+            lr_sched.adjust_learning_rate(optimizer, ...)      # group["lr"] is re-read (pinned buffer) at every replay
+            loss = step(x, y)                                  # device tensor, valid until the next call
+
+    What is baked in at capture time: shapes, the pruning schedule (``keep_rate_list``; capture one instance per
+    schedule, as the reference's per-epoch keep-rate schedule changes it), mask probabilities, DropPath RATES (the masks
+    themselves are redrawn by the captured RNG kernels at every replay).  Requires ``FusedAdamW`` (its step counter lives
+    on the device).  Single-process only for now: with torch.distributed initialised the constructor raises -- capturing
+    the NCCL gradient buckets hung on this stack (torch 2.11 / NCCL 2.28.9, two B200s), so multi-GPU steps run eagerly."""
+
+    def __init__(self, model, optimizer, criterion, sample_x: torch.Tensor, sample_y: torch.Tensor, keep_rate_list=None,
+                 warmup: int = 3, **forward_kwargs):
+        from .optim import FusedAdamW
+        if not isinstance(optimizer, FusedAdamW):
+            raise TypeError("GraphedTrainStep needs tpat.optim.FusedAdamW (device-side step counter, flat buffers)")
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise RuntimeError("GraphedTrainStep: capturing the NCCL gradient all-reduce is not supported; run the step eagerly")
+        self.model, self.opt, self.criterion = model, optimizer, criterion
+        self.kw = dict(keep_rate_list=keep_rate_list, **forward_kwargs)
+        self.x = sample_x.detach().clone()
+        self.y = sample_y.detach().clone()
+        side = torch.cuda.Stream(device=self.x.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up on a side stream (torch's capture recipe)
+            for _ in range(max(1, warmup)):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager()
+        self.replays = 0
+
+    def _eager(self):
+        loss = self.criterion(self.model(self.x, **self.kw), self.y)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor, copy: bool = True) -> torch.Tensor:
+        """One training step on (x, y).  ``copy=False``: the caller has already written into ``self.x`` / ``self.y``."""
+        if copy:
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y, non_blocking=True)
+        self.opt.sync_hyperparams()           # the captured H2D copy of the (lr, weight decay) table reads the pinned buffer now
+        self.graph.replay()
+        self.replays += 1
+        return self.loss
