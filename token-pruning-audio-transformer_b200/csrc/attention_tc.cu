@@ -512,6 +512,13 @@ extern "C" int tpat_debug_attn_trace(long long* host_out) {   // debug builds on
 
 int attention_tc_qtiles(int N) { return (N + AT_BM - 1) / AT_BM; }
 
+// attention_tc3.cu: two query tiles per CTA, one thread per row, 128-key blocks (tiles that feed no importance score)
+int attention_tc3(const void* qkv, void* out, int B, int N, int H, float scale, int qt_offset, float* lse, cudaStream_t st);
+static bool use_v3() {
+  const char* e = getenv("TPAT_ATTN_V3");      // read per call so that tests can A/B both kernels
+  return e != nullptr && e[0] == '1';
+}
+
 template <bool TWO_PASS, bool SPLIT = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tv, const CUtensorMap& to,
                        const AttnTcParams& p, dim3 grid, size_t smem, cudaStream_t st) {
@@ -575,9 +582,11 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
     if (qk_planes) { if (int rc = launch_attn<true, true>(tm_qs, tm_ks, tm_kv, tm_o, p, dim3(1, H, B), base_smem + split_extra, st)) return rc; }
     else if (int rc = launch_attn<true>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(1, H, B), base_smem, st)) return rc;
     if (p.n_qt == 1) return 0;
+    if (use_v3()) return attention_tc3(qkv, out, B, N, H, scale, 1, lse, st);
     p.qt_offset = 1;
     return launch_attn<false>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt - 1, H, B), base_smem, st);
   }
+  if (use_v3()) return attention_tc3(qkv, out, B, N, H, scale, 0, lse, st);
   return launch_attn<false>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem, st);
 }
 
