@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 9
+#define TPAT_VERSION 10
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -329,6 +329,9 @@ typedef struct tpat_gemm_extra {
   const void* aux; int ld_aux;                   /* TPAT_EPI_DGELU: that saved derivative (dtype of C); C = (A W^T) * aux           */
   const float* row_scale; int rows_per_clip;     /* TPAT_EPI_BIAS_RESIDUAL: C = R + row_scale[m / rows_per_clip] * (A W^T + b):
                                                     timm DropPath's per-sample scale 0 | 1 / keep_prob (models_vit.py:149,198,205)   */
+  int w_kn;                                      /* 1: W is stored [K, N] row-major (C = A W): the data gradient dX = dY W reads the
+                                                    forward weight [out, in] as it is, as an MN-major tcgen05 B operand -- no
+                                                    transposed copy.  tcgen05 path only (N % 8 == 0)                                   */
 } tpat_gemm_extra;
 int tpat_gemm_train(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias, void* C, int c_dtype,
                     int ldc, const float* residual, int ldr, int M, int N, int K, int epilogue, int impl,

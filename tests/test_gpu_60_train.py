@@ -96,6 +96,9 @@ def test_colsum_and_batch_sum():
     x = torch.randn(1000, 3072, device=dev())
     assert rel_err(ops.colsum(x), x.double().sum(0)) < 1e-5
     assert rel_err(ops.colsum(x.to(torch.bfloat16)), x.to(torch.bfloat16).double().sum(0)) < 1e-5
+    for M, C in ((64 * 178 + 3, 2304), (17, 3072), (4000, 772)):         # 16-byte-load kernel (C % 8 == 0) and the narrow one
+        xb = torch.randn(M, C, device=dev()).to(torch.bfloat16)
+        assert rel_err(ops.colsum(xb), xb.double().sum(0)) < 1e-5
     y = torch.randn(7, 527, device=dev())
     assert rel_err(ops.batch_sum(y), y.double().sum(0)) < 1e-6
 
@@ -191,6 +194,29 @@ def test_gemm_train_epilogues(impl_name):
     want = res.double() + scale.double().repeat_interleave(n).view(M, 1) * (hid.double() @ w2.double().T + b2.double())
     assert rel_err(out, want) < tol
     assert torch.equal(out[:n], res[:n])                                # a dropped clip keeps its residual bit for bit
+
+
+@pytest.mark.parametrize("M,Nout,Nin", [(64 * 178, 3072, 768), (5000, 768, 3072), (3000, 768, 3072), (3000, 3072, 768), (700, 2304, 768),
+                                        (300, 768, 768), (130, 768, 320)])
+def test_gemm_dgrad_on_forward_weight(M, Nout, Nin):
+    """dX = dY W with W = the forward weight [out, in] read as an MN-major tcgen05 B operand (tpat_gemm_extra.w_kn):
+    bit-identical to the GEMM on the transposed copy, for the CTA-pair kernel and the 1-CTA kernel's 256 / 128 / 64 tiles."""
+    from tpat import ops, _lib
+    torch.manual_seed(M)
+    dy = (torch.randn(M, Nout, device=dev()) * 0.1).to(torch.bfloat16)
+    w = (torch.randn(Nout, Nin, device=dev()) * 0.05).to(torch.bfloat16)
+    for out_dtype in (torch.bfloat16, torch.float32):
+        got = ops.gemm_train(dy, w, None, out_dtype, _lib.EPI_BIAS, _lib.IMPL_TC, w_kn=True)
+        ref = ops.gemm_train(dy, w.T.contiguous(), None, out_dtype, _lib.EPI_BIAS, _lib.IMPL_TC)
+        assert torch.equal(got, ref)
+        assert nerr(got.float(), dy.double() @ w.double()) < (1e-2 if out_dtype == torch.bfloat16 else 2e-5)
+    if Nout == 768 and Nin == 3072:      # GELU-backward epilogue on top
+        aux = torch.rand(M, Nin, device=dev()).to(torch.bfloat16)
+        got = ops.gemm_train(dy, w, None, torch.bfloat16, _lib.EPI_DGELU, _lib.IMPL_TC, aux=aux, w_kn=True)
+        ref = ops.gemm_train(dy, w.T.contiguous(), None, torch.bfloat16, _lib.EPI_DGELU, _lib.IMPL_TC, aux=aux)
+        assert torch.equal(got, ref)
+    with pytest.raises(RuntimeError):
+        ops.gemm_train(dy.float(), w.float(), None, torch.float32, _lib.EPI_BIAS, _lib.IMPL_SIMT, w_kn=True)
 
 
 @pytest.mark.parametrize("K,Mo,No", [(513 * 3, 768, 768), (1000, 2304, 768), (4104, 768, 3072), (70, 256, 256), (32832, 3072, 768)])

@@ -55,6 +55,46 @@ attn_delta_kernel(const T* __restrict__ o, const T* __restrict__ d_o, float* __r
   }
 }
 
+// bf16 flavour with 16-byte loads: lane = 8 elements of one (row, head), one uint4 of O and one of dO each; two
+// (row, head) pairs per thread in flight
+__global__ void __launch_bounds__(256)
+attn_delta8_kernel(const uint4* __restrict__ o, const uint4* __restrict__ d_o, float* __restrict__ delta, int B, int N, int H) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t total8 = (size_t)B * N * H * 8;          // uint4 elements: [row][h][8]
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  auto dot8 = [](const uint4& a, const uint4& g) {
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s0 = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), s0);
+      s1 = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(gw[e] & 0xffff0000u), s1);
+    }
+    return s0 + s1;
+  };
+  auto finish = [&](float s, size_t j) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((j & 7) == 0 && j < total8) {
+      const size_t i = j >> 3;
+      const int h = (int)(i % H);
+      const size_t row = i / H;
+      delta[((row / N) * H + h) * (size_t)N + row % N] = s;
+    }
+  };
+  // the loop bound is warp-uniform (the shuffles need all 32 lanes); lanes past the end load nothing
+  const uint32_t lane = threadIdx.x & 31;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j - lane < total8; j += 2 * stride) {
+    const size_t j2 = j + stride;
+    const bool has1 = j < total8, has2 = j2 < total8;
+    uint4 a = make_uint4(0, 0, 0, 0), g = a, a2 = a, g2 = a;
+    if (has1) { a = __ldg(o + j); g = __ldg(d_o + j); }
+    if (has2) { a2 = __ldg(o + j2); g2 = __ldg(d_o + j2); }
+    finish(dot8(a, g), has1 ? j : total8);
+    finish(dot8(a2, g2), has2 ? j2 : total8);
+  }
+}
+
 template <typename T, bool DKDV>
 __global__ void __launch_bounds__(256)
 attn_bwd_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ d_o, const float* __restrict__ lse,
@@ -211,9 +251,8 @@ namespace tpat {
 // delta = rowsum(dO o O) for the tcgen05 backward (same kernel as the CUDA-core path)
 int attention_bwd_delta_bf16(const void* out, const void* d_out, float* delta, int B, int N, int H, cudaStream_t st) {
   const size_t total = (size_t)B * N * H;
-  const int dgrid = (int)((total * 8 + 255) / 256 < 8192 ? (total * 8 + 255) / 256 : 8192);
-  TPAT_CUDA(launch_kernel(attn_delta_kernel<__nv_bfloat16>, dim3(dgrid), dim3(256), 0, st, (const __nv_bfloat16*)out,
-                          (const __nv_bfloat16*)d_out, delta, B, N, H));
+  const int dgrid = (int)((total * 4 + 255) / 256 < 8192 ? (total * 4 + 255) / 256 : 8192);     // two (row, head) pairs per 8 lanes
+  TPAT_CUDA(launch_kernel(attn_delta8_kernel, dim3(dgrid), dim3(256), 0, st, (const uint4*)out, (const uint4*)d_out, delta, B, N, H));
   TPAT_LAUNCH_CHECK();
   return 0;
 }

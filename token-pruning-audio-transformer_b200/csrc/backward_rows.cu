@@ -191,6 +191,54 @@ colsum_kernel(const T* __restrict__ x, int ld, int M, int C, float* __restrict__
   }
 }
 
+// the same for bf16 rows with C % 8 == 0: 16-byte loads (a warp instruction covers 512 contiguous bytes, as in the
+// LayerNorm kernels), blockDim.x / 2 column groups of 8 x 2 row phases, eight rows in flight per thread
+__global__ void __launch_bounds__(256)
+colsum8_kernel(const __nv_bfloat16* __restrict__ x, int ld, int M, int C, float* __restrict__ partials) {
+  __shared__ float red[128][9];
+  pdl_trigger();
+  pdl_wait();
+  const int gpb = blockDim.x >> 1;
+  const int cgp = threadIdx.x % gpb, ph = threadIdx.x / gpb;
+  const int c8 = blockIdx.x * gpb + cgp;
+  const int per = (M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(M, r0 + per);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  auto add = [&](const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {               // bf16 -> fp32 is a 16-bit shift
+      acc[2 * e] += __uint_as_float(w[e] << 16);
+      acc[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+    }
+  };
+  if (c8 < C / 8) {
+    const uint4* base = reinterpret_cast<const uint4*>(x) + c8;
+    const size_t ld16 = (size_t)ld / 8;
+    int r = r0 + ph;
+    for (; r + 14 < r1; r += 16) {
+      uint4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = __ldg(base + (size_t)(r + 2 * k) * ld16);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) add(u[k]);
+    }
+    for (; r < r1; r += 2) add(__ldg(base + (size_t)r * ld16));
+  }
+  if (ph == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[cgp][e] = acc[e];
+  }
+  __syncthreads();
+  if (ph == 0 && c8 < C / 8) {
+    float4* dst = reinterpret_cast<float4*>(partials + (size_t)blockIdx.y * C) + 2 * c8;
+    dst[0] = make_float4(acc[0] + red[cgp][0], acc[1] + red[cgp][1], acc[2] + red[cgp][2], acc[3] + red[cgp][3]);
+    dst[1] = make_float4(acc[4] + red[cgp][4], acc[5] + red[cgp][5], acc[6] + red[cgp][6], acc[7] + red[cgp][7]);
+  }
+}
+
 // dst_q[c] += sum_p partials[p][q][c], q < nq (<= 4), in a fixed order.  CTA = 32 columns x 16 part-slices: slice s sums
 // parts s, s + 16, ... (four independent accumulators), the 16 slice sums are combined through shared memory in order --
 // the loop over up to 296 parts is 5 dependent rounds instead of 74.
@@ -406,7 +454,10 @@ extern "C" int tpat_colsum(const void* x, int dtype, int ld, int M, int C, float
   TPAT_CHECK(x && partials_ws && dst, "tpat_colsum: null pointer");
   TPAT_CHECK(M >= 0 && C > 0 && C % 4 == 0 && C <= 4096 && ld >= C && aligned16(x) && (ld * dtype_size(dtype)) % 8 == 0, "tpat_colsum: need C %% 4 == 0, C <= 4096, aligned rows");
   if (M == 0) return 0;
-  const int cblocks = (C / 4 + 127) / 128;
+  const bool wide = dtype != TPAT_F32 && C % 8 == 0 && ld % 8 == 0;
+  const int groups = wide ? C / 8 : C / 4;
+  const int cblocks = (groups + 127) / 128;
+  const int gpb = wide ? ((groups + cblocks - 1) / cblocks + 31) / 32 * 32 : 128;   // balanced column blocks (C = 2304: 3 x 96)
   int grid = (M + 63) / 64;                                 // row slabs
   // up to ~8 CTAs per SM in flight (this kernel is pure streaming: occupancy = bytes in flight); the partials buffer holds
   // tpat_bwd_partials_floats / C >= 1184 * 4096 / C slabs
@@ -415,6 +466,7 @@ extern "C" int tpat_colsum(const void* x, int dtype, int ld, int M, int C, float
   if (grid > max_slabs) grid = max_slabs;
   cudaStream_t st = as_stream(stream);
   if (dtype == TPAT_F32) TPAT_CUDA(launch_kernel(colsum_kernel<float>, dim3(cblocks, grid), dim3(256), 0, st, (const float*)x, ld, M, C, partials_ws));
+  else if (wide) TPAT_CUDA(launch_kernel(colsum8_kernel, dim3(cblocks, grid), dim3(2 * gpb), 0, st, (const __nv_bfloat16*)x, ld, M, C, partials_ws));
   else TPAT_CUDA(launch_kernel(colsum_kernel<__nv_bfloat16>, dim3(cblocks, grid), dim3(256), 0, st, (const __nv_bfloat16*)x, ld, M, C, partials_ws));
   TPAT_LAUNCH_CHECK();
   return finish_partials(partials_ws, grid, 1, C, dst, nullptr, nullptr, nullptr, st);

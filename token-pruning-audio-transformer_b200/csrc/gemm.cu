@@ -57,6 +57,11 @@ static int gemm_entry(const void* A, int a_dtype, int lda, const void* W, int w_
       TPAT_CHECK(epilogue == TPAT_EPI_BIAS_RESIDUAL && extra->rows_per_clip > 0, "tpat_gemm_train: row_scale needs the residual epilogue and rows_per_clip > 0");
       ep.row_scale = extra->row_scale; ep.rows_per_clip = extra->rows_per_clip;
     }
+    if (extra->w_kn) {
+      TPAT_CHECK(impl == TPAT_IMPL_TC && N % 8 == 0 && aligned16(W) && fold == nullptr,
+                 "tpat_gemm_train: w_kn (W stored [K, N]) exists on the tcgen05 path only and needs N %% 8 == 0");
+      ep.w_kn = 1;
+    }
   }
   if (fold != nullptr && (fold->xb != nullptr || fold->ln_part != nullptr)) {
     TPAT_CHECK(impl == TPAT_IMPL_TC, "tpat_gemm_ln: the LayerNorm fold exists on the tcgen05 path only");

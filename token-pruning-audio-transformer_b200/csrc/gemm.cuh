@@ -19,6 +19,7 @@ struct EpiParams {
   void* dact_out = nullptr; int ld_dact = 0;            // BIAS_GELU: also store gelu'(acc + bias), dtype of C
   const void* aux = nullptr; int ld_aux = 0;          // DGELU: the saved gelu'(h) (dtype of C): C = acc * aux
   const float* row_scale = nullptr; int rows_per_clip = 0;   // BIAS_RESIDUAL: C = R + row_scale[m / rows_per_clip] * (acc + bias)  (DropPath)
+  int w_kn = 0;                                         // W stored [K, N] (MN-major B operand)
 };
 
 // CUDA-core fp32-FMA path (gemm_simt.cu)

@@ -212,7 +212,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], TG_A_BYTES + p.bn * TG_BK * 2);
           ptx::tma_load_2d(smem_a + stage * TG_A_BYTES, &tmap_a, &full_bar[stage], kb * TG_BK, m0);
-          ptx::tma_load_2d(smem_b + stage * TG_B_BYTES, &tmap_w, &full_bar[stage], kb * TG_BK, n0);
+          if (p.w_kn) {        // W[K][N]: bn / 64 boxes of 64 k-rows x 64 n-columns, 8 KB apart
+            for (int j = 0; j < p.bn / 64; ++j)
+              ptx::tma_load_2d(smem_b + stage * TG_B_BYTES + j * 8192, &tmap_w, &full_bar[stage], n0 + 64 * j, kb * TG_BK);
+          } else {
+            ptx::tma_load_2d(smem_b + stage * TG_B_BYTES, &tmap_w, &full_bar[stage], kb * TG_BK, n0);
+          }
           if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -220,7 +225,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::idesc_bf16_f32(TG_BM, p.bn, 0, 0);
+      const uint32_t idesc = ptx::idesc_bf16_f32(TG_BM, p.bn, 0, p.w_kn ? 1 : 0);
+      const uint32_t b_lbo = p.w_kn ? 8192u : 16u;        // MN-major B: 64-column chunks 8 KB apart, 16 k-rows = 2048 B per step
+      const uint64_t b_kstep = p.w_kn ? 128u : 2u;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -231,11 +238,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint64_t a_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_a + stage * TG_A_BYTES), 16, 1024);
-          const uint64_t b_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * TG_B_BYTES), 16, 1024);
+          const uint64_t b_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * TG_B_BYTES), b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < TG_BK / TG_UMMA_K; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            ptx::mma_f16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            ptx::mma_f16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + b_kstep * (uint64_t)k, idesc, (kb | k) != 0);
           }
           ptx::tc_commit(&empty_bar[stage]);   // stage reusable once these MMAs retire
           if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
@@ -314,13 +321,15 @@ int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc
   }
   CUtensorMap ta, tw;
   if (int rc = encode_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, TG_BM, TG_BK, true)) return rc;
-  if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, bn, TG_BK, true)) return rc;
+  if (ep.w_kn) { if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)K, (uint64_t)N, (uint64_t)N * 2, 64, 64, true)) return rc; }
+  else if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, bn, TG_BK, true)) return rc;
   TPAT_CHECK(ep.xb == nullptr && ep.ln_part == nullptr, "tpat_gemm_ln: the LayerNorm fold needs the CTA-pair kernel (TPAT_GEMM_2CTA=0 is set)");
   TcGemmParams p{};
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.dact_out = ep.dact_out; p.ld_dact = ep.ld_dact; p.aux = ep.aux; p.ld_aux = ep.ld_aux; p.row_scale = ep.row_scale; p.rows_per_clip = ep.rows_per_clip;
   p.bn = bn;
+  p.w_kn = ep.w_kn;
   p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + bn - 1) / bn;
   p.desc = g_walk_desc;
   p.debug_skip = 0;

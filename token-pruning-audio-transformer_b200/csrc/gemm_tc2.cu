@@ -111,7 +111,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const bool load_b = p.debug_skip == 0 || first_fill;
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * ((load_a ? T2_A_BYTES : 0) + (load_b ? T2_B_BYTES : 0)));
           if (load_a) ptx::tma_load_2d_2cta(smem_a + stage * T2_A_BYTES, &tmap_a, full_leader, kb * TG_BK, m0);
-          if (load_b) ptx::tma_load_2d_2cta(smem_b + stage * T2_B_BYTES, &tmap_w, full_leader, kb * TG_BK, n0);
+          if (load_b) {
+            if (p.w_kn) {      // W[K][N]: this CTA's 128 n-columns as two 64 x 64 boxes, 8 KB apart
+              ptx::tma_load_2d_2cta(smem_b + stage * T2_B_BYTES, &tmap_w, full_leader, n0, kb * TG_BK);
+              ptx::tma_load_2d_2cta(smem_b + stage * T2_B_BYTES + 8192, &tmap_w, full_leader, n0 + 64, kb * TG_BK);
+            } else {
+              ptx::tma_load_2d_2cta(smem_b + stage * T2_B_BYTES, &tmap_w, full_leader, kb * TG_BK, n0);
+            }
+          }
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -119,7 +126,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp == 1) {
     // ===== MMA issuer: leader CTA only =====
     if (leader && ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(256, TG_BN, 0, 0);
+      const uint32_t idesc = ptx::idesc_bf16_f32(256, TG_BN, 0, p.w_kn ? 1 : 0);
+      // MN-major B (w_kn): 16 k-rows per step = two 8-row groups of 1024 B (SBO), 64-column chunks 8 KB apart (LBO)
+      const uint32_t b_lbo = p.w_kn ? 8192u : 16u;
+      const uint64_t b_kstep = p.w_kn ? 128u : 2u;        // in the descriptor's (address >> 4) field: 2048 B | 32 B
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = tile_first; tile < tile_end; tile += tile_step) {
@@ -130,10 +140,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint64_t a_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_a + stage * T2_A_BYTES), 16, 1024);
-          const uint64_t b_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * T2_B_BYTES), 16, 1024);
+          const uint64_t b_desc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * T2_B_BYTES), b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < TG_BK / TG_UMMA_K; ++k)
-            ptx::mma_f16_ss_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            ptx::mma_f16_ss_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + b_kstep * (uint64_t)k, idesc, (kb | k) != 0);
           ptx::tc_commit_2cta(&empty_bar[stage], 0b11);   // stage free in both CTAs
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -318,8 +328,10 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
              const EpiParams& ep, cudaStream_t st) {
   CUtensorMap ta, tw;
   if (int rc = encode_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 128, TG_BK, true)) return rc;
-  if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, 128, TG_BK, true)) return rc;
+  if (ep.w_kn) { if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)K, (uint64_t)N, (uint64_t)N * 2, 64, 64, true)) return rc; }
+  else if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, 128, TG_BK, true)) return rc;
   TcGemmParams p{};
+  p.w_kn = ep.w_kn;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.xb = (__nv_bfloat16*)ep.xb; p.ldxb = ep.ldxb; p.part_out = reinterpret_cast<float2*>(ep.part_out); p.part_ld = ep.part_ld;

@@ -40,6 +40,7 @@ struct TcGemmParams {
   const float* row_scale; int rows_per_clip;
   int pf_l2;        // 1: tmap_r covers the tensor the epilogue reads with plain loads (residual / saved GELU derivative);
                     //    the TMA warp prefetches each tile's 128 x 256 block into L2 when it starts loading the tile
+  int w_kn;         // 1: W is [K, N] row-major; B tiles are 64 x 64 boxes ([64 k rows][128 B of n]), MN-major descriptors
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
 };
 

@@ -123,11 +123,18 @@ static int validate_train(const tpat_train_args* t) {
   return 0;
 }
 
-// dX[M, Nin] = epilogue(dY[M, Nout] . W[Nout, Nin]) through the forward GEMM kernels on the [Nin, Nout] copy of W
-static int dgrad(const void* dY, int act, int M, int Nout, int Nin, const void* Wt, void* dX, int dx_dtype, int epilogue,
-                 const void* aux, int impl, tpat_stream_t st) {
+// dX[M, Nin] = epilogue(dY[M, Nout] . W[Nout, Nin]) through the forward GEMM kernels.  tcgen05 path: W is read as it is
+// (the forward weight as an MN-major B operand, tpat_gemm_extra.w_kn); fp32 path: the [Nin, Nout] copy Wt.
+static int dgrad(const void* dY, int act, int M, int Nout, int Nin, const void* W, const void* Wt, void* dX, int dx_dtype,
+                 int epilogue, const void* aux, int impl, tpat_stream_t st) {
   tpat_gemm_extra ex{};
   ex.aux = aux; ex.ld_aux = Nin;
+  static const bool force_copy = getenv("TPAT_DGRAD_TRANSPOSE") != nullptr;
+  if (impl == TPAT_IMPL_TC && !(force_copy && Wt != nullptr)) {
+    ex.w_kn = 1;
+    return tpat_gemm_train(dY, act, Nout, W, act, nullptr, dX, dx_dtype, Nin, nullptr, 0, M, Nin, Nout, epilogue, impl, &ex, st);
+  }
+  TPAT_CHECK(Wt != nullptr, "tpat_train_backward: the fp32 path needs the [in, out] weight copies (tpat_block_wt)");
   return tpat_gemm_train(dY, act, Nout, Wt, act, nullptr, dX, dx_dtype, Nin, nullptr, 0, M, Nin, Nout, epilogue, impl, &ex, st);
 }
 
@@ -282,14 +289,13 @@ extern "C" int tpat_train_backward(const tpat_train_args* t, int stage_hi, int s
       const BlockSaved& k = s.blk[i];
       const int N = k.N, M = B * N, N2 = k.N2, M2 = B * N2;
       const bool prune = a->prune[i] != 0;
-      TPAT_CHECK(wt.qkv_wt && wt.proj_wt && wt.fc1_wt && wt.fc2_wt, "tpat_train_backward: block %d needs the [in, out] weight copies", i);
       // fc2: gb = scale * dL/dx_out  [M2, D]
       if (int rc = wgrad(w.gb, k.a, gr.fc2_w, M2, D, Dh, act, impl, w, stream)) return rc;
-      if (int rc = dgrad(w.gb, act, M2, D, Dh, wt.fc2_wt, w.dh, act, TPAT_EPI_DGELU, k.h, impl, stream)) return rc;
+      if (int rc = dgrad(w.gb, act, M2, D, Dh, bw.fc2_w, wt.fc2_wt, w.dh, act, TPAT_EPI_DGELU, k.h, impl, stream)) return rc;
       // fc1
       if (gr.fc1_b) if (int rc = tpat_colsum(w.dh, act, Dh, M2, Dh, w.parts, gr.fc1_b, stream)) return rc;
       if (int rc = wgrad(w.dh, k.y2, gr.fc1_w, M2, Dh, D, act, impl, w, stream)) return rc;
-      if (int rc = dgrad(w.dh, act, M2, Dh, D, wt.fc1_wt, w.dy, dyt, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
+      if (int rc = dgrad(w.dh, act, M2, Dh, D, bw.fc1_w, wt.fc1_wt, w.dy, dyt, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
       // norm2 backward + residual (+ scatter): g [M2] -> g_alt [M]
       if (prune) if (int rc = tpat_inverse_index(a->topk_idx[i], w.inv, B, N - extra, a->keep[i], stream)) return rc;
       if (int rc = tpat_row_bwd(w.dy, dyt, k.x_g, bw.ln2_g, g, g_alt, w.gb, act, t->drop_scale[i][0], prune ? w.inv : nullptr, w.parts,
@@ -297,13 +303,13 @@ extern "C" int tpat_train_backward(const tpat_train_args* t, int stage_hi, int s
       { float* tmp = g; g = g_alt; g_alt = tmp; }
       // proj
       if (int rc = wgrad(w.gb, k.ao, gr.proj_w, M, D, D, act, impl, w, stream)) return rc;
-      if (int rc = dgrad(w.gb, act, M, D, D, wt.proj_wt, w.d_ao, act, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
+      if (int rc = dgrad(w.gb, act, M, D, D, bw.proj_w, wt.proj_wt, w.d_ao, act, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
       // attention
       if (int rc = tpat_attention_bwd(k.qkv, k.ao, w.d_ao, k.lse, w.dqkv, act, B, N, H, 64, scale, impl, w.delta, stream)) return rc;
       // qkv
       if (gr.qkv_b) if (int rc = tpat_colsum(w.dqkv, act, 3 * D, M, 3 * D, w.parts, gr.qkv_b, stream)) return rc;
       if (int rc = wgrad(w.dqkv, k.y1, gr.qkv_w, M, 3 * D, D, act, impl, w, stream)) return rc;
-      if (int rc = dgrad(w.dqkv, act, M, 3 * D, D, wt.qkv_wt, w.dy, dyt, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
+      if (int rc = dgrad(w.dqkv, act, M, 3 * D, D, bw.qkv_w, wt.qkv_wt, w.dy, dyt, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
       // norm1 backward + residual: g [M] -> g_alt [M]; operand copy scaled for the previous block's fc2 (+ its bias gradient)
       if (int rc = tpat_row_bwd(w.dy, dyt, k.x_in, bw.ln1_g, g, g_alt, i > 0 ? w.gb : nullptr, act, i > 0 ? t->drop_scale[i - 1][1] : nullptr,
                                 nullptr, w.parts, gr.ln1_g, gr.ln1_b, i > 0 ? t->grads[i - 1].fc2_b : nullptr, B, N, N, extra, 0, D, a->ln_eps, stream)) return rc;

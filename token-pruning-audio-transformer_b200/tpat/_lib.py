@@ -13,7 +13,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("TPAT_LIB_PATH") or os.path.join(_PKG_ROOT, "lib", "libtpat.so")   # override: kernel experiments
 
 TPAT_MAX_DEPTH = 32
-TPAT_VERSION = 9          # must equal TPAT_VERSION in include/tpat.h (checked at load)
+TPAT_VERSION = 10         # must equal TPAT_VERSION in include/tpat.h (checked at load)
 F32, BF16, BF16_SPLIT3 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_POS, EPI_DGELU = 0, 1, 2, 3, 4
 IMPL_SIMT, IMPL_TC = 0, 1
@@ -55,7 +55,7 @@ class ForwardArgs(Structure):
 class GemmExtra(Structure):
     """tpat_gemm_extra (include/tpat.h)."""
     _fields_ = [("dact_out", c_void_p), ("ld_dact", c_int), ("aux", c_void_p), ("ld_aux", c_int), ("row_scale", c_void_p),
-                ("rows_per_clip", c_int)]
+                ("rows_per_clip", c_int), ("w_kn", c_int)]
 
 
 BLOCK_GRAD_NAMES = ("ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")

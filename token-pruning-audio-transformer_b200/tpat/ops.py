@@ -329,13 +329,15 @@ def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, lse
 
 def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dtype: torch.dtype, epilogue: int, impl: int,
                residual: Optional[torch.Tensor] = None, want_dact: bool = False, aux: Optional[torch.Tensor] = None,
-               row_scale: Optional[torch.Tensor] = None, rows_per_clip: int = 0):
+               row_scale: Optional[torch.Tensor] = None, rows_per_clip: int = 0, w_kn: bool = False):
     """tpat_gemm_train: out = epilogue(a @ w.T + bias) with the training extras (GELU-derivative output, GELU-backward
-    epilogue, DropPath row scale)."""
+    epilogue, DropPath row scale).  ``w_kn``: ``w`` is [K, N] and out = epilogue(a @ w) (data gradients on the forward
+    weight, tcgen05 path only)."""
     import ctypes
     _req(a, name="a"); _req(w, a.dtype, "w")
     M, K = a.shape
-    N = w.shape[0]
+    N = w.shape[1] if w_kn else w.shape[0]
+    assert w.shape[0 if w_kn else 1] == K
     out = torch.empty(M, N, device=a.device, dtype=out_dtype)
     ex = _lib.GemmExtra()
     pre = None
@@ -347,6 +349,7 @@ def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], o
         ex.aux, ex.ld_aux = aux.data_ptr(), N
     if row_scale is not None:
         ex.row_scale, ex.rows_per_clip = row_scale.data_ptr(), rows_per_clip
+    ex.w_kn = 1 if w_kn else 0
     check(lib.tpat_gemm_train(a.data_ptr(), _DT[a.dtype], K, w.data_ptr(), _DT[w.dtype], _ptr(bias), out.data_ptr(), _DT[out_dtype], N,
                               _ptr(residual), N if residual is not None else 0, M, N, K, epilogue, impl, ctypes.byref(ex), _stream()),
           "tpat_gemm_train")

@@ -18,6 +18,7 @@ backward after ``optimizer.zero_grad()`` overwrites, a second backward without i
 """
 import ctypes
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -29,6 +30,7 @@ from .engine import pruning_schedule, tokens_entering
 
 BLOCK_ROLES = _lib.BLOCK_GRAD_NAMES   # ln1_g ... fc2_b
 MATRIX_ROLES = ("qkv_w", "proj_w", "fc1_w", "fc2_w")
+_DGRAD_TRANSPOSE = os.environ.get("TPAT_DGRAD_TRANSPOSE") is not None     # A/B switch: [in, out] bf16 copies instead of w_kn
 
 
 class TrainEngine:
@@ -111,7 +113,9 @@ class TrainEngine:
         self._operands_fresh = bf16_fresh
 
     def refresh_operands(self, impl: int) -> None:
-        """bf16 copy of the flat parameters + [in, out] copies of the block matrices, rebuilt when the weights changed."""
+        """bf16 copy of the flat parameters (tcgen05 path: the data-gradient GEMMs read the forward weights as MN-major
+        operands, no transposed copies) or fp32 [in, out] copies of the block matrices (fp32 path), rebuilt when the
+        weights changed."""
         versions = tuple(p._version for _, _, p in self.entries)
         if versions == self._versions and (impl == _lib.IMPL_SIMT or self.flat_pb is not None) and self._wt.get("impl") == impl:
             return
@@ -125,7 +129,7 @@ class TrainEngine:
         act = torch.bfloat16 if impl == _lib.IMPL_TC else torch.float32
         dt = _lib.BF16 if impl == _lib.IMPL_TC else _lib.F32
         for st, role, p in self.entries:
-            if role in MATRIX_ROLES and st >= 1:
+            if role in MATRIX_ROLES and st >= 1 and (impl == _lib.IMPL_SIMT or _DGRAD_TRANSPOSE):
                 key = (st, role)
                 out_f, in_f = p.shape
                 t = self._wt.get(key)
@@ -214,7 +218,8 @@ class TrainEngine:
                 setattr(bw, role, (op(p) if role in MATRIX_ROLES else p).data_ptr())
                 setattr(gr, role, gptr(p))
             for role in MATRIX_ROLES:
-                setattr(wt, role + "t", self._wt[(i + 1, role)].data_ptr())
+                t = self._wt.get((i + 1, role))
+                setattr(wt, role + "t", t.data_ptr() if t is not None and t.dtype == (torch.float32 if impl == _lib.IMPL_SIMT else torch.bfloat16) else None)
 
     def forward(self, spec: torch.Tensor, keep_rates: Sequence[float], num_classes: int, precision: str, roles,
                 drop_scales: Optional[List[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]]] = None,

@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
 run() { local name=$1 to=$2; shift 2; timeout $to "$@" > gpurun_out/$name.log 2>&1; echo "== $name rc=$? =="; tail -n ${TAILN:-25} gpurun_out/$name.log; }
-run t12a 120 python -m pytest tests/test_gpu_12_attention_v3.py -q -m gpu -s -x -k "matches_reference and 66"
-run t12 240 python -m pytest tests/test_gpu_12_attention_v3.py -q -m gpu -s
-run v3b 200 python tools/attn_v3_bench.py
+TAILN=8 run t60 600 python -m pytest tests/test_gpu_60_train.py -q -m gpu -x
+TAILN=40 run tkb 200 python tools/train_kernel_bench.py
+TAILN=3 run bt_graph 200 python bench.py --mode train --steps 10 --warmup 3 --no-e2e
+TAILN=3 run bt_tr 200 env TPAT_DGRAD_TRANSPOSE=1 python bench.py --mode train --steps 10 --warmup 3 --no-e2e
+TAILN=3 run bi_pdl 200 env TPAT_PDL=1 python bench.py --steps 20 --warmup 5
+TAILN=3 run bi 200 python bench.py --steps 20 --warmup 5
