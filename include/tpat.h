@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPAT_VERSION 10
+#define TPAT_VERSION 11
 #define TPAT_MAX_DEPTH 32
 
 typedef void* tpat_stream_t; /* cudaStream_t */
@@ -332,7 +332,13 @@ typedef struct tpat_gemm_extra {
   int w_kn;                                      /* 1: W is stored [K, N] row-major (C = A W): the data gradient dX = dY W reads the
                                                     forward weight [out, in] as it is, as an MN-major tcgen05 B operand -- no
                                                     transposed copy.  tcgen05 path only (N % 8 == 0)                                   */
+  float* colsum_out;                             /* TPAT_EPI_DGELU: colsum_out[n] += sum_m C[m, n] -- the bias gradient of the Linear
+                                                    whose dY this GEMM produces (fc1).  tcgen05 path: summed in the epilogue from
+                                                    the fp32 values (per 32-row partials in colsum_ws, fixed-order finish: no extra
+                                                    pass over C); otherwise, or when colsum_ws is too small, one tpat_colsum pass     */
+  float* colsum_ws; size_t colsum_ws_floats;     /* >= tpat_gemm_colsum_ws_floats(M, N) for the fused form                           */
 } tpat_gemm_extra;
+size_t tpat_gemm_colsum_ws_floats(int M, int N);
 int tpat_gemm_train(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias, void* C, int c_dtype,
                     int ldc, const float* residual, int ldr, int M, int N, int K, int epilogue, int impl,
                     const tpat_gemm_extra* extra, tpat_stream_t stream);
@@ -359,10 +365,13 @@ int tpat_attention_train(const void* qkv, void* out, int dtype, float* score_par
 /* Attention backward: dqkv [B * N, 3 * H * hd] (dtype) from qkv, out (= O), d_out and lse; P is recomputed, nothing of
  * size N x N touches HBM; no gradient through the importance score / top-k (indices).
  * delta_ws: tpat_attention_bwd_ws_floats(B, N, H, hd) floats (row sums of dO o O, and the fp32 dQ accumulator of the
- * tcgen05 kernel, which adds each key tile's contribution with TMA reduce operations). */
+ * tcgen05 kernel, which adds each key tile's contribution with TMA reduce operations).
+ * dbias (optional, tcgen05 bf16 path only): dbias[3 * H * hd] += column sums of dqkv, i.e. the bias gradient of the qkv
+ * projection, taken where dqkv is produced (dK / dV tiles in shared memory, dQ in the fp32 -> bf16 pass) instead of a
+ * separate pass over dqkv. */
 size_t tpat_attention_bwd_ws_floats(int B, int N, int H, int hd);
 int tpat_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int dtype,
-                       int B, int N, int H, int hd, float scale, int impl, float* delta_ws, tpat_stream_t stream);
+                       int B, int N, int H, int hd, float scale, int impl, float* delta_ws, float* dbias, tpat_stream_t stream);
 
 /* floats a `partials_ws` scratch buffer must hold for the three functions below */
 size_t tpat_bwd_partials_floats(int D_max);

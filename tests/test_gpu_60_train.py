@@ -156,6 +156,21 @@ def test_attention_backward(impl_name, N):
     for w in range(3):   # dq, dk, dv separately
         a, b = dqkv.float()[:, w * 768:(w + 1) * 768], q.grad[:, w * 768:(w + 1) * 768]
         assert nerr(a, b) < tol, w
+    if impl_name == "tc":
+        # fused qkv bias gradient: column sums taken where dqkv is produced, added to what dbias holds; dqkv itself unchanged
+        base = torch.randn(3 * H * 64, device=dev())
+        dbias = base.clone()
+        dqkv2 = ops.attention_bwd(qkv, out, d_out, lse, B, N, H, impl, dbias=dbias)
+        assert torch.equal(dqkv2[:, 768:], dqkv[:, 768:])           # dK, dV: bit-identical
+        assert nerr(dqkv2[:, :768].float(), dqkv[:, :768].float()) < 3e-3   # dQ: TMA reduce-adds land in any order
+        want = dqkv.double().sum(0)
+        e_b = nerr(dbias - base, want)
+        print(f"[attention bwd tc] N={N}: fused qkv bias gradient err {e_b:.2e} (vs the column sums of the bf16 dqkv)")
+        assert e_b < 4e-3            # the q third sums the fp32 values before their rounding to bf16 (~1e-3 expected)
+        assert nerr((dbias - base)[768:], want[768:]) < 1e-5
+    else:
+        with pytest.raises(RuntimeError):
+            ops.attention_bwd(qkv, out, d_out, lse, B, N, H, impl, dbias=torch.zeros(3 * H * 64, device=dev()))
 
 
 @pytest.mark.parametrize("impl_name", ["simt", "tc"])
@@ -217,6 +232,31 @@ def test_gemm_dgrad_on_forward_weight(M, Nout, Nin):
         assert torch.equal(got, ref)
     with pytest.raises(RuntimeError):
         ops.gemm_train(dy.float(), w.float(), None, torch.float32, _lib.EPI_BIAS, _lib.IMPL_SIMT, w_kn=True)
+
+
+@pytest.mark.parametrize("impl_name,M", [("tc", 64 * 178 + 5), ("tc", 3000), ("tc", 100), ("simt", 300)])
+def test_gemm_dgelu_fused_bias_gradient(impl_name, M):
+    """The GELU-backward GEMM also leaves the column sums of its output (= fc1's bias gradient), accumulated into
+    colsum_out; the output itself does not change.  CTA-pair kernel, 1-CTA kernel and the fp32 path (separate pass)."""
+    from tpat import ops, _lib
+    torch.manual_seed(M)
+    impl = _lib.IMPL_SIMT if impl_name == "simt" else _lib.IMPL_TC
+    dt = torch.float32 if impl_name == "simt" else torch.bfloat16
+    D, Dh = 768, 3072
+    g = (torch.randn(M, D, device=dev()) * 0.3).to(dt)
+    w2 = (torch.randn(D, Dh, device=dev()) * 0.03).to(dt)
+    aux = torch.rand(M, Dh, device=dev()).to(dt)
+    base = torch.randn(Dh, device=dev())
+    cs = base.clone()
+    kw = dict(w_kn=True) if impl_name == "tc" else {}
+    wop = w2 if impl_name == "tc" else w2.T.contiguous()
+    dh = ops.gemm_train(g, wop, None, dt, _lib.EPI_DGELU, impl, aux=aux, colsum_out=cs, **kw)
+    ref = ops.gemm_train(g, wop, None, dt, _lib.EPI_DGELU, impl, aux=aux, **kw)
+    assert torch.equal(dh, ref)
+    want = (g.double() @ w2.double()) * aux.double()
+    e = nerr(cs - base, want.sum(0))
+    print(f"[dgelu colsum {impl_name}] M={M}: err {e:.2e}")
+    assert e < (1e-5 if impl_name == "simt" else 2e-3)
 
 
 @pytest.mark.parametrize("K,Mo,No", [(513 * 3, 768, 768), (1000, 2304, 768), (4104, 768, 3072), (70, 256, 256), (32832, 3072, 768)])

@@ -48,13 +48,15 @@ extern "C" int tpat_attention_train(const void* qkv, void* out, int dtype, float
 }
 
 extern "C" int tpat_attention_bwd(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int dtype,
-                                  int B, int N, int H, int hd, float scale, int impl, float* delta_ws, tpat_stream_t stream) {
+                                  int B, int N, int H, int hd, float scale, int impl, float* delta_ws, float* dbias,
+                                  tpat_stream_t stream) {
   using namespace tpat;
   TPAT_CHECK(qkv && out && d_out && lse && dqkv && delta_ws, "tpat_attention_bwd: null pointer");
   TPAT_CHECK(B >= 0 && N > 0 && H > 0 && hd == 64, "tpat_attention_bwd: bad sizes B=%d N=%d H=%d hd=%d", B, N, H, hd);
   TPAT_CHECK(dtype == TPAT_F32 || dtype == TPAT_BF16, "tpat_attention_bwd: bad dtype %d", dtype);
   TPAT_CHECK(aligned16(qkv) && aligned16(out) && aligned16(d_out) && aligned16(dqkv), "tpat_attention_bwd: pointers must be 16-byte aligned");
   if (B == 0) return 0;
-  if (impl == TPAT_IMPL_TC && dtype == TPAT_BF16) return attention_bwd_tc(qkv, out, d_out, lse, dqkv, B, N, H, scale, delta_ws, as_stream(stream));
+  if (impl == TPAT_IMPL_TC && dtype == TPAT_BF16) return attention_bwd_tc(qkv, out, d_out, lse, dqkv, B, N, H, scale, delta_ws, dbias, as_stream(stream));
+  TPAT_CHECK(dbias == nullptr, "tpat_attention_bwd: the fused bias gradient (dbias) exists on the tcgen05 bf16 path only; use tpat_colsum");
   return attention_bwd_simt(qkv, out, d_out, lse, dqkv, dtype, B, N, H, scale, delta_ws, as_stream(stream));
 }

@@ -19,6 +19,8 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
 
 // tcgen05 backward (bf16 operands); falls back to the CUDA-core kernels until attention_bwd_tc.cu provides it
 int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int N, int H,
-                     float scale, float* delta_ws, cudaStream_t st);
+                     float scale, float* delta_ws, float* dbias, cudaStream_t st);
+// dst[c] += sum over the nparts rows of partials[nparts][C], fixed order (backward_rows.cu)
+int finish_colsum_partials(const float* partials, int nparts, int C, float* dst, cudaStream_t st);
 
 }  // namespace tpat

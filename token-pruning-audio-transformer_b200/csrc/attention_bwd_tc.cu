@@ -44,6 +44,7 @@ struct AttnBwdTcParams {
   long long* trace;      // debug builds (TPAT_ATTN_BWD_TRACE): clock stamps of one softmax thread and of the MMA thread
   const float* lse;      // [B, H, N] natural log
   const float* delta;    // [B, H, N]
+  float* bias_part;      // optional [B * n_t * 2][3 * H * 64]: column sums of this CTA's dK / dV rows (two 64-row halves)
   int N, H, n_t;
   float scale, scale_log2;
 };
@@ -348,6 +349,23 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       ptx::tma_store_3d(&tm_dkv, v_s, col_v, jt * BT_M, b);
       ptx::tma_store_commit();
     }
+    if (p.bias_part != nullptr) {
+      // bias gradient of the qkv projection, K / V columns: column sums of the bf16 tiles just staged (valid key rows
+      // only), thread = (row half, tensor, column); a warp reads 64 contiguous bytes of one swizzled row
+      const int t = threadIdx.x - 64;
+      const int c = t & 63, tsel = (t >> 6) & 1, rh = t >> 7;
+      const uint8_t* blk = tsel ? v_s : k_s;
+      const int r_end = min(rh * 64 + 64, min(BT_M, p.N - jt * BT_M));
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      auto at = [&](int r) {
+        const uint16_t u = *reinterpret_cast<const uint16_t*>(blk + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1)));
+        return __uint_as_float((uint32_t)u << 16);
+      };
+      int r = rh * 64;
+      for (; r + 3 < r_end; r += 4) { s0 += at(r); s1 += at(r + 1); s2 += at(r + 2); s3 += at(r + 3); }
+      for (; r < r_end; ++r) s0 += at(r);
+      p.bias_part[((size_t)(b * p.n_t + jt) * 2 + rh) * (size_t)(3 * p.H * BT_HD) + (tsel ? col_v : col_k) + c] = (s0 + s1) + (s2 + s3);
+    }
     if (lane == 0) ptx::tma_store_wait<0>();                    // reduces / stores complete before the CTA retires
   }
 
@@ -373,12 +391,42 @@ dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqk
   }
 }
 
+// the same per (clip, 128-row tile) with the column sums of the fp32 rows (q columns of the qkv bias gradient): thread =
+// (16-byte column group, row phase); partial rows as attention_bwd_tc_kernel writes them
+__global__ void __launch_bounds__(1024)
+dq_convert_sum_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ part, int N, int HD, int n_t) {
+  pdl_trigger();
+  pdl_wait();
+  const int jt = blockIdx.x, b = blockIdx.y;
+  const int c4n = HD / 4;
+  const int c4 = threadIdx.x % c4n, ph = threadIdx.x / c4n;
+  const int r1 = min(N, jt * 128 + 128);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int r = jt * 128 + ph;
+  auto one = [&](int rr, const float4& v) {
+    reinterpret_cast<uint2*>(dqkv + ((size_t)b * N + rr) * 3 * HD)[c4] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  };
+  for (; r + 6 < r1; r += 8) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(acc + ((size_t)b * N + r + 2 * k) * HD) + c4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) one(r + 2 * k, v[k]);
+  }
+  for (; r < r1; r += 2) one(r, __ldg(reinterpret_cast<const float4*>(acc + ((size_t)b * N + r) * HD) + c4));
+  reinterpret_cast<float4*>(part + ((size_t)(b * n_t + jt) * 2 + ph) * (size_t)(3 * HD))[c4] = s;
+}
+
 int attention_bwd_delta_bf16(const void* out, const void* d_out, float* delta, int B, int N, int H, cudaStream_t st);
 
 int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const float* lse, void* dqkv, int B, int N, int H,
-                     float scale, float* delta_ws, cudaStream_t st) {
+                     float scale, float* delta_ws, float* dbias, cudaStream_t st) {
   static const bool force_simt = getenv("TPAT_ATTN_BWD_SIMT") != nullptr;
-  if (force_simt) return attention_bwd_simt(qkv, out, d_out, lse, dqkv, TPAT_BF16, B, N, H, scale, delta_ws, st);
+  if (force_simt) {
+    TPAT_CHECK(dbias == nullptr, "tpat_attention_bwd: dbias needs the tcgen05 kernel (TPAT_ATTN_BWD_SIMT is set)");
+    return attention_bwd_simt(qkv, out, d_out, lse, dqkv, TPAT_BF16, B, N, H, scale, delta_ws, st);
+  }
   // workspace: delta [B * H * N] then the fp32 dQ accumulator [B * N, H * 64] (256-byte aligned)
   float* delta = delta_ws;
   const size_t dq_off = ((size_t)B * H * N + 63) / 64 * 64;
@@ -397,6 +445,8 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const 
     p.trace = dbg; extern long long* g_attn_bwd_trace_buf; g_attn_bwd_trace_buf = dbg; }
 #endif
   p.lse = lse; p.delta = delta; p.N = N; p.H = H; p.n_t = (N + BT_M - 1) / BT_M;
+  // (column-sum partials behind the dQ accumulator; every entry is written by this launch pair, no memset)
+  p.bias_part = dbias != nullptr ? dq_acc + (size_t)B * N * H * BT_HD : nullptr;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   static DeviceOnce once;
   if (once.first()) {
@@ -407,6 +457,13 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const 
   const size_t rows = (size_t)B * N;
   const size_t total = rows * (H * BT_HD / 4);
   const int grid = (int)((total + 255) / 256 < (size_t)sm_count() * 16 ? (total + 255) / 256 : (size_t)sm_count() * 16);
+  if (dbias != nullptr) {
+    TPAT_CHECK(H * BT_HD / 4 * 2 <= 1024, "tpat_attention_bwd: dbias supports up to 32 heads");
+    TPAT_CUDA(launch_kernel(dq_convert_sum_kernel, dim3(p.n_t, B), dim3(H * BT_HD / 4 * 2), 0, st, (const float*)dq_acc, (__nv_bfloat16*)dqkv,
+                            p.bias_part, N, H * BT_HD, p.n_t));
+    TPAT_LAUNCH_CHECK();
+    return finish_colsum_partials(p.bias_part, B * p.n_t * 2, 3 * H * BT_HD, dbias, st);
+  }
   TPAT_CUDA(launch_kernel(dq_convert_kernel, dim3(grid), dim3(256), 0, st, (const float*)dq_acc, (__nv_bfloat16*)dqkv, rows, H * BT_HD));
   TPAT_LAUNCH_CHECK();
   return 0;
@@ -423,5 +480,5 @@ extern "C" int tpat_debug_attn_bwd_trace(long long* host_out) {   // debug build
 #endif
 
 extern "C" size_t tpat_attention_bwd_ws_floats(int B, int N, int H, int hd) {
-  return ((size_t)B * H * N + 63) / 64 * 64 + (size_t)B * N * H * hd;
+  return ((size_t)B * H * N + 63) / 64 * 64 + (size_t)B * N * H * hd + (size_t)B * ((N + 127) / 128) * 2 * 3 * H * hd;
 }

@@ -16,6 +16,7 @@
 //   pool_norm_bwd       backward of tpat_pool_norm, one CTA per clip.
 // Bytes per row (D = 768, bf16 operands): 3 KB (dy fp32) + 3 KB (x) + 3 KB (g_up) read, 3 KB + 1.5 KB written.
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace tpat {
 
@@ -386,6 +387,10 @@ static int finish_partials(const float* partials, int nparts, int nq, int C, flo
   TPAT_CUDA(launch_kernel(partials_finish_kernel, dim3((C + 31) / 32, nq), dim3(512), 0, st, partials, nparts, nq, C, dst));
   TPAT_LAUNCH_CHECK();
   return 0;
+}
+
+int finish_colsum_partials(const float* partials, int nparts, int C, float* dst, cudaStream_t st) {
+  return finish_partials(partials, nparts, 1, C, dst, nullptr, nullptr, nullptr, st);
 }
 
 template <typename DyT, typename OutT, bool HAS_LN>

@@ -21,6 +21,9 @@ extern "C" int tpat_gemm_ln(const void* A, int a_dtype, int lda, const void* W, 
                     nullptr, stream);
 }
 
+/* partial rows: one per 32 output rows, rounded up to whole 256-row tiles (the 1-CTA kernel's 128-row tiles fit inside) */
+extern "C" size_t tpat_gemm_colsum_ws_floats(int M, int N) { return (size_t)((M + 255) / 256 * 8) * (size_t)N; }
+
 extern "C" int tpat_gemm_train(const void* A, int a_dtype, int lda, const void* W, int w_dtype, const float* bias,
                                void* C, int c_dtype, int ldc, const float* residual, int ldr, int M, int N, int K,
                                int epilogue, int impl, const tpat_gemm_extra* extra, tpat_stream_t stream) {
@@ -57,6 +60,8 @@ static int gemm_entry(const void* A, int a_dtype, int lda, const void* W, int w_
       TPAT_CHECK(epilogue == TPAT_EPI_BIAS_RESIDUAL && extra->rows_per_clip > 0, "tpat_gemm_train: row_scale needs the residual epilogue and rows_per_clip > 0");
       ep.row_scale = extra->row_scale; ep.rows_per_clip = extra->rows_per_clip;
     }
+    if (extra->colsum_out != nullptr)
+      TPAT_CHECK(epilogue == TPAT_EPI_DGELU && N % 32 == 0, "tpat_gemm_train: colsum_out needs the DGELU epilogue and N %% 32 == 0");
     if (extra->w_kn) {
       TPAT_CHECK(impl == TPAT_IMPL_TC && N % 8 == 0 && aligned16(W) && fold == nullptr,
                  "tpat_gemm_train: w_kn (W stored [K, N]) exists on the tcgen05 path only and needs N %% 8 == 0");
@@ -76,10 +81,28 @@ static int gemm_entry(const void* A, int a_dtype, int lda, const void* W, int w_
       ep.ln_part = fold->ln_part; ep.ln_chunks = K / 32; ep.ln_colsum = fold->ln_colsum; ep.ln_eps = fold->ln_eps;
     }
   }
-  if (impl == TPAT_IMPL_SIMT) return gemm_simt(A, a_dtype, lda, W, C, c_dtype, ldc, M, N, K, ep, as_stream(stream));
+  float* colsum_out = extra != nullptr ? extra->colsum_out : nullptr;
+  if (impl == TPAT_IMPL_SIMT) {
+    if (int rc = gemm_simt(A, a_dtype, lda, W, C, c_dtype, ldc, M, N, K, ep, as_stream(stream))) return rc;
+    if (colsum_out != nullptr) {
+      TPAT_CHECK(extra->colsum_ws != nullptr, "tpat_gemm_train: colsum_out needs colsum_ws");
+      return tpat_colsum(C, c_dtype, ldc, M, N, extra->colsum_ws, colsum_out, stream);
+    }
+    return 0;
+  }
   if (impl == TPAT_IMPL_TC) {
     TPAT_CHECK(a_dtype == TPAT_BF16, "tpat_gemm: the tcgen05 path takes bf16 operands");
-    return gemm_tc(A, lda, W, C, c_dtype, ldc, M, N, K, ep, as_stream(stream));
+    static const bool no_fuse = getenv("TPAT_NO_FUSED_COLSUM") != nullptr;
+    const bool fuse = colsum_out != nullptr && !no_fuse && extra->colsum_ws != nullptr &&
+                      extra->colsum_ws_floats >= tpat_gemm_colsum_ws_floats(M, N);
+    if (fuse) ep.cs_part = extra->colsum_ws;
+    if (int rc = gemm_tc(A, lda, W, C, c_dtype, ldc, M, N, K, ep, as_stream(stream))) return rc;
+    if (fuse) return finish_colsum_partials(extra->colsum_ws, (M + 31) / 32, N, colsum_out, as_stream(stream));   // (rows past M are zeros)
+    if (colsum_out != nullptr) {
+      TPAT_CHECK(extra->colsum_ws != nullptr, "tpat_gemm_train: colsum_out needs colsum_ws");
+      return tpat_colsum(C, c_dtype, ldc, M, N, extra->colsum_ws, colsum_out, stream);
+    }
+    return 0;
   }
   set_error("tpat_gemm: bad impl %d", impl);
   return 1;

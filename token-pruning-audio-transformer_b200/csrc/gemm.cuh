@@ -20,7 +20,11 @@ struct EpiParams {
   const void* aux = nullptr; int ld_aux = 0;          // DGELU: the saved gelu'(h) (dtype of C): C = acc * aux
   const float* row_scale = nullptr; int rows_per_clip = 0;   // BIAS_RESIDUAL: C = R + row_scale[m / rows_per_clip] * (acc + bias)  (DropPath)
   int w_kn = 0;                                         // W stored [K, N] (MN-major B operand)
+  float* cs_part = nullptr;                             // DGELU: per-32-row partial column sums of C, [ceil(M / 32) rounded to tiles][N]
 };
+
+// dst[c] += sum over the nparts rows of partials[nparts][C], fixed order (backward_rows.cu)
+int finish_colsum_partials(const float* partials, int nparts, int C, float* dst, cudaStream_t st);
 
 // CUDA-core fp32-FMA path (gemm_simt.cu)
 int gemm_simt(const void* A, int a_dtype, int lda, const void* W, void* C, int c_dtype, int ldc, int M, int N, int K,

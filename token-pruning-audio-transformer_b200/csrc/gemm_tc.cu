@@ -330,6 +330,7 @@ int gemm_tc(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc
   p.dact_out = ep.dact_out; p.ld_dact = ep.ld_dact; p.aux = ep.aux; p.ld_aux = ep.ld_aux; p.row_scale = ep.row_scale; p.rows_per_clip = ep.rows_per_clip;
   p.bn = bn;
   p.w_kn = ep.w_kn;
+  p.cs_part = ep.cs_part;
   p.tiles_m = (M + TG_BM - 1) / TG_BM; p.tiles_n = (N + bn - 1) / bn;
   p.desc = g_walk_desc;
   p.debug_skip = 0;

@@ -332,6 +332,7 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
   else if (int rc = encode_tmap_2d(&tw, W, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, 128, TG_BK, true)) return rc;
   TcGemmParams p{};
   p.w_kn = ep.w_kn;
+  p.cs_part = ep.cs_part;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = ep.bias; p.residual = ep.residual; p.ldr = ep.ldr;
   p.pos = ep.pos; p.P = ep.P; p.num_extra = ep.num_extra;
   p.xb = (__nv_bfloat16*)ep.xb; p.ldxb = ep.ldxb; p.part_out = reinterpret_cast<float2*>(ep.part_out); p.part_ld = ep.part_ld;

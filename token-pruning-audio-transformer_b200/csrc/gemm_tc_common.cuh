@@ -40,6 +40,7 @@ struct TcGemmParams {
   const float* row_scale; int rows_per_clip;
   int pf_l2;        // 1: tmap_r covers the tensor the epilogue reads with plain loads (residual / saved GELU derivative);
                     //    the TMA warp prefetches each tile's 128 x 256 block into L2 when it starts loading the tile
+  float* cs_part;   // DGELU: partial column sums of the output, row (m0 / 32) of [.][N], written by every epilogue warp
   int w_kn;         // 1: W is [K, N] row-major; B tiles are 64 x 64 boxes ([64 k rows][128 B of n]), MN-major descriptors
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
 };
@@ -270,6 +271,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
         } else {
           v[it].x *= extra[it].x; v[it].y *= extra[it].y; v[it].z *= extra[it].z; v[it].w *= extra[it].w;
         }
+      }
+      if (p.cs_part != nullptr) {
+        // bias gradient of the producing Linear: column sums of this warp's 32 rows (rows >= M carry aux = 0), reduced over
+        // the four row groups of the coalesced layout; one 128-byte row segment per warp and chunk
+        float4 cs = v[0];
+#pragma unroll
+        for (int it = 1; it < 8; ++it) { cs.x += v[it].x; cs.y += v[it].y; cs.z += v[it].z; cs.w += v[it].w; }
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+          cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+        }
+        if (rl == 0) *reinterpret_cast<float4*>(p.cs_part + (size_t)(m0 >> 5) * p.N + ncol) = cs;
       }
     } else if constexpr (EPI == TPAT_EPI_BIAS_RESIDUAL || EPI == TPAT_EPI_BIAS_POS) {
       if (EPI == TPAT_EPI_BIAS_RESIDUAL && p.row_scale != nullptr) {     // DropPath: per-clip scale of the branch

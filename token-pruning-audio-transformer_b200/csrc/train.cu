@@ -38,6 +38,7 @@ struct Saved {
 struct BwdWs {
   float* g[2]; void* gb; void* dh; float* dy; void* d_ao; void* dqkv; void* t1; void* t2; int32_t* inv; float* parts; float* delta;
   float* dpooled; float* x0g;
+  size_t parts_floats;
   size_t bytes;
 };
 
@@ -105,7 +106,10 @@ static BwdWs carve_bwd(const tpat_train_args* t, uint8_t* base) {
   w.t1 = a->impl == TPAT_IMPL_TC ? take(Cmax * Mpad * act) : nullptr;
   w.t2 = a->impl == TPAT_IMPL_TC ? take(Cmax * Mpad * act) : nullptr;
   w.inv = (int32_t*)take(B * P * 4);
-  w.parts = (float*)take(tpat_bwd_partials_floats((int)(Dh > D ? Dh : D)) * 4);
+  // per-CTA partial sums of the row kernels, or the per-32-row column sums the GELU-backward GEMM leaves for fc1's bias
+  w.parts_floats = tpat_bwd_partials_floats((int)(Dh > D ? Dh : D));
+  if (const size_t need = tpat_gemm_colsum_ws_floats((int)Mmax, (int)Dh); need > w.parts_floats) w.parts_floats = need;
+  w.parts = (float*)take(w.parts_floats * 4);
   w.delta = (float*)take(tpat_attention_bwd_ws_floats((int)B, (int)Nfull, (int)H, 64) * 4);
   w.dpooled = (float*)take(B * D * 4);
   w.x0g = t->mask_keep_idx ? (float*)take(Mmax * D * 4) : nullptr;
@@ -126,9 +130,11 @@ static int validate_train(const tpat_train_args* t) {
 // dX[M, Nin] = epilogue(dY[M, Nout] . W[Nout, Nin]) through the forward GEMM kernels.  tcgen05 path: W is read as it is
 // (the forward weight as an MN-major B operand, tpat_gemm_extra.w_kn); fp32 path: the [Nin, Nout] copy Wt.
 static int dgrad(const void* dY, int act, int M, int Nout, int Nin, const void* W, const void* Wt, void* dX, int dx_dtype,
-                 int epilogue, const void* aux, int impl, tpat_stream_t st) {
+                 int epilogue, const void* aux, int impl, tpat_stream_t st, float* colsum_out = nullptr, float* colsum_ws = nullptr,
+                 size_t colsum_ws_floats = 0) {
   tpat_gemm_extra ex{};
   ex.aux = aux; ex.ld_aux = Nin;
+  ex.colsum_out = colsum_out; ex.colsum_ws = colsum_ws; ex.colsum_ws_floats = colsum_ws_floats;
   static const bool force_copy = getenv("TPAT_DGRAD_TRANSPOSE") != nullptr;
   if (impl == TPAT_IMPL_TC && !(force_copy && Wt != nullptr)) {
     ex.w_kn = 1;
@@ -291,9 +297,9 @@ extern "C" int tpat_train_backward(const tpat_train_args* t, int stage_hi, int s
       const bool prune = a->prune[i] != 0;
       // fc2: gb = scale * dL/dx_out  [M2, D]
       if (int rc = wgrad(w.gb, k.a, gr.fc2_w, M2, D, Dh, act, impl, w, stream)) return rc;
-      if (int rc = dgrad(w.gb, act, M2, D, Dh, bw.fc2_w, wt.fc2_wt, w.dh, act, TPAT_EPI_DGELU, k.h, impl, stream)) return rc;
+      // (+ fc1's bias gradient = column sums of dh, taken in the same epilogue)
+      if (int rc = dgrad(w.gb, act, M2, D, Dh, bw.fc2_w, wt.fc2_wt, w.dh, act, TPAT_EPI_DGELU, k.h, impl, stream, gr.fc1_b, w.parts, w.parts_floats)) return rc;
       // fc1
-      if (gr.fc1_b) if (int rc = tpat_colsum(w.dh, act, Dh, M2, Dh, w.parts, gr.fc1_b, stream)) return rc;
       if (int rc = wgrad(w.dh, k.y2, gr.fc1_w, M2, Dh, D, act, impl, w, stream)) return rc;
       if (int rc = dgrad(w.dh, act, M2, Dh, D, bw.fc1_w, wt.fc1_wt, w.dy, dyt, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
       // norm2 backward + residual (+ scatter): g [M2] -> g_alt [M]
@@ -305,9 +311,13 @@ extern "C" int tpat_train_backward(const tpat_train_args* t, int stage_hi, int s
       if (int rc = wgrad(w.gb, k.ao, gr.proj_w, M, D, D, act, impl, w, stream)) return rc;
       if (int rc = dgrad(w.gb, act, M, D, D, bw.proj_w, wt.proj_wt, w.d_ao, act, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
       // attention
-      if (int rc = tpat_attention_bwd(k.qkv, k.ao, w.d_ao, k.lse, w.dqkv, act, B, N, H, 64, scale, impl, w.delta, stream)) return rc;
+      // (tcgen05 path: + the qkv bias gradient = column sums of dqkv, taken where dqkv is produced)
+      static const bool no_fuse = getenv("TPAT_NO_FUSED_COLSUM") != nullptr;
+      const bool fuse_qkv_b = impl == TPAT_IMPL_TC && act == TPAT_BF16 && !no_fuse && getenv("TPAT_ATTN_BWD_SIMT") == nullptr;
+      if (int rc = tpat_attention_bwd(k.qkv, k.ao, w.d_ao, k.lse, w.dqkv, act, B, N, H, 64, scale, impl, w.delta,
+                                      fuse_qkv_b ? gr.qkv_b : nullptr, stream)) return rc;
       // qkv
-      if (gr.qkv_b) if (int rc = tpat_colsum(w.dqkv, act, 3 * D, M, 3 * D, w.parts, gr.qkv_b, stream)) return rc;
+      if (gr.qkv_b && !fuse_qkv_b) if (int rc = tpat_colsum(w.dqkv, act, 3 * D, M, 3 * D, w.parts, gr.qkv_b, stream)) return rc;
       if (int rc = wgrad(w.dqkv, k.y1, gr.qkv_w, M, 3 * D, D, act, impl, w, stream)) return rc;
       if (int rc = dgrad(w.dqkv, act, M, 3 * D, D, bw.qkv_w, wt.qkv_wt, w.dy, dyt, TPAT_EPI_BIAS, nullptr, impl, stream)) return rc;
       // norm1 backward + residual: g [M] -> g_alt [M]; operand copy scaled for the previous block's fc2 (+ its bias gradient)

@@ -13,7 +13,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("TPAT_LIB_PATH") or os.path.join(_PKG_ROOT, "lib", "libtpat.so")   # override: kernel experiments
 
 TPAT_MAX_DEPTH = 32
-TPAT_VERSION = 10         # must equal TPAT_VERSION in include/tpat.h (checked at load)
+TPAT_VERSION = 11         # must equal TPAT_VERSION in include/tpat.h (checked at load)
 F32, BF16, BF16_SPLIT3 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_POS, EPI_DGELU = 0, 1, 2, 3, 4
 IMPL_SIMT, IMPL_TC = 0, 1
@@ -55,7 +55,8 @@ class ForwardArgs(Structure):
 class GemmExtra(Structure):
     """tpat_gemm_extra (include/tpat.h)."""
     _fields_ = [("dact_out", c_void_p), ("ld_dact", c_int), ("aux", c_void_p), ("ld_aux", c_int), ("row_scale", c_void_p),
-                ("rows_per_clip", c_int), ("w_kn", c_int)]
+                ("rows_per_clip", c_int), ("w_kn", c_int), ("colsum_out", c_void_p), ("colsum_ws", c_void_p),
+                ("colsum_ws_floats", c_size_t)]
 
 
 BLOCK_GRAD_NAMES = ("ln1_g", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
@@ -119,12 +120,13 @@ SIGNATURES = {
     "tpat_gemm_train": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                                 c_int, c_int, c_int, c_int, c_int, POINTER(GemmExtra), c_void_p]),
     "tpat_gemm_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "tpat_gemm_colsum_ws_floats": (c_size_t, [c_int, c_int]),
     "tpat_gemm_wgrad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tpat_transpose": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "tpat_attention_train": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_float, c_int, c_void_p]),
     "tpat_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
-                                   c_int, c_void_p, c_void_p]),
+                                   c_int, c_void_p, c_void_p, c_void_p]),
     "tpat_attention_bwd_ws_floats": (c_size_t, [c_int, c_int, c_int, c_int]),
     "tpat_bwd_partials_floats": (c_size_t, [c_int]),
     "tpat_inverse_index": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

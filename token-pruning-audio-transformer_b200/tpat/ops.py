@@ -317,19 +317,23 @@ def attention_train(qkv: torch.Tensor, B: int, N: int, H: int, num_extra: int, s
     return out, lse
 
 
-def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, lse: torch.Tensor, B: int, N: int, H: int, impl: int
-                  ) -> torch.Tensor:
-    _req(qkv, name="qkv"); _req(out, qkv.dtype, "out"); _req(d_out, qkv.dtype, "d_out"); _req(lse, torch.float32, "lse")
+def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, lse: torch.Tensor, B: int, N: int, H: int, impl: int,
+                  dbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dqkv; ``dbias`` [3 * H * 64] fp32 (tcgen05 path only) additionally receives += the column sums of dqkv."""
+    _req(qkv, name="qkv")
+    if dbias is not None:
+        _req(dbias, torch.float32, "dbias"); _req(out, qkv.dtype, "out"); _req(d_out, qkv.dtype, "d_out"); _req(lse, torch.float32, "lse")
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(lib.tpat_attention_bwd_ws_floats(B, N, H, 64), device=qkv.device, dtype=torch.float32)
     check(lib.tpat_attention_bwd(qkv.data_ptr(), out.data_ptr(), d_out.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), _DT[qkv.dtype], B, N,
-                                 H, 64, 64 ** -0.5, impl, delta.data_ptr(), _stream()), "tpat_attention_bwd")
+                                 H, 64, 64 ** -0.5, impl, delta.data_ptr(), _ptr(dbias), _stream()), "tpat_attention_bwd")
     return dqkv
 
 
 def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_dtype: torch.dtype, epilogue: int, impl: int,
                residual: Optional[torch.Tensor] = None, want_dact: bool = False, aux: Optional[torch.Tensor] = None,
-               row_scale: Optional[torch.Tensor] = None, rows_per_clip: int = 0, w_kn: bool = False):
+               row_scale: Optional[torch.Tensor] = None, rows_per_clip: int = 0, w_kn: bool = False,
+               colsum_out: Optional[torch.Tensor] = None):
     """tpat_gemm_train: out = epilogue(a @ w.T + bias) with the training extras (GELU-derivative output, GELU-backward
     epilogue, DropPath row scale).  ``w_kn``: ``w`` is [K, N] and out = epilogue(a @ w) (data gradients on the forward
     weight, tcgen05 path only)."""
@@ -350,6 +354,11 @@ def gemm_train(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], o
     if row_scale is not None:
         ex.row_scale, ex.rows_per_clip = row_scale.data_ptr(), rows_per_clip
     ex.w_kn = 1 if w_kn else 0
+    if colsum_out is not None:           # += column sums of the output (DGELU epilogue: the producing Linear's bias gradient)
+        _req(colsum_out, torch.float32, "colsum_out")
+        nws = max(int(lib.tpat_gemm_colsum_ws_floats(M, N)), int(lib.tpat_bwd_partials_floats(N)))
+        ws = torch.empty(nws, device=a.device, dtype=torch.float32)
+        ex.colsum_out, ex.colsum_ws, ex.colsum_ws_floats = colsum_out.data_ptr(), ws.data_ptr(), nws
     check(lib.tpat_gemm_train(a.data_ptr(), _DT[a.dtype], K, w.data_ptr(), _DT[w.dtype], _ptr(bias), out.data_ptr(), _DT[out_dtype], N,
                               _ptr(residual), N if residual is not None else 0, M, N, K, epilogue, impl, ctypes.byref(ex), _stream()),
           "tpat_gemm_train")

@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
 run() { local name=$1 to=$2; shift 2; timeout $to "$@" > gpurun_out/$name.log 2>&1; echo "== $name rc=$? =="; tail -n ${TAILN:-25} gpurun_out/$name.log; }
-TAILN=8 run t60 600 python -m pytest tests/test_gpu_60_train.py -q -m gpu -x
-TAILN=40 run tkb 200 python tools/train_kernel_bench.py
+TAILN=12 run t60 600 python -m pytest tests/test_gpu_60_train.py -q -m gpu -x -s -k "not loop and not graphed"
+TAILN=6 run t60b 600 python -m pytest tests/test_gpu_60_train.py -q -m gpu -x -k "loop or graphed"
+TAILN=12 run tkb 200 python tools/train_kernel_bench.py
 TAILN=3 run bt_graph 200 python bench.py --mode train --steps 10 --warmup 3 --no-e2e
-TAILN=3 run bt_tr 200 env TPAT_DGRAD_TRANSPOSE=1 python bench.py --mode train --steps 10 --warmup 3 --no-e2e
-TAILN=3 run bi_pdl 200 env TPAT_PDL=1 python bench.py --steps 20 --warmup 5
-TAILN=3 run bi 200 python bench.py --steps 20 --warmup 5
+TAILN=3 run bt_nofuse 200 env TPAT_NO_FUSED_COLSUM=1 python bench.py --mode train --steps 10 --warmup 3 --no-e2e
