@@ -30,8 +30,13 @@ constexpr int BT_M = 128;                 // queries per tile = keys per tile
 constexpr int BT_HD = 64;
 constexpr int BT_TILE = BT_M * BT_HD * 2; // 16 KB: one [128][64] bf16 operand tile
 constexpr int BT_PS = 2 * BT_TILE;        // 32 KB: P or dS, two 64-key column blocks of [128 queries][128 B]
-constexpr int BT_THREADS = 320;
-constexpr int BT_SMEM = 1024 + 2 * BT_TILE + 4 * BT_TILE + 2 * BT_PS + 8 * 4096 + 256;
+// CW = softmax / epilogue warps: 8 (thread = query row x 64 keys; default) or 16 (x 32 keys: four warps per SM sub-partition,
+// TPAT_ATTN_BWD_WARPS=16).  Measured equal (0.471 vs 0.474 ms at N = 513, profiles/r02y_attn_bwd_trace_16warps.txt): the warps
+// move through their phases in lock-step (exponentials: MUFU-bound, 1 024 cycles per tile whatever the warp count; P / dS
+// stores: shared-memory-bandwidth-bound, 512 cycles) because the single P / dS buffer is handed over by CTA-wide barriers, so
+// more warps do not overlap one phase with another.
+constexpr int bt_threads(int cw) { return 64 + 32 * cw; }
+constexpr int bt_smem(int cw) { return 1024 + 2 * BT_TILE + 4 * BT_TILE + 2 * BT_PS + cw * 4096 + 256; }
 constexpr uint32_t BT_S = 0, BT_DP = 128, BT_DV = 256, BT_DK = 320, BT_DQ = 384;   // dQ: two buffers, [384,448) and [448,512)
 
 #ifdef TPAT_ATTN_BWD_TRACE
@@ -58,7 +63,8 @@ __device__ __forceinline__ void bt_store_row32(uint8_t* block, int r_local, int 
                    pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]));
 }
 
-__global__ void __launch_bounds__(BT_THREADS, 1)
+template <int CW>
+__global__ void __launch_bounds__(bt_threads(CW), 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dkv,
                         const AttnBwdTcParams p) {
@@ -70,16 +76,19 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   uint8_t* do_s = q_s + 2 * BT_TILE;       // 2 stages
   uint8_t* p_s = do_s + 2 * BT_TILE;
   uint8_t* ds_s = p_s + BT_PS;
-  uint8_t* stg = ds_s + BT_PS;             // 8 x 4 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 8 * 4096);
+  uint8_t* stg = ds_s + BT_PS;             // CW x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + CW * 4096);
+  constexpr int NPART = CW / 4;            // column parts of the 128-key tile per query row: 2 | 4
+  constexpr int COLS = BT_M / NPART;       // keys per thread: 64 | 32
+  constexpr int NCH = COLS / 32;           // 32-column TMEM chunks per thread
   uint64_t* kv_full = bars;                // [1]
   uint64_t* q_full = bars + 1;             // [2]
   uint64_t* qdo_empty = bars + 3;          // [2]
   uint64_t* s_full = bars + 5;             // [1]
-  uint64_t* pds_full = bars + 6;           // [1] 8 arrivals
+  uint64_t* pds_full = bars + 6;           // [1] CW arrivals
   uint64_t* dq_full = bars + 7;            // [1]
   uint64_t* dkv_full = bars + 8;           // [1]
-  uint64_t* sdp_free = bars + 9;           // [1] 8 arrivals: S / dP of the current tile are in registers
+  uint64_t* sdp_free = bars + 9;           // [1] CW arrivals: S / dP of the current tile are in registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   pdl_trigger();
@@ -95,10 +104,10 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     ptx::mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&q_full[s], 1); ptx::mbar_init(&qdo_empty[s], 1); }
     ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(pds_full, 8);
+    ptx::mbar_init(pds_full, CW);
     ptx::mbar_init(dq_full, 1);
     ptx::mbar_init(dkv_full, 1);
-    ptx::mbar_init(sdp_free, 8);
+    ptx::mbar_init(sdp_free, CW);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -197,7 +206,8 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   } else {
     // ===== softmax / epilogue warps =====
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;      // which COLS keys of the tile; half = which 32 columns in the dQ / dK / dV epilogues
+    const int half = part & 1;
     const int r_local = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const float* lse_bh = p.lse + ((size_t)b * p.H + h) * p.N;
@@ -213,7 +223,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     int tn = 0;
     BWD_TRACE(0);
 #endif
-    uint32_t pk_p[32], pk_ds[32];          // this thread's 64 keys of P and dS, packed bf16 pairs
+    uint32_t pk_p[COLS / 2], pk_ds[COLS / 2];      // this thread's keys of P and dS, packed bf16 pairs
     // log-sum-exp and delta of this thread's row of tile i are requested one tile ahead (their global-load latency was
     // ~850 cycles per tile pair on the critical path, profiles/r02m_attn_bwd_trace_v3.txt)
     float lse_nx = 0.f, dlt_nx = 0.f;
@@ -226,7 +236,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     auto compute = [&](int i, float lse_row, float dlt) {
       const int row = i * BT_M + r_local;
       const bool row_ok = row < p.N;
+      BWD_TRACE(10);
       const float lse2 = lse_row * LOG2E;
+#ifdef TPAT_ATTN_BWD_TRACE
+      asm volatile("" :: "f"(lse2), "f"(dlt));      // the scoreboard wait for the prefetched row values lands here
+#endif
       BWD_TRACE(1);
       ptx::mbar_wait(s_full, i & 1);
       ptx::tc_fence_after();
@@ -236,13 +250,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       const float nds = -dlt * p.scale;
       const bool all_ok = (i * BT_M + BT_M <= p.N) && (jt * BT_M + BT_M <= p.N);     // CTA-uniform
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = half * 64 + cc * 32;               // column of the 128-key tile
+      for (int cc = 0; cc < NCH; ++cc) {
+        const int col0 = part * COLS + cc * 32;             // column of the 128-key tile
         uint32_t rs[32], rd[32];
         ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_S + col0, rs);
         ptx::tmem_ld_32x32b_x32(tmem + lane_off + BT_DP + col0, rd);
         ptx::tmem_ld_wait();
-        if (cc == 1) {                       // both chunks are out of tensor memory: S / dP may be overwritten
+        if (cc == NCH - 1) {                 // all chunks are out of tensor memory: S / dP may be overwritten
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(sdp_free);
@@ -271,11 +285,13 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       BWD_TRACE(3);
     };
     auto store_pds = [&]() {
-      uint8_t* prow = p_s + half * BT_TILE + r_local * 128;
-      uint8_t* drow = ds_s + half * BT_TILE + r_local * 128;
+      // the tile is two 64-key column blocks of [128 rows][128 B]; this thread owns COLS / 8 16-byte pieces of one of them
+      const int blk = (part * COLS) >> 6, pc0 = ((part * COLS) & 63) >> 3;
+      uint8_t* prow = p_s + blk * BT_TILE + r_local * 128;
+      uint8_t* drow = ds_s + blk * BT_TILE + r_local * 128;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {        // eight 16-byte pieces = this thread's 64 keys
-        const int sw = (g ^ (r_local & 7)) * 16;
+      for (int g = 0; g < COLS / 8; ++g) {
+        const int sw = ((pc0 + g) ^ (r_local & 7)) * 16;
         *reinterpret_cast<uint4*>(prow + sw) = make_uint4(pk_p[4 * g], pk_p[4 * g + 1], pk_p[4 * g + 2], pk_p[4 * g + 3]);
         *reinterpret_cast<uint4*>(drow + sw) = make_uint4(pk_ds[4 * g], pk_ds[4 * g + 1], pk_ds[4 * g + 2], pk_ds[4 * g + 3]);
       }
@@ -303,6 +319,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     for (int i = 0; i < n_t; ++i) {
       const float lse_i1 = lse_nx, dlt_i1 = dlt_nx;      // tile i + 1's values (requested a whole iteration ago)
       prefetch_row(i + 2);
+      BWD_TRACE(9);
       if (i > 0) {                         // MMAs(i - 1) have retired: P / dS shared memory is free, dQ(i - 1) is complete
         BWD_TRACE(4);
         ptx::mbar_wait(dq_full, (i - 1) & 1);
@@ -314,18 +331,20 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(pds_full);
       BWD_TRACE(6);
-      if (i > 0) dq_epilogue(i - 1);
+      // (16 warps: the two warp groups take the dQ epilogue of alternate tiles)
+      if (i > 0 && (NPART == 2 || (part >> 1) == ((i - 1) & 1))) dq_epilogue(i - 1);
       BWD_TRACE(7);
       if (i + 1 < n_t) compute(i + 1, lse_i1, dlt_i1);
     }
     ptx::mbar_wait(dq_full, (n_t - 1) & 1);
     ptx::tc_fence_after();
-    dq_epilogue(n_t - 1);
+    if (NPART == 2 || (part >> 1) == ((n_t - 1) & 1)) dq_epilogue(n_t - 1);
     BWD_TRACE(8);
 #ifdef TPAT_ATTN_BWD_TRACE
     if (tracing) p.trace[254] = tn;
 #endif
     // ---- dK_j, dV_j: TMEM -> bf16 -> the (dead) K / V tiles -> two TMA stores ----
+    if (part < 2) {                        // (16 warps: the first eight finish the CTA; thread = key row x 32 of the 64 columns)
     ptx::mbar_wait(dkv_full, 0);
     ptx::tc_fence_after();
     {
@@ -365,6 +384,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       for (; r + 3 < r_end; r += 4) { s0 += at(r); s1 += at(r + 1); s2 += at(r + 2); s3 += at(r + 3); }
       for (; r < r_end; ++r) s0 += at(r);
       p.bias_part[((size_t)(b * p.n_t + jt) * 2 + rh) * (size_t)(3 * p.H * BT_HD) + (tsel ? col_v : col_k) + c] = (s0 + s1) + (s2 + s3);
+    }
     }
     if (lane == 0) ptx::tma_store_wait<0>();                    // reduces / stores complete before the CTA retires
   }
@@ -448,12 +468,22 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const 
   // (column-sum partials behind the dQ accumulator; every entry is written by this launch pair, no memset)
   p.bias_part = dbias != nullptr ? dq_acc + (size_t)B * N * H * BT_HD : nullptr;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  static DeviceOnce once;
-  if (once.first()) {
-    TPAT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
-    once.mark();
+  static const int cw = [] { const char* e = getenv("TPAT_ATTN_BWD_WARPS"); return e != nullptr && atoi(e) == 16 ? 16 : 8; }();
+  if (cw == 8) {
+    static DeviceOnce once;
+    if (once.first()) {
+      TPAT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem(8)));
+      once.mark();
+    }
+    TPAT_CUDA(launch_kernel(attention_bwd_tc_kernel<8>, dim3(p.n_t, H, B), dim3(bt_threads(8)), (size_t)bt_smem(8), st, tm_qkv, tm_do, tm_dq, tm_dkv, p));
+  } else {
+    static DeviceOnce once;
+    if (once.first()) {
+      TPAT_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt_smem(16)));
+      once.mark();
+    }
+    TPAT_CUDA(launch_kernel(attention_bwd_tc_kernel<16>, dim3(p.n_t, H, B), dim3(bt_threads(16)), (size_t)bt_smem(16), st, tm_qkv, tm_do, tm_dq, tm_dkv, p));
   }
-  TPAT_CUDA(launch_kernel(attention_bwd_tc_kernel, dim3(p.n_t, H, B), dim3(BT_THREADS), (size_t)BT_SMEM, st, tm_qkv, tm_do, tm_dq, tm_dkv, p));
   const size_t rows = (size_t)B * N;
   const size_t total = rows * (H * BT_HD / 4);
   const int grid = (int)((total + 255) / 256 < (size_t)sm_count() * 16 ? (total + 255) / 256 : (size_t)sm_count() * 16);

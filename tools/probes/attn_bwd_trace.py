@@ -20,6 +20,12 @@ o, lse = ops.attention_train(qkv, B, N, H, 1, _lib.SCORE_NONE, _lib.IMPL_TC)
 for _ in range(3):
     ops.attention_bwd(qkv, o, d_out, lse, B, N, H, _lib.IMPL_TC)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    ops.attention_bwd(qkv, o, d_out, lse, B, N, H, _lib.IMPL_TC)
+e1.record(); torch.cuda.synchronize()
+print(f"TPAT_ATTN_BWD_WARPS={os.environ.get('TPAT_ATTN_BWD_WARPS', '16 (default)')}: {e0.elapsed_time(e1) / 10:.4f} ms per backward (traced build, back to back)")
 lib = ctypes.CDLL(out)
 buf = (ctypes.c_longlong * 512)()
 assert lib.tpat_debug_attn_bwd_trace(buf) == 0
@@ -29,7 +35,7 @@ for i in range(buf[254]):
 for i in range(256, buf[511]):
     ev.append((buf[i] & ((1 << 48) - 1), buf[i] >> 48, "mma"))
 ev.sort()
-names = {0: "start", 1: "wait s_full", 2: "s_full", 3: "P/dS in regs", 4: "wait dq_full", 5: "dq_full", 6: "stored+arrived", 7: "dQ epilogue done", 8: "end",
+names = {0: "start", 1: "wait s_full", 2: "s_full", 3: "P/dS in regs", 4: "wait dq_full", 5: "dq_full", 6: "stored+arrived", 7: "dQ epilogue done", 8: "end", 9: "loop top (prefetch issued)", 10: "compute entry",
          20: "wait pds_full", 21: "pds_full", 22: "MMAs issued"}
 t0, prev = ev[0][0], ev[0][0]
 for t, slot, who in ev:
