@@ -207,7 +207,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           ++ci;
         }
       };
+      const bool red = EPI == TPAT_EPI_BIAS_RESIDUAL && !FOLD && p.red_add != 0;     // grid-uniform
       auto issue_load = [&](int tile, int ci, int b) {   // lane 0 only
+        if (red) return;
         const int m0 = tc_tile_m(p, tile) * 256 + (int)rank * 128 + q * 32;
         ptx::tma_store_wait_read<0>();                   // the store that last read this buffer has drained its smem reads
         ptx::mbar_arrive_expect_tx(&rb[b], 4096);
@@ -248,8 +250,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (nt < tile_end) issue_load(nt, nc, buf ^ 1);
           }
           const int n = item_cols(tile, ci);
-          ptx::mbar_wait(&rb[buf], buf ? rph1 : rph0);
-          if (buf) rph1 ^= 1; else rph0 ^= 1;
+          if (red) {
+            if (lane == 0) ptx::tma_store_wait_read<1>();      // the reduce that last read THIS buffer has drained it
+            __syncwarp();
+          } else {
+            ptx::mbar_wait(&rb[buf], buf ? rph1 : rph0);
+            if (buf) rph1 ^= 1; else rph0 ^= 1;
+          }
           uint8_t* rowp = stg + buf * 4096 + lane * 128;
           // DropPath (training): the branch of clip b is scaled by row_scale[b] (0 or 1 / keep_prob)
           const float sc = (EPI == TPAT_EPI_BIAS_RESIDUAL && p.row_scale != nullptr) ? __ldg(p.row_scale + min(m0 + lane, p.M - 1) / p.rows_per_clip) : 1.0f;
@@ -257,7 +264,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           for (int j = 0; j < 8; ++j) {
             float4* cell = reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4));
             const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 x = *cell;
+            float4 x = red ? make_float4(0.f, 0.f, 0.f, 0.f) : *cell;
             x.x = fmaf(sc, __uint_as_float(r[4 * j]) + bb.x, x.x); x.y = fmaf(sc, __uint_as_float(r[4 * j + 1]) + bb.y, x.y);
             x.z = fmaf(sc, __uint_as_float(r[4 * j + 2]) + bb.z, x.z); x.w = fmaf(sc, __uint_as_float(r[4 * j + 3]) + bb.w, x.w);
             *cell = x;
@@ -278,7 +285,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_2d(&tmap_c, stg + buf * 4096, n, store_row(m0));   // rows >= M are clipped by the tensor map
+            if (red) ptx::tma_reduce_add_2d(&tmap_c, stg + buf * 4096, n, store_row(m0));
+            else ptx::tma_store_2d(&tmap_c, stg + buf * 4096, n, store_row(m0));   // rows >= M are clipped by the tensor map
             ptx::tma_store_commit();
           }
           if constexpr (FOLD && EPI == TPAT_EPI_BIAS_RESIDUAL) {
@@ -324,6 +332,10 @@ static int launch_tc2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
   return 0;
 }
 
+#ifndef TPAT_RES_REDUCE_DEFAULT
+#define TPAT_RES_REDUCE_DEFAULT 0
+#endif
+
 int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ldc, int M, int N, int K,
              const EpiParams& ep, cudaStream_t st) {
   CUtensorMap ta, tw;
@@ -366,7 +378,12 @@ int gemm_tc2(const void* A, int lda, const void* W, void* C, int c_dtype, int ld
       // Long-K GEMMs (fc2, K = 3072) hide the register-path epilogue behind the main loop and prefer the fifth
       // pipeline stage; short-K ones (proj, K = 768) are bound by the residual read-modify-write and use the
       // TMA-fed epilogue (measured r01: proj 0.081 -> 0.064 ms, fc2 0.129 -> 0.140 ms with it).
-      if (K > 1536) {
+      // In place (C == R, the forward's residual stream) the read-modify-write can be left to L2: TMA reduce-add of
+      // acc + bias blocks (TPAT_GEMM_RES_REDUCE = proj | all | 0; bit-identical: x + v is the same fp32 addition)
+      static const int red_mode = [] { const char* e = getenv("TPAT_GEMM_RES_REDUCE"); return e == nullptr ? TPAT_RES_REDUCE_DEFAULT : (e[0] == 'a' ? 2 : (e[0] == 'p' ? 1 : 0)); }();
+      const bool can_red = ep.residual == C && ep.ldr == ldc && p.xb == nullptr && ep.row_scale == nullptr;
+      p.red_add = can_red && (red_mode == 2 || (red_mode == 1 && K <= 1536));
+      if (K > 1536 && !p.red_add) {
         CUtensorMap tx = ta;
         static const bool pf_res = getenv("TPAT_GEMM_RES_L2_PREFETCH") != nullptr;     // (A/B switch)
         if (pf_res && N % 256 == 0) {

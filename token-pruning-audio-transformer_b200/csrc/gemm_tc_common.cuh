@@ -41,6 +41,8 @@ struct TcGemmParams {
   int pf_l2;        // 1: tmap_r covers the tensor the epilogue reads with plain loads (residual / saved GELU derivative);
                     //    the TMA warp prefetches each tile's 128 x 256 block into L2 when it starts loading the tile
   float* cs_part;   // DGELU: partial column sums of the output, row (m0 / 32) of [.][N], written by every epilogue warp
+  int red_add;      // 1 (TMA residual epilogue, C == R in place, no row scale): blocks of acc + bias are ADDED to C by TMA reduce
+                    //    operations in L2 -- the residual never travels through the SM
   int w_kn;         // 1: W is [K, N] row-major; B tiles are 64 x 64 boxes ([64 k rows][128 B of n]), MN-major descriptors
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
 };
