@@ -411,18 +411,20 @@ dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqk
   }
 }
 
-// the same per (clip, 128-row tile) with the column sums of the fp32 rows (q columns of the qkv bias gradient): thread =
-// (16-byte column group, row phase); partial rows as attention_bwd_tc_kernel writes them
+// the same per (clip, 64-row half of a 128-row tile) with the column sums of the fp32 rows (q columns of the qkv bias
+// gradient): thread = (16-byte column group, row phase), the two phases combined through shared memory; partial rows as
+// attention_bwd_tc_kernel writes them (one per tile half)
 __global__ void __launch_bounds__(1024)
 dq_convert_sum_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ part, int N, int HD, int n_t) {
+  __shared__ float4 red[512];
   pdl_trigger();
   pdl_wait();
-  const int jt = blockIdx.x, b = blockIdx.y;
+  const int jt = blockIdx.x, b = blockIdx.y, rh = blockIdx.z;
   const int c4n = HD / 4;
   const int c4 = threadIdx.x % c4n, ph = threadIdx.x / c4n;
-  const int r1 = min(N, jt * 128 + 128);
+  const int r1 = min(N, jt * 128 + rh * 64 + 64);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  int r = jt * 128 + ph;
+  int r = jt * 128 + rh * 64 + ph;
   auto one = [&](int rr, const float4& v) {
     reinterpret_cast<uint2*>(dqkv + ((size_t)b * N + rr) * 3 * HD)[c4] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -435,7 +437,12 @@ dq_convert_sum_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__
     for (int k = 0; k < 4; ++k) one(r + 2 * k, v[k]);
   }
   for (; r < r1; r += 2) one(r, __ldg(reinterpret_cast<const float4*>(acc + ((size_t)b * N + r) * HD) + c4));
-  reinterpret_cast<float4*>(part + ((size_t)(b * n_t + jt) * 2 + ph) * (size_t)(3 * HD))[c4] = s;
+  if (ph == 1) red[c4] = s;
+  __syncthreads();
+  if (ph == 0) {
+    const float4 o = red[c4];
+    reinterpret_cast<float4*>(part + ((size_t)(b * n_t + jt) * 2 + rh) * (size_t)(3 * HD))[c4] = make_float4(s.x + o.x, s.y + o.y, s.z + o.z, s.w + o.w);
+  }
 }
 
 int attention_bwd_delta_bf16(const void* out, const void* d_out, float* delta, int B, int N, int H, cudaStream_t st);
@@ -489,7 +496,7 @@ int attention_bwd_tc(const void* qkv, const void* out, const void* d_out, const 
   const int grid = (int)((total + 255) / 256 < (size_t)sm_count() * 16 ? (total + 255) / 256 : (size_t)sm_count() * 16);
   if (dbias != nullptr) {
     TPAT_CHECK(H * BT_HD / 4 * 2 <= 1024, "tpat_attention_bwd: dbias supports up to 32 heads");
-    TPAT_CUDA(launch_kernel(dq_convert_sum_kernel, dim3(p.n_t, B), dim3(H * BT_HD / 4 * 2), 0, st, (const float*)dq_acc, (__nv_bfloat16*)dqkv,
+    TPAT_CUDA(launch_kernel(dq_convert_sum_kernel, dim3(p.n_t, B, 2), dim3(H * BT_HD / 4 * 2), 0, st, (const float*)dq_acc, (__nv_bfloat16*)dqkv,
                             p.bias_part, N, H * BT_HD, p.n_t));
     TPAT_LAUNCH_CHECK();
     return finish_colsum_partials(p.bias_part, B * p.n_t * 2, 3 * H * BT_HD, dbias, st);

@@ -26,12 +26,14 @@ dw = torch.zeros(Dh, D, device=dev)
 spec = torch.randn(B, 1024, 128, device=dev) * 0.5
 idx = torch.stack([torch.randperm(N - 1, device=dev)[:359] for _ in range(B)])
 partial = torch.rand(B, 12 * 5, N, device=dev)
+dbq = torch.zeros(3 * D, device=dev); db1 = torch.zeros(Dh, device=dev)
+w1t = (torch.randn(D, Dh, device=dev) * 0.02).to(bf)        # a [K = 768, N = 3072] weight for the w_kn GELU-backward GEMM
 
 
 def one_pass():
     out, lse = ops.attention_train(qkv, B, N, H, 1, _lib.SCORE_NONE, _lib.IMPL_TC)          # attention_tc_kernel<0,0>
     ops.attention(qkv, B, N, H, 1, _lib.SCORE_COLMEAN, _lib.IMPL_TC)                        # attention_tc_kernel<1,0>
-    ops.attention_bwd(qkv, out, d_out, lse, B, N, H, _lib.IMPL_TC)                          # delta, attention_bwd_tc, dq_convert
+    ops.attention_bwd(qkv, out, d_out, lse, B, N, H, _lib.IMPL_TC, dbias=dbq)               # delta8, attention_bwd_tc<8>, dq_convert_sum, finish
     ops.gemm_wgrad(dh, y, out=dw)                                                           # gemm_wgrad_tc_kernel
     ops.gemm(y, wq, bq, bf, _lib.EPI_BIAS, _lib.IMPL_TC)                                    # qkv
     act, dact = ops.gemm_train(y, w1, b1, bf, _lib.EPI_BIAS_GELU, _lib.IMPL_TC, want_dact=True)   # fc1 + GELU (+ derivative)
@@ -39,7 +41,8 @@ def one_pass():
     xr = x32.view(M, D).clone()
     ops.gemm(act, w2, b2, torch.float32, _lib.EPI_BIAS_RESIDUAL, _lib.IMPL_TC, residual=xr, out=xr)     # fc2 + residual
     ops.gemm(y, wp, b2, torch.float32, _lib.EPI_BIAS_RESIDUAL, _lib.IMPL_TC, residual=xr, out=xr)       # proj + residual
-    ops.gemm_train(y, w1.T.contiguous()[:D].contiguous() if False else w1, None, bf, _lib.EPI_DGELU, _lib.IMPL_TC, aux=dact)  # dgrad + GELU'
+    ops.gemm_train(y, w1t, None, bf, _lib.EPI_DGELU, _lib.IMPL_TC, aux=dact, w_kn=True, colsum_out=db1)   # dgrad on the forward-layout weight + GELU' + fc1 bias gradient
+    ops.gemm_train(dh, w1, None, bf, _lib.EPI_BIAS, _lib.IMPL_TC, w_kn=True)                # plain dgrad (fc1): dX = dh W1, W1 [out, in] as it is
     ops.row_bwd(dy32, x32, gam, gu, bf)                                                     # row_bwd_kernel
     ops.colsum(dh)                                                                          # colsum_kernel
     ops.layernorm(x32, gam, bet, 1e-6, bf)                                                  # layernorm_kernel

@@ -17,12 +17,12 @@ METRICS = [
     ("gpu__time_duration.sum", "us"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU %"),
-    ("smsp__issue_active.avg.pct", "issue %"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
     ("launch__registers_per_thread", "regs"),
     ("dram__bytes_read.sum", "DRAM rd"),
     ("dram__bytes_write.sum", "DRAM wr"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
 ]
 
