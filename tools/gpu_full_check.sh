@@ -4,3 +4,5 @@ timeout 2400 python -m pytest tests/ -x -q -m gpu > gpurun_out/pytest_gpu.log 2>
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_default.log | cut -c1-400
 timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-300
+timeout 600 python bench.py --mode train --steps 10 --warmup 3 > gpurun_out/bench_train.log 2>&1; echo "train rc=$?"; tail -1 gpurun_out/bench_train.log | cut -c1-200
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager-baseline > gpurun_out/bench_20.log 2>&1; echo "b20 rc=$?"; tail -1 gpurun_out/bench_20.log | cut -c1-200
