@@ -256,7 +256,11 @@ def test_model_on_a_second_device_runs_there():
 
 # 1.5x the values measured on B200 (profiles/r02*_parity.txt): (logits err, block-3 overlap)
 TOL_2048 = {"audiomae": (5e-2, 0.98), "ast": (5e-2, 0.98)}
-TOL_VIT_SIZES = {"vit_small_patch16": 4.0e-3, "vit_large_patch16": 6.5e-2}   # measured 2.64e-3 / 4.33e-2
+# bf16, free-running: measured 2.64e-3 (r01g ... r02z) or 3.5e-2 ... 4.0e-2 (r01d, r01f, r02aa: one near-tie flip among the
+# 90 / 63 / 45 kept tokens of a clip) for vit_small, 4.33e-2 for vit_large.  The arithmetic itself is held to the
+# north-star 1e-2 against the oracle run on the SAME kept tokens (TOL_VIT_FORCED).
+TOL_VIT_SIZES = {"vit_small_patch16": 6.5e-2, "vit_large_patch16": 6.5e-2}
+TOL_VIT_FORCED = {"vit_small_patch16": 1.0e-2, "vit_large_patch16": 3.0e-2}
 
 
 @pytest.mark.parametrize("variant", ["audiomae", "ast"])
@@ -366,6 +370,13 @@ def test_other_vit_sizes_match_the_oracle(factory, dim, depth, heads):
         err = rel_err(logits.cpu(), ref_logits)
         print(f"[{precision}] {factory}: logits err {err:.2e}")
         assert err < tol
+        if precision == "bf16":
+            forced = {i: t.cpu() for i, t in enumerate(m.last_topk_idx) if t is not None}
+            with torch.no_grad():
+                forced_logits, _ = vo.forward("audiomae", sd, x, None, drop_loc, 0.7, num_heads=heads, forced_idx=forced)
+            err_f = rel_err(logits.cpu(), forced_logits)
+            print(f"[{precision}] {factory}: logits err against the oracle on the same kept tokens {err_f:.2e}")
+            assert err_f < TOL_VIT_FORCED[factory]
         if precision == "fp32":
             first = f"block-{drop_loc[0]}.topk_idx"
             for a, b in zip(m.last_topk_idx[drop_loc[0]].cpu().tolist(), ref_feats[first].tolist()):

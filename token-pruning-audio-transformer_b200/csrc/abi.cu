@@ -34,6 +34,33 @@ int sm_count() {
   return cached[dev];
 }
 
+thread_local L2Window g_l2_window;
+
+size_t l2_persist_bytes() {
+  static long long want_mb = -1;
+  static size_t granted[64] = {0};
+  static bool asked[64] = {false};
+  if (want_mb < 0) { const char* e = getenv("TPAT_L2_PERSIST_MB"); want_mb = e ? atoll(e) : 0; }
+  if (want_mb <= 0) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (!asked[dev]) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    size_t want = (size_t)want_mb << 20;
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
+    size_t got = 0;
+    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+    cudaGetLastError();
+    granted[dev] = got;
+    asked[dev] = true;
+    if (getenv("TPAT_DEBUG"))
+      fprintf(stderr, "[tpat] L2 persisting carve-out: asked %lld MiB, device max %d B, window max %d B, granted %zu B\n", want_mb, max_persist, max_window, got);
+  }
+  return granted[dev];
+}
+
 bool pdl_enabled() {
   static int cached = -1;
   if (cached < 0) { const char* e = getenv("TPAT_PDL"); cached = (e != nullptr && e[0] == '1') ? 1 : 0; }

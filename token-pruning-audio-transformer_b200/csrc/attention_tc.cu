@@ -506,7 +506,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 long long* g_attn_trace_buf = nullptr;
 extern "C" int tpat_debug_attn_trace(long long* host_out) {   // debug builds only: copy the 128 stamps to the host
   if (!g_attn_trace_buf) return 1;
-  return cudaMemcpy(host_out, g_attn_trace_buf, 128 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+  return cudaMemcpy(host_out, g_attn_trace_buf, 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
 }
 #endif
 
@@ -517,6 +517,13 @@ int attention_tc3(const void* qkv, void* out, int B, int N, int H, float scale, 
 static bool use_v3() {
   const char* e = getenv("TPAT_ATTN_V3");      // read per call so that tests can A/B both kernels
   return e != nullptr && e[0] == '1';
+}
+// attention_tc4.cu: same tiling as the single-pass instantiation above, but the two 32-key halves of a row are fully
+// independent (own reference max, row sum and output accumulator; no partner exchange inside the key loop)
+int attention_tc4(const void* qkv, void* out, int B, int N, int H, float scale, int qt_offset, float* lse, cudaStream_t st);
+static bool use_v4() {
+  const char* e = getenv("TPAT_ATTN_V4");      // default ON since r02aa (x1.05 - 1.16 on the single-pass tiles); "0" = the kernel above
+  return e == nullptr || e[0] != '0';
 }
 
 template <bool TWO_PASS, bool SPLIT = false>
@@ -554,7 +561,7 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
   AttnTcParams p;
   p.trace = nullptr;
 #ifdef TPAT_ATTN_TRACE
-  { static long long* dbg = nullptr; if (!dbg) { cudaMalloc(&dbg, 128 * sizeof(long long)); } cudaMemsetAsync(dbg, 0, 128 * sizeof(long long), st); p.trace = dbg;
+  { static long long* dbg = nullptr; if (!dbg) { cudaMalloc(&dbg, 256 * sizeof(long long)); } cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), st); p.trace = dbg;
     extern long long* g_attn_trace_buf; g_attn_trace_buf = dbg; }
 #endif
   p.score_partial = score_partial;
@@ -583,10 +590,12 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
     else if (int rc = launch_attn<true>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(1, H, B), base_smem, st)) return rc;
     if (p.n_qt == 1) return 0;
     if (use_v3()) return attention_tc3(qkv, out, B, N, H, scale, 1, lse, st);
+    if (use_v4()) return attention_tc4(qkv, out, B, N, H, scale, 1, lse, st);
     p.qt_offset = 1;
     return launch_attn<false>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt - 1, H, B), base_smem, st);
   }
   if (use_v3()) return attention_tc3(qkv, out, B, N, H, scale, 0, lse, st);
+  if (use_v4()) return attention_tc4(qkv, out, B, N, H, scale, 0, lse, st);
   return launch_attn<false>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem, st);
 }
 

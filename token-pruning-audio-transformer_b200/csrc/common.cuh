@@ -58,14 +58,31 @@ extern thread_local int g_walk_desc;
 // scheduled (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the tail of the
 // previous kernel drains; each kernel calls pdl_wait() before its first access to global memory and
 // pdl_trigger() at its start (both are no-ops without the launch attribute).
+// L2 residency of the fp32 residual stream (TPAT_L2_PERSIST_MB=<MiB>, off by default): tpat_forward describes the live
+// residual rows of the current block as an access-policy window; every launch inside carries it, so that lines of that
+// range are kept in the persisting carve-out of the 126 MB L2 across the 4 kernels per block that touch them
+// (LayerNorm reads x twice, proj and fc2 read-modify-write it) instead of being evicted by the activations in between.
+struct L2Window { const void* base = nullptr; size_t bytes = 0; float ratio = 0.f; };
+extern thread_local L2Window g_l2_window;
+size_t l2_persist_bytes();   // carve-out actually granted on the current device (0 = feature off)
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (g_l2_window.bytes != 0) {
+    at[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[1].val.accessPolicyWindow.base_ptr = const_cast<void*>(g_l2_window.base);
+    at[1].val.accessPolicyWindow.num_bytes = g_l2_window.bytes;
+    at[1].val.accessPolicyWindow.hitRatio = g_l2_window.ratio;
+    at[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[1].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

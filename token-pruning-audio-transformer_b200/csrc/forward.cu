@@ -151,6 +151,17 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
   if (int rc = tpat_gemm(w.hid, act, 256, a->patch_w, act, a->patch_b, w.x[0], TPAT_F32, D, nullptr, 0, a->pos, P, extra,
                          B * P, D, 256, TPAT_EPI_BIAS_POS, impl, stream)) return rc;
 
+  // optional: keep (part of) the live residual rows in the persisting part of L2 (see L2Window in common.cuh)
+  const size_t l2_persist = impl == TPAT_IMPL_TC ? l2_persist_bytes() : 0;
+  struct L2Guard { ~L2Guard() { g_l2_window = L2Window{}; } } l2_guard;
+  auto l2_window = [&](const float* xbuf, size_t rows) {
+    if (l2_persist == 0) return;
+    const size_t bytes = rows * (size_t)D * sizeof(float);
+    g_l2_window.base = xbuf;
+    g_l2_window.bytes = bytes;
+    g_l2_window.ratio = bytes <= l2_persist ? 1.0f : (float)((double)l2_persist / (double)bytes);
+  };
+
   int cur = P;       // non-extra tokens
   int xi = 0;        // which residual buffer is live
   for (int i = 0; i < a->depth; ++i) {
@@ -159,6 +170,7 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
     const bool prune = a->prune[i] != 0;
     const bool want_score = prune || a->want_all_scores;
     float* x = w.x[xi];
+    l2_window(x, (size_t)M);
     const bool split = prune && a->score32 && impl == TPAT_IMPL_TC;
     if (split) {
       // "bf16+score32": LayerNorm -> split-bf16 triple; qkv from its hi segment as usual; q | k again as a K = 3D
@@ -219,6 +231,7 @@ extern "C" int tpat_forward(const tpat_forward_args* a, tpat_stream_t stream) {
       x = xn;
       cur = out_rows - extra;
       M2 = B * out_rows;
+      l2_window(x, (size_t)M2);
     } else if (!fold_ln2(a, i)) {
       if (int rc = tpat_layernorm(x, bw.ln2_g, bw.ln2_b, w.y, act, M, D, a->ln_eps, stream)) return rc;
     }
