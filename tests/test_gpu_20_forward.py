@@ -260,7 +260,7 @@ TOL_2048 = {"audiomae": (5e-2, 0.98), "ast": (5e-2, 0.98)}
 # 90 / 63 / 45 kept tokens of a clip) for vit_small, 4.33e-2 for vit_large.  The arithmetic itself is held to the
 # north-star 1e-2 against the oracle run on the SAME kept tokens (TOL_VIT_FORCED).
 TOL_VIT_SIZES = {"vit_small_patch16": 6.5e-2, "vit_large_patch16": 6.5e-2}
-TOL_VIT_FORCED = {"vit_small_patch16": 1.0e-2, "vit_large_patch16": 3.0e-2}
+TOL_VIT_FORCED = {"vit_small_patch16": 1.0e-2, "vit_large_patch16": 1.0e-2}   # measured 2.50e-3 / 6.68e-3 (r02aa)
 
 
 @pytest.mark.parametrize("variant", ["audiomae", "ast"])

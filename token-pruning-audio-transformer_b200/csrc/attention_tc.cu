@@ -176,7 +176,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       auto issue_s = [&]() {
         const int sb = sidx % AT_SBUF;
         ptx::mbar_wait(&kv_full[slot], phase);
-        ptx::mbar_wait(&s_empty[sb], ((sidx / AT_SBUF) & 1) ^ 1);
+        // Main pass of the two-pass tiles, from its third block on: S(j) reuses the buffer of S(j-2), which every softmax
+        // warp had read before it arrived on p_full(j-2) -- and this thread waited for that before P(j-2).V(j-2), i.e.
+        // before it got here.  The softmax warps therefore do not signal s_empty in the main pass at all; the first two
+        // main-pass tiles wait for the last two pass-1 reads.
+        if (!TWO_PASS || sidx < nb + 2) ptx::mbar_wait(&s_empty[sb], ((sidx / AT_SBUF) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint64_t k_desc = ptx::smem_desc_sw128(ptx::smem_u32(kv_s + slot * SLOT_BYTES), 16, 1024);
 #pragma unroll
@@ -314,6 +318,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (TWO_PASS && p.lse != nullptr && half == 0 && warp_live && row < p.N)
       p.lse[((size_t)b * p.H + h) * p.N + row] = off * 0.69314718055994531f;
     const float row_w = (row >= p.num_extra && row < p.N) ? 1.0f : 0.f;
+    const bool mask_rows = q0 + quarter * 32 < p.num_extra || q0 + quarter * 32 + 32 > p.N;
     const bool cls_writer = TWO_PASS && (p.score_mode == TPAT_SCORE_CLS_ROW) && (row == 0);
     float* colsum_w = colsum_s + (size_t)quarter * nb * AT_BK;
     float l2a = 0.f, l2b = 0.f, l2c = 0.f, l2d = 0.f;
@@ -329,13 +334,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (!warp_live) {
         if (TWO_PASS && p.score_mode == TPAT_SCORE_COLMEAN)     // this warp's rows contribute nothing to the column sums
           colsum_w[j * AT_BK + half * 32 + lane] = 0.f;
-        release_s(sb);                                   // (fence::before_thread_sync + __syncwarp inside)
+        if (!TWO_PASS) release_s(sb);                    // (fence::before_thread_sync + __syncwarp inside)
+        else { ptx::tc_fence_before(); __syncwarp(); }
         if (lane == 0) ptx::mbar_arrive(&p_full[pb]);
         continue;
       }
       uint32_t r[32];
       if (vh > 0) { ptx::tmem_ld_32x32b_x32(tmem_base + lane_off + sb * AT_BK + half * 32, r); ptx::tmem_ld_wait(); }
-      release_s(sb);
+      if (!TWO_PASS) release_s(sb);                      // (two-pass main pass: p_full doubles as "S read", see issue_s)
       if (vh > 0) mask_tail(vh, r);
       ATTN_TRACE(4);
       if (!TWO_PASS) {
@@ -383,8 +389,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (TWO_PASS) {
           if (p.score_mode == TPAT_SCORE_COLMEAN) {
             // column sums over this warp's 32 rows: butterfly transpose-reduce, lane i ends with column col0+i
+            if (mask_rows) {                              // warp-uniform: only warps that hold a cls row or rows >= N
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= row_w;
+              for (int i = 0; i < 32; ++i) v[i] *= row_w;
+            }
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) {
               const bool upper = (lane & o) != 0;
