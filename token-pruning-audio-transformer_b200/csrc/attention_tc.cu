@@ -529,6 +529,12 @@ static bool use_v3() {
 // attention_tc4.cu: same tiling as the single-pass instantiation above, but the two 32-key halves of a row are fully
 // independent (own reference max, row sum and output accumulator; no partner exchange inside the key loop)
 int attention_tc4(const void* qkv, void* out, int B, int N, int H, float scale, int qt_offset, float* lse, cudaStream_t st);
+// attention_tc5.cu: the same kernel made persistent (two resident CTAs per SM walk the (clip, head, tile) items)
+int attention_tc5(const void* qkv, void* out, int B, int N, int H, float scale, int qt_offset, float* lse, cudaStream_t st);
+static bool use_v5() {
+  const char* e = getenv("TPAT_ATTN_V5");
+  return e != nullptr && e[0] == '1';
+}
 static bool use_v4() {
   const char* e = getenv("TPAT_ATTN_V4");      // default ON since r02aa (x1.05 - 1.16 on the single-pass tiles); "0" = the kernel above
   return e == nullptr || e[0] != '0';
@@ -598,11 +604,13 @@ int attention_tc(const void* qkv, void* out, float* score_partial, int score_mod
     else if (int rc = launch_attn<true>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(1, H, B), base_smem, st)) return rc;
     if (p.n_qt == 1) return 0;
     if (use_v3()) return attention_tc3(qkv, out, B, N, H, scale, 1, lse, st);
+    if (use_v5()) return attention_tc5(qkv, out, B, N, H, scale, 1, lse, st);
     if (use_v4()) return attention_tc4(qkv, out, B, N, H, scale, 1, lse, st);
     p.qt_offset = 1;
     return launch_attn<false>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt - 1, H, B), base_smem, st);
   }
   if (use_v3()) return attention_tc3(qkv, out, B, N, H, scale, 0, lse, st);
+  if (use_v5()) return attention_tc5(qkv, out, B, N, H, scale, 0, lse, st);
   if (use_v4()) return attention_tc4(qkv, out, B, N, H, scale, 0, lse, st);
   return launch_attn<false>(tm_q, tm_kv, tm_kv, tm_o, p, dim3(p.n_qt, H, B), base_smem, st);
 }

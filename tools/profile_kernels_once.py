@@ -31,7 +31,7 @@ w1t = (torch.randn(D, Dh, device=dev) * 0.02).to(bf)        # a [K = 768, N = 30
 
 
 def one_pass():
-    out, lse = ops.attention_train(qkv, B, N, H, 1, _lib.SCORE_NONE, _lib.IMPL_TC)          # attention_tc_kernel<0,0>
+    out, lse = ops.attention_train(qkv, B, N, H, 1, _lib.SCORE_NONE, _lib.IMPL_TC)          # attention_tc4_kernel (single-pass tiles; attention_tc_kernel<0,0> with TPAT_ATTN_V4=0)
     ops.attention(qkv, B, N, H, 1, _lib.SCORE_COLMEAN, _lib.IMPL_TC)                        # attention_tc_kernel<1,0>
     ops.attention_bwd(qkv, out, d_out, lse, B, N, H, _lib.IMPL_TC, dbias=dbq)               # delta8, attention_bwd_tc<8>, dq_convert_sum, finish
     ops.gemm_wgrad(dh, y, out=dw)                                                           # gemm_wgrad_tc_kernel

@@ -83,7 +83,7 @@ def fwd(csv_path, out):
         "gemm_fc1_tcgen05": {"dram_bytes": first(lambda n: "gemm_tc2_kernel<1" in n)},
         "gemm_fc2_tcgen05": {"dram_bytes": first(lambda n: "gemm_tc2_kernel<2, float, 0" in n)},
         "layernorm": {"dram_bytes": first(lambda n: "layernorm_kernel" in n and "gather" not in n)},
-        "attention_tcgen05": {"dram_bytes": first(lambda n: "attention_tc_kernel<0" in n)},
+        "attention_tcgen05": {"dram_bytes": first(lambda n: "attention_tc4_kernel" in n or "attention_tc_kernel<0" in n)},
     }
     json.dump(res, open(out, "w"), indent=1)
     print(json.dumps(res, indent=1))
