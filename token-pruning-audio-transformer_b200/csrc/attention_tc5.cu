@@ -38,7 +38,15 @@ constexpr float A5_RESCALE_SUM = 18446744073709551616.0f;   // 2^64: a block sum
 // The non-persistent kernel gets that de-phasing for free from the block scheduler.
 __device__ unsigned int g_a5_ticket[1024];
 
+#ifdef TPAT_ATTN_TRACE
+// debug builds only: clock stamps of one softmax thread ([0, 120), count at [127]) and of the MMA thread ([128, 250), count at [255])
+#define A5_TRACE(slot) do { if (tracing && trace_n < 120) p.trace[trace_base + trace_n++] = clock64() - t_start + ((long long)(slot) << 48); } while (0)
+#else
+#define A5_TRACE(slot) do { } while (0)
+#endif
+
 struct Attn5Params {
+  long long* trace;      // TPAT_ATTN_TRACE builds only
   float* lse;            // optional [B, H, N] natural-log sum of exp(scale * s) per query row (training)
   int B, N, H, nb, qt_offset, n_tiles, n_items;
   int stagger;           // cycles the second CTA of an SM waits before its first item (0 = off)
@@ -180,7 +188,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::tc_commit(&s_full[sb]);
         if (++slot == A5_SLOTS) { slot = 0; phase ^= 1; }
       };
+#ifdef TPAT_ATTN_TRACE
+      const bool tracing = p.trace != nullptr && blockIdx.x == 100;
+      int trace_n = 0; const int trace_base = 128;
+      const long long t_start = clock64();
+      if (tracing) p.trace[254] = t_start;
+#endif
       ptx::mbar_wait(&q_full[0], 0);
+      A5_TRACE(20);
       issue_s(0, 0);
       int n = 0;
       for (int it = it0; it < p.n_items; it += it_step, ++n) {
@@ -192,9 +207,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             issue_s(g + 1, (n + 1) & 1);
           }
           const int sb = g & 1;
+          A5_TRACE(21);
           ptx::mbar_wait(&kv_full[slot], phase);                 // V_j
           ptx::mbar_wait(&p_full[sb], (g >> 1) & 1);             // P_j written by the softmax warps (over S_j)
-          if (j == 0 && n > 0) ptx::mbar_wait(o_empty, (n - 1) & 1);   // the previous item's accumulators were read out
+          A5_TRACE(22);
+          if (j == 0 && n > 0) { ptx::mbar_wait(o_empty, (n - 1) & 1); A5_TRACE(23); }   // the previous item's accumulators were read out
           ptx::tc_fence_after();
           const uint32_t v_addr = ptx::smem_u32(kv_s + slot * A5_KV_BYTES);
           const int valid = min(A5_BK, p.N - j * A5_BK);         // keys of this block that exist
@@ -214,6 +231,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           if (++slot == A5_SLOTS) { slot = 0; phase ^= 1; }
         }
       }
+#ifdef TPAT_ATTN_TRACE
+      if (tracing) p.trace[255] = trace_n;
+#endif
     }
   } else {
     // ===== softmax / epilogue warps: TMEM lane quarter = warp % 4, thread = (query row, 32-key half) =====
@@ -240,8 +260,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ptx::mbar_arrive(&q_empty[qb]);
     };
 
+#ifdef TPAT_ATTN_TRACE
+    const bool tracing = p.trace != nullptr && blockIdx.x == 100 && threadIdx.x == 64;
+    int trace_n = 0; const int trace_base = 0;
+    long long t_start = 0;
+    if (tracing) { t_start = clock64(); p.trace[126] = t_start; }
+#endif
     int g = 0, n = 0;
     for (int it = it0; it < p.n_items; it += it_step, ++n) {
+      A5_TRACE(1);
       // A warp whose 32 query rows all lie beyond N only keeps the barrier protocol going.
       const bool warp_live = a5_item(p, it).q0 + quarter * 32 < p.N;
       float m_ref = -INFINITY;                           // this half's reference max (raw score units)
@@ -251,6 +278,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int sb = g & 1;
         ptx::mbar_wait(&s_full[sb], (g >> 1) & 1);
         ptx::tc_fence_after();
+        A5_TRACE(3);
         const int vh = p.N - j * A5_BK - half * 32;      // valid columns in this thread's half (may be <= 0: no MMA k-step reads them)
         if (warp_live && vh > 0) {
           const uint32_t t_sp = tmem_base + lane_off + sb * A5_BK + half * 32;   // own 32 score columns; P over the first 16
@@ -280,6 +308,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             bsum = (a0 + a1) + (a2 + a3);
           };
           emit();
+          A5_TRACE(5);
           // Lazy rescale (see attention_tc4.cu): sum-triggered, warp-collective slow path, f = 1 for rows that do not need it
           const bool need = j > 0 && !(bsum <= A5_RESCALE_SUM);
           if (__any_sync(0xffffffffu, need)) {
@@ -306,6 +335,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[sb]);
+        A5_TRACE(7);
         if (storer && j == 0 && n > 0) retire_store((n - 1) & 1);   // the previous item's O store has long finished reading its tile
       }
 
@@ -329,8 +359,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           p.lse[((size_t)im.b * p.H + im.h) * p.N + row] = fmaf(m, c, __log2f(l_tot)) * 0.69314718055994531f;
       }
       // ---- epilogue: (w_a O_a + w_b O_b) / l -> bf16 -> swizzled smem tile (the item's dead Q tile) -> one TMA store ----
+      A5_TRACE(9);
       ptx::mbar_wait(o_full, n & 1);       // every P.V of the item retired (and every S: the Q tile is dead)
       ptx::tc_fence_after();
+      A5_TRACE(10);
       float v[32];
       if (warp_live) {
         // this thread writes output columns [32 half, 32 half + 32) of its row: the same columns of both accumulators
@@ -353,15 +385,21 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(o_empty);          // the next item's first P.V may overwrite the accumulators
+      A5_TRACE(12);
       uint8_t* stage = q_s + (n & 1) * A5_Q_BYTES;
       if (warp_live) a5_store_row32(stage + r_local * 128, half, r_local, v);
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      A5_TRACE(13);
       if (storer) {
         ptx::tma_store_3d(&tmap_o, stage, im.h * A5_HD, im.q0, im.b);   // rows >= N are clipped by the tensor map
         ptx::tma_store_commit();
       }
+      A5_TRACE(11);
     }
+#ifdef TPAT_ATTN_TRACE
+    if (tracing) p.trace[127] = trace_n;
+#endif
     if (storer && n > 0) retire_store((n - 1) & 1);      // smem must outlive the last bulk store's reads
   }
 
@@ -379,6 +417,10 @@ int attention_tc5(const void* qkv, void* out, int B, int N, int H, float scale, 
   if (int rc = encode_tmap_3d_qkv(&tm_kv, qkv, B, N, 3 * H * A5_HD, A5_BK)) return rc;
   if (int rc = encode_tmap_3d_qkv(&tm_o, out, B, N, H * A5_HD, A5_BM)) return rc;
   Attn5Params p;
+  p.trace = nullptr;
+#ifdef TPAT_ATTN_TRACE
+  { extern long long* g_attn_trace_buf; p.trace = g_attn_trace_buf; }
+#endif
   p.lse = lse; p.B = B; p.N = N; p.H = H;
   p.nb = (N + A5_BK - 1) / A5_BK;
   p.qt_offset = qt_offset;
@@ -389,8 +431,8 @@ int attention_tc5(const void* qkv, void* out, int B, int N, int H, float scale, 
   p.scale_log2 = scale * 1.4426950408889634f;
   int grid = 2 * sm_count();
   if (grid > p.n_items) grid = p.n_items;
-  // start offset of every SM's second CTA: TPAT_A5_STAGGER_PCT percent (default 50) of one item's ~1300 (nb + 1) cycles
-  static const int stagger_pct = [] { const char* e = getenv("TPAT_A5_STAGGER_PCT"); return e ? atoi(e) : 50; }();
+  // start offset of every SM's second CTA: TPAT_A5_STAGGER_PCT percent (default 0 = off: measured no effect) of one item's ~1300 (nb + 1) cycles
+  static const int stagger_pct = [] { const char* e = getenv("TPAT_A5_STAGGER_PCT"); return e ? atoi(e) : 0; }();
   p.stagger = p.n_items > grid ? 13 * (p.nb + 1) * stagger_pct : 0;
   static DeviceOnce once;
   if (once.first()) {

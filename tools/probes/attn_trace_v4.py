@@ -13,7 +13,8 @@ subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O
 import torch
 lib = ctypes.CDLL(out)
 B, N, H = 64, int(sys.argv[1]) if len(sys.argv) > 1 else 513, 12
-os.environ["TPAT_ATTN_V4"] = sys.argv[2] if len(sys.argv) > 2 else "1"
+os.environ["TPAT_ATTN_V4"] = "1"
+os.environ["TPAT_ATTN_V5"] = sys.argv[2] if len(sys.argv) > 2 else "0"     # 1: the persistent kernel (CTA 100, its first items)
 qkv = (torch.randn(B * N, 3 * H * 64, device="cuda") * 1.0).to(torch.bfloat16)
 o = torch.empty(B * N, H * 64, device="cuda", dtype=torch.bfloat16)
 partial = torch.empty(B, H * 8, N, device="cuda")
@@ -26,7 +27,8 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 256)()
 assert lib.tpat_debug_attn_trace(buf) == 0
 names = {1: "start", 2: "wait S", 3: "S ready", 4: "S in regs", 5: "exps+st issued", 6: "P in TMEM", 7: "arrived", 9: "loop done",
-         10: "O ready", 11: "end", 20: "MMA: Q ready", 21: "MMA: S(j+1) issued", 22: "MMA: P_j ready"}
+         10: "O ready", 11: "end / store issued", 12: "O in regs, o_empty arrived", 13: "staged + CTA barrier", 20: "MMA: Q ready",
+         21: "MMA: S(j+1) issued", 22: "MMA: P_j ready", 23: "MMA: o_empty ready"}
 t0_s, t0_m = buf[126], buf[254]
 ev = []
 for base, n, t0 in ((0, buf[127], t0_s), (128, buf[255], t0_m)):
