@@ -166,3 +166,24 @@ def test_attention_tc_online_softmax_rescale(N, extra):
     assert rel_err(out.float(), out2.float()) < 1e-2
     score, _ = ops.score_topk(partial, H * (N - extra), extra, 0)
     assert rel_err(score, ref_score(attn, extra, "colmean")) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(3100, 768, 256), (5001, 2304, 768), (4100, 800, 128), (32832, 3072, 768)])
+@pytest.mark.parametrize("with_bias", [True, False])
+def test_gemm_tma_store_epilogue_is_bit_identical(M, N, K, with_bias, monkeypatch):
+    """bf16 outputs of the bias / bias + GELU epilogues of the CTA-pair kernel leave through TMA stores (32 x 32 blocks staged
+    in 64B-swizzled shared memory).  Same bits as the per-lane-store epilogue (TPAT_GEMM_TMA_STORE=0), row tails clipped
+    by the tensor map (M % 32 != 0), column tiles that end inside a 256-column tile (N = 800), nothing written past M."""
+    from tpat import ops, _lib
+    a, w, bias = _mk(M, N, K, 13)
+    b = bias if with_bias else None
+    base = a.double() @ w.double().T + (bias.double() if with_bias else 0.0)
+    for epi, ref in ((_lib.EPI_BIAS, base), (_lib.EPI_BIAS_GELU, F.gelu(base))):
+        big = torch.full((M + 64, N), 7.0, device=dev(), dtype=torch.bfloat16)
+        monkeypatch.setenv("TPAT_GEMM_TMA_STORE", "1")
+        out = ops.gemm(a, w, b, torch.bfloat16, epi, _lib.IMPL_TC, out=big[:M])
+        assert rel_err(out.float(), ref) < 5e-3
+        assert (big[M:] == 7.0).all()
+        monkeypatch.setenv("TPAT_GEMM_TMA_STORE", "0")
+        old = ops.gemm(a, w, b, torch.bfloat16, epi, _lib.IMPL_TC)
+        assert torch.equal(out, old)

@@ -91,6 +91,35 @@ int encode_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t 
   return 0;
 }
 
+// 2-D bf16 map with a 32-column x 32-row box and 64-byte swizzle: the output blocks of the TMA-store epilogue (gemm_tc2.cu)
+int encode_tmap_2d_c32(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t pitch_bytes) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{gptr, rows, cols, pitch_bytes, 32, 32, 2, true};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  TPAT_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  TPAT_CHECK(aligned16(gptr) && pitch_bytes % 16 == 0, "TMA needs a 16-byte aligned base and row pitch (pitch=%llu)", (unsigned long long)pitch_bytes);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TPAT_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (32 x 32 bf16, 64B swizzle) failed with CUresult %d (rows=%llu cols=%llu pitch=%llu)", (int)r,
+             (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
 // 3-D map over a token-major activation [B][N][ld] (bf16): box = 64 columns x box_rows rows x 1 clip, 128B swizzle.
 // Rows >= N of a clip are out of bounds of dim 1 and are zero-filled (never the next clip's rows).
 int encode_tmap_3d_qkv(CUtensorMap* out, const void* gptr, int B, int N, int ld, int box_rows) {

@@ -8,6 +8,7 @@ namespace tpat {
 
 int encode_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                    uint32_t box_rows, uint32_t box_cols, bool swizzle128);
+int encode_tmap_2d_c32(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t pitch_bytes);
 
 constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_UMMA_K = 16;
 // EW epilogue warps (8 or 16): warp e -> TMEM lane quarter (e + 2) % 4 (hardware rule: warp id % 4), group e / 4;
@@ -43,6 +44,7 @@ struct TcGemmParams {
   float* cs_part;   // DGELU: partial column sums of the output, row (m0 / 32) of [.][N], written by every epilogue warp
   int red_add;      // 1 (TMA residual epilogue, C == R in place, no row scale): blocks of acc + bias are ADDED to C by TMA reduce
                     //    operations in L2 -- the residual never travels through the SM
+  int tma_c;        // 1 (bf16 C, bias / bias + GELU epilogues of the CTA-pair kernel): output blocks leave through TMA stores
   int w_kn;         // 1: W is [K, N] row-major; B tiles are 64 x 64 boxes ([64 k rows][128 B of n]), MN-major descriptors
   int debug_skip;   // timing experiments only (TPAT_GEMM_DEBUG_SKIP): 1 = no TMA after the first ring fill, 2 = skip W loads
 };
@@ -336,6 +338,63 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
             make_uint2(pack_bf16x2(v[it].x, v[it].y), pack_bf16x2(v[it].z, v[it].w));
       }
     }
+  }
+}
+
+// Epilogue of one accumulator for one epilogue warp, bf16 output through TMA stores (bias / bias + GELU; gemm_tc2.cu).
+// thread = row all the way: tcgen05.ld -> + bias (, GELU) -> 16 packed bf16 pairs -> this row's 64 bytes of a
+// [32 rows][64 B] block in shared memory (64B swizzle: 16-byte chunk position XOR (row / 2) % 4, conflict-free) -> ONE
+// cp.async.bulk.tensor store per 32 x 32 block, issued by lane 0.  The warp's 4 KB staging buffer holds two such blocks:
+// block k + 2 reuses the half of block k once its store has drained it (wait_group.read 1).  No transpose through shared
+// memory, no per-lane global stores.  Motivation: with the stores compiled out the generic epilogue runs the qkv GEMM 9 %
+// and fc1 + GELU 12 % faster (profiles/r02p_epilogue_probe_variants.txt).  Result (profiles/r02ac_gemm_tma_store_epilogue_ab.txt):
+// no gain -- qkv 3 % slower, fc1 equal -- so what the stores cost is their L2 / HBM write traffic, not instruction issue.
+// Same arithmetic, same bits; opt-in (TPAT_GEMM_TMA_STORE=1).
+//   kcount : running block counter of this warp (selects the staging half)
+template <int EPI, int EW, typename ReleaseFn>
+__device__ __forceinline__ void tc_epilogue_tile_tma(const TcGemmParams& p, const CUtensorMap* tmap_c, uint32_t taddr_row, int m0, int n0,
+                                                     int cg, uint8_t* stg, int lane, int& kcount, ReleaseFn release) {
+  constexpr int NCH = TcEpiPrefetch<EW>::NCH, CSTRIDE = TcEpiPrefetch<EW>::CSTRIDE;
+  bool released = false;
+#pragma unroll
+  for (int ci = 0; ci < NCH; ++ci) {
+    const int c = cg + CSTRIDE * ci;
+    const int n = n0 + c * 32;
+    const bool live = c < p.bn / 32 && n < p.N;      // warp-uniform
+    uint32_t r[32];
+    if (live) {
+      ptx::tmem_ld_32x32b_x32(taddr_row + c * 32, r);
+      ptx::tmem_ld_wait();
+    }
+    if (!released && (ci == NCH - 1 || c + CSTRIDE >= p.bn / 32 || n + CSTRIDE * 32 >= p.N)) {
+      released = true;                               // last TMEM read of this tile: hand the accumulator back
+      ptx::tc_fence_before();
+      __syncwarp();
+      release();
+    }
+    if (!live) continue;
+    uint8_t* buf = stg + (kcount & 1) * 2048;
+    if (lane == 0) ptx::tma_store_wait_read<1>();    // the store issued two blocks ago has read this half
+    __syncwarp();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 bb = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float x0 = __uint_as_float(r[4 * j]) + bb.x, x1 = __uint_as_float(r[4 * j + 1]) + bb.y;
+      float x2 = __uint_as_float(r[4 * j + 2]) + bb.z, x3 = __uint_as_float(r[4 * j + 3]) + bb.w;
+      if constexpr (EPI == TPAT_EPI_BIAS_GELU) { x0 = gelu_erf_fast(x0); x1 = gelu_erf_fast(x1); x2 = gelu_erf_fast(x2); x3 = gelu_erf_fast(x3); }
+      pk[2 * j] = pack_bf16x2(x0, x1); pk[2 * j + 1] = pack_bf16x2(x2, x3);
+    }
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4)
+      *reinterpret_cast<uint4*>(buf + lane * 64 + ((c4 ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (m0 < p.M) ptx::tma_store_2d(tmap_c, buf, n, m0);     // rows >= M are clipped by the tensor map
+      ptx::tma_store_commit();
+    }
+    ++kcount;
   }
 }
 
