@@ -40,5 +40,9 @@ with torch.no_grad():
         ts.append(e0.elapsed_time(e1) / steps)
         torch.cuda._sleep(int(2e8))      # let the power state relax between bursts
         torch.cuda.synchronize()
+with torch.no_grad():
+    chk = m(xs[0]).float()
+import hashlib
+digest = hashlib.sha256(chk.cpu().numpy().tobytes()).hexdigest()[:12]
 med = sorted(ts)[len(ts) // 2]
-print(f"{label or 'default':40s} {variant} kr={kr}: {med:.4f} ms/step (min {min(ts):.4f}, max {max(ts):.4f})  {B * 1e3 / med:8.0f} clips/s", flush=True)
+print(f"{label or 'default':40s} {variant} kr={kr}: {med:.4f} ms/step (min {min(ts):.4f}, max {max(ts):.4f})  {B * 1e3 / med:8.0f} clips/s  logits sha {digest}", flush=True)
