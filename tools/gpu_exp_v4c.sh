@@ -1,3 +1,4 @@
+# A/B against variants/libtpat_base.so = the library built from the PREVIOUS commit (git archive HEAD token-pruning-audio-transformer_b200/csrc include | tar -x -C /tmp/base; tools/build_variant.sh variants/libtpat_base.so from there)
 # full GPU suite (v4 default, trimmed two-pass main pass) + smoke + v4 trace + two-pass A/B against the HEAD build
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/ -x -q -m gpu -s -k "test_other_vit_sizes" > gpurun_out/v4c_pytest_sizes.log 2>&1; echo "sizes rc=$?"; grep "logits err" gpurun_out/v4c_pytest_sizes.log

@@ -1,3 +1,4 @@
+# A/B against variants/libtpat_base.so = the library built from the PREVIOUS commit (git archive HEAD token-pruning-audio-transformer_b200/csrc include | tar -x -C /tmp/base; tools/build_variant.sh variants/libtpat_base.so from there)
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_13_attention_v4.py -x -q -m gpu > gpurun_out/v4d_pytest.log 2>&1; echo "v4 pytest rc=$?"; tail -3 gpurun_out/v4d_pytest.log
 for i in 1 2; do

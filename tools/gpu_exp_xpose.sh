@@ -1,3 +1,4 @@
+# A/B against variants/libtpat_base.so = the library built from the PREVIOUS commit (git archive HEAD token-pruning-audio-transformer_b200/csrc include | tar -x -C /tmp/base; tools/build_variant.sh variants/libtpat_base.so from there)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_10_tensorcore.py tests/test_gpu_20_forward.py tests/test_gpu_25_parity_protocol.py -x -q -m gpu > gpurun_out/xp_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/xp_pytest.log
 for i in 1 2; do
